@@ -1,0 +1,382 @@
+"""Synthetic mesh / DoF generators for the B200 GLS Navier-Stokes operator.
+
+The reference obtains cells, DoF numbering, constraints, geometry and the
+partition from deal.II (DoFHandler, AffineConstraints, MappingQ,
+parallel::distributed::Triangulation; performance.cc:29-42, main.cc:230-310).
+deal.II is not available to this build, so this module produces the same kind
+of *description* (the arrays the deal.II adapter would extract, SURVEY.md
+Appendix B) for structured, optionally deformed and optionally periodic blocks:
+
+  * hypercube()      -- performance.cc's unit hypercube, Cartesian cells
+  * cylinder_shell() -- an O-grid around a cylinder, extruded (curved cells)
+
+DoF numbering imitates DoFHandler::distribute_dofs on a Morton-ordered forest:
+cells are walked in (Morton) order and every node is numbered by the first
+cell that touches it; the dim+1 components of a node are consecutive
+(FESystem(FE_Q(p), dim+1) numbers all components of a vertex/line/quad/hex
+dof together).  A rank owns the nodes first touched by its contiguous cell
+range (= lowest touching rank, like deal.II).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+import numpy as np
+
+
+def gauss_lobatto_points(p: int) -> np.ndarray:
+    """Support points of FE_Q(p) on [0,1]."""
+    if p == 1:
+        return np.array([0.0, 1.0])
+    c = np.zeros(p + 1)
+    c[p] = 1.0
+    dc = np.polynomial.legendre.legder(c)
+    x = np.sort(np.real(np.polynomial.legendre.legroots(dc)))
+    ddc = np.polynomial.legendre.legder(dc)
+    for _ in range(3):
+        x = x - np.polynomial.legendre.legval(x, dc) / np.polynomial.legendre.legval(x, ddc)
+    x = np.concatenate([[-1.0], x, [1.0]])
+    x = 0.5 * (x - x[::-1])
+    return 0.5 * (x + 1.0)
+
+
+def _morton_key(coords: np.ndarray) -> np.ndarray:
+    """Interleave the bits of integer coordinates [n, dim] (x lowest)."""
+    dim = coords.shape[1]
+    key = np.zeros(coords.shape[0], dtype=np.uint64)
+    nbits = max(1, int(coords.max()).bit_length()) if coords.size else 1
+    for b in range(nbits):
+        for e in range(dim):
+            key |= ((coords[:, e].astype(np.uint64) >> np.uint64(b)) & np.uint64(1)) << np.uint64(b * dim + e)
+    return key
+
+
+@dataclass
+class RankPartition:
+    """What Utilities::MPI::Partitioner holds for one rank."""
+    rank: int
+    n_ranks: int
+    n_owned: int
+    n_ghost: int
+    owned_offset: int                 # first global index owned by this rank
+    ghost_global: np.ndarray          # global indices of the ghosts (sorted => grouped by owner)
+    ghost_owner: np.ndarray           # owner rank of each ghost
+    # per neighbour: (rank, recv_offset_in_ghost_block, recv_count)
+    recv: list = field(default_factory=list)
+    # per neighbour: (rank, owned-local indices this rank must send)
+    send: list = field(default_factory=list)
+
+
+@dataclass
+class Mesh:
+    dim: int
+    degree: int
+    n_cells: int
+    n_dofs: int                       # local vector length (owned + ghost)
+    n_owned: int
+    cell_dofs: np.ndarray             # uint32/int64 [n_cells, C*n^dim], comp-blocked lexicographic
+    geometry_type: int                # 0 Cartesian, 2 general
+    cell_points: np.ndarray           # [n_cells, (k+1)^dim, dim] mapping support points
+    mapping_degree: int
+    constraints: dict                 # {dof: [(master, weight), ...]} local indices
+    cell_h_min: np.ndarray
+    cell_measure: np.ndarray
+    cart_inv_jac: np.ndarray | None = None   # [n_cells, dim] diag of J^-1 (Cartesian)
+    cart_det: np.ndarray | None = None       # [n_cells]
+    partition: RankPartition | None = None
+    node_compact: bool = True         # comp c of a node at index0 + c
+    n_global_dofs: int = 0
+    cell_is_boundary: np.ndarray | None = None  # touches ghost dofs
+
+    @property
+    def C(self):
+        return self.dim + 1
+
+    @property
+    def n_loc(self):
+        return (self.degree + 1) ** self.dim
+
+
+def _vertex_geometry(verts: np.ndarray, dim: int):
+    """minimum_vertex_distance() and measure() from the 2^dim vertices."""
+    nv = verts.shape[1]
+    h = np.full(verts.shape[0], np.inf)
+    for a in range(nv):
+        for b in range(a + 1, nv):
+            h = np.minimum(h, np.sqrt(((verts[:, a] - verts[:, b]) ** 2).sum(axis=1)))
+    # measure of the multilinear cell: 2-point Gauss per direction is exact
+    g = np.array([0.5 - 0.5 / np.sqrt(3.0), 0.5 + 0.5 / np.sqrt(3.0)])
+    meas = np.zeros(verts.shape[0])
+    for qi in range(2 ** dim):
+        xi = [g[(qi >> e) & 1] for e in range(dim)]
+        J = np.zeros((verts.shape[0], dim, dim))
+        for v in range(2 ** dim):
+            for e in range(dim):
+                dphi = 1.0
+                for f in range(dim):
+                    bit = (v >> f) & 1
+                    if f == e:
+                        dphi *= 1.0 if bit else -1.0
+                    else:
+                        dphi *= xi[f] if bit else 1.0 - xi[f]
+                J[:, :, e] += verts[:, v, :] * dphi
+        meas += np.linalg.det(J) / 2 ** dim
+    return h, meas
+
+
+def structured_mesh(dim, shape, degree, *, deform=None, mapping_degree=1, periodic=None,
+                    order="morton", numbering="node", dirichlet=None,
+                    n_ranks=1, rank=0, extent=None, origin=None, index_dtype=np.uint32):
+    """Structured block of prod(shape) cells.
+
+    deform:    callable(points[..., dim]) -> points[..., dim]; None => Cartesian cells
+    periodic:  tuple of bools per direction (node identification, O-grid)
+    dirichlet: callable(ref_coords[n_nodes, dim], comp) -> bool mask of zero-constrained nodes
+    numbering: "node" (components of a node consecutive, deal.II-like) or
+               "component" (component-major blocks; exercises the general index path)
+    """
+    shape = tuple(int(s) for s in shape)
+    assert len(shape) == dim
+    periodic = tuple(periodic) if periodic is not None else (False,) * dim
+    extent = np.ones(dim) if extent is None else np.asarray(extent, dtype=np.float64)
+    origin = np.zeros(dim) if origin is None else np.asarray(origin, dtype=np.float64)
+    p = degree
+    n = p + 1
+    C = dim + 1
+    n_loc = n ** dim
+    ncell = int(np.prod(shape))
+
+    # ---- cell traversal order -------------------------------------------------
+    cc = np.stack(np.meshgrid(*[np.arange(s) for s in shape], indexing="ij"), axis=-1).reshape(-1, dim)
+    if order == "morton":
+        perm = np.argsort(_morton_key(cc), kind="stable")
+    else:  # lexicographic, x fastest
+        key = np.zeros(ncell, dtype=np.int64)
+        mul = 1
+        for e in range(dim):
+            key += cc[:, e] * mul
+            mul *= shape[e]
+        perm = np.argsort(key, kind="stable")
+    cc = cc[perm]
+
+    # ---- node grid ------------------------------------------------------------
+    npts = tuple(p * shape[e] + (0 if periodic[e] else 1) for e in range(dim))
+    nnode = int(np.prod(npts))
+    # local lexicographic offsets
+    loc = np.stack(np.meshgrid(*[np.arange(n)] * dim, indexing="ij"), axis=-1).reshape(-1, dim)
+    # make x fastest: meshgrid 'ij' makes the last axis fastest -> reverse columns
+    loc = loc[:, ::-1].copy()  # loc[l] = (i_x, i_y, i_z) with x fastest
+    cell_nodes = np.zeros((ncell, n_loc), dtype=np.int64)
+    mul = 1
+    for e in range(dim):
+        g = (p * cc[:, e][:, None] + loc[None, :, e]) % npts[e]
+        cell_nodes += g * mul
+        mul *= npts[e]
+
+    # ---- numbering: first-touching cell wins ----------------------------------
+    # local ordering inside a cell: vertices, lines, quads, hexes, then lexicographic
+    ent_dim = ((loc > 0) & (loc < p)).sum(axis=1)
+    sortpos = np.empty(n_loc, dtype=np.int64)
+    sortpos[np.lexsort((np.arange(n_loc), ent_dim))] = np.arange(n_loc)
+    colorder = np.argsort(sortpos)
+    flat_nodes = cell_nodes[:, colorder].reshape(-1)   # ascending key = position in this array
+    first_key = np.empty(nnode, dtype=np.int64)
+    # walk the keys in descending order: the smallest key of a node is written last and wins
+    first_key[flat_nodes[::-1]] = np.arange(flat_nodes.size - 1, -1, -1, dtype=np.int64)
+    node_rank = np.empty(nnode, dtype=np.int64)
+    node_rank[np.argsort(first_key, kind="stable")] = np.arange(nnode)
+    first_cell = first_key // n_loc
+
+    # ---- partition ------------------------------------------------------------
+    bounds = [(ncell * r) // n_ranks for r in range(n_ranks + 1)]
+    node_owner_of_rank = np.searchsorted(np.asarray(bounds[1:]), first_cell, side="right")
+    # owned node ranges in the global numbering are contiguous
+    owned_counts = np.bincount(node_owner_of_rank, minlength=n_ranks)
+    owned_off_nodes = np.concatenate([[0], np.cumsum(owned_counts)])
+
+    c0, c1 = bounds[rank], bounds[rank + 1]
+    my_cells = slice(c0, c1)
+    my_nodes_g = node_rank[cell_nodes[my_cells]]  # global node ranks [ncell_loc, n_loc]
+    ncell_loc = c1 - c0
+
+    if numbering == "node":
+        def gdof(noderank, c):
+            return noderank * C + c
+    else:
+        def gdof(noderank, c):
+            # component-major inside each owner's range keeps ownership contiguous
+            own = np.searchsorted(owned_off_nodes[1:], noderank, side="right")
+            base = owned_off_nodes[own]
+            cnt = owned_counts[own]
+            return base * C + c * cnt + (noderank - base)
+
+    cell_gdofs = np.concatenate([gdof(my_nodes_g, c) for c in range(C)], axis=1)  # comp-blocked
+
+    n_global_dofs = nnode * C
+    owned_lo = owned_off_nodes[rank] * C
+    owned_hi = owned_off_nodes[rank + 1] * C
+    n_owned = int(owned_hi - owned_lo)
+    uniq = np.unique(cell_gdofs)
+    ghosts = uniq[(uniq < owned_lo) | (uniq >= owned_hi)]
+    n_ghost = len(ghosts)
+    # local index map
+    is_owned = (cell_gdofs >= owned_lo) & (cell_gdofs < owned_hi)
+    local = np.where(is_owned, cell_gdofs - owned_lo, 0)
+    if n_ghost:
+        gpos = np.searchsorted(ghosts, cell_gdofs)
+        gpos = np.clip(gpos, 0, n_ghost - 1)
+        local = np.where(is_owned, local, n_owned + gpos)
+    n_local = n_owned + n_ghost
+
+    part = None
+    if n_ranks > 1:
+        ghost_owner = np.searchsorted(owned_off_nodes[1:] * C, ghosts, side="right")
+        part = RankPartition(rank=rank, n_ranks=n_ranks, n_owned=n_owned, n_ghost=n_ghost,
+                             owned_offset=int(owned_lo), ghost_global=ghosts, ghost_owner=ghost_owner)
+        for r in np.unique(ghost_owner):
+            sel = np.nonzero(ghost_owner == r)[0]
+            part.recv.append((int(r), int(sel[0]), int(len(sel))))
+        # what others need from me: recompute their ghost sets (cheap for test sizes; the
+        # deal.II Partitioner gets this from a consensus exchange)
+        for r in range(n_ranks):
+            if r == rank:
+                continue
+            oc = slice(bounds[r], bounds[r + 1])
+            on = node_rank[cell_nodes[oc]]
+            og = np.unique(np.concatenate([gdof(on, c) for c in range(C)], axis=1))
+            mine = og[(og >= owned_lo) & (og < owned_hi)]
+            if len(mine):
+                part.send.append((r, (mine - owned_lo).astype(np.int64)))
+
+    # ---- geometry -------------------------------------------------------------
+    hcell = extent / np.asarray(shape, dtype=np.float64)
+    k = mapping_degree if deform is not None else 1
+    mp = gauss_lobatto_points(k)
+    mloc = np.stack(np.meshgrid(*[np.arange(k + 1)] * dim, indexing="ij"), axis=-1).reshape(-1, dim)[:, ::-1]
+    ref = origin[None, None, :] + (cc[my_cells][:, None, :] + mp[mloc][None, :, :]) * hcell[None, None, :]
+    pts = deform(ref) if deform is not None else ref
+    verts_idx = [sum((k * ((v >> e) & 1)) * (k + 1) ** e for e in range(dim)) for v in range(2 ** dim)]
+    h_min, meas = _vertex_geometry(pts[:, verts_idx, :], dim)
+
+    mesh = Mesh(dim=dim, degree=p, n_cells=ncell_loc, n_dofs=n_local, n_owned=n_owned,
+                cell_dofs=local.astype(index_dtype), geometry_type=0 if deform is None else 2,
+                cell_points=pts, mapping_degree=k, constraints={}, cell_h_min=h_min,
+                cell_measure=meas, partition=part, node_compact=(numbering == "node"),
+                n_global_dofs=n_global_dofs)
+    if deform is None:
+        mesh.cart_inv_jac = np.broadcast_to(1.0 / hcell, (ncell_loc, dim)).copy()
+        mesh.cart_det = np.full(ncell_loc, float(np.prod(hcell)))
+    mesh.cell_is_boundary = (local >= n_owned).any(axis=1)
+
+    # ---- zero (Dirichlet-type) constraints -------------------------------------
+    if dirichlet is not None:
+        gp = gauss_lobatto_points(p)
+        nref = origin[None, None, :] + (cc[my_cells][:, None, :] + gp[loc][None, :, :]) * hcell[None, None, :]
+        for c in range(C):
+            mask = dirichlet(nref.reshape(-1, dim), c).reshape(ncell_loc, n_loc)
+            dofs = local[:, c * n_loc:(c + 1) * n_loc][mask]
+            for dof in np.unique(dofs):
+                mesh.constraints[int(dof)] = []
+    return mesh
+
+
+def hypercube(dim, n_per_dir, degree, **kw):
+    """performance.cc:29-31: GridGenerator::hyper_cube + uniform cells."""
+    shape = (n_per_dir,) * dim if np.isscalar(n_per_dir) else tuple(n_per_dir)
+    return structured_mesh(dim, shape, degree, **kw)
+
+
+def cylinder_shell(shape, degree, *, r_inner=0.05, r_outer=0.5, length=0.41,
+                   mapping_degree=None, no_slip=True, **kw):
+    """O-grid around a cylinder (r, theta periodic[, z]) -- curved cells, like the
+    blocks next to the cylinder in include/grid_cylinder.h:22-90,154-191."""
+    dim = len(shape)
+    mapping_degree = degree if mapping_degree is None else mapping_degree
+
+    def deform(x):
+        r = r_inner + (r_outer - r_inner) * x[..., 0] ** 1.5  # graded towards the wall
+        th = 2.0 * np.pi * x[..., 1]
+        out = np.empty_like(x)
+        out[..., 0] = r * np.cos(th)
+        out[..., 1] = r * np.sin(th)
+        if dim == 3:
+            out[..., 2] = length * x[..., 2]
+        return out
+
+    periodic = (False, True) + ((False,) if dim == 3 else ())
+
+    def dirichlet(ref, c):
+        if c == dim:
+            return np.zeros(len(ref), dtype=bool)
+        m = np.abs(ref[:, 0]) < 1e-12          # cylinder surface
+        m |= np.abs(ref[:, 0] - 1.0) < 1e-12   # outer wall
+        return m
+
+    return structured_mesh(dim, shape, degree, deform=deform, mapping_degree=mapping_degree,
+                           periodic=periodic, dirichlet=dirichlet if no_slip else None, **kw)
+
+
+def add_random_constraints(mesh: Mesh, n_weighted: int, n_zero: int, seed: int = 0,
+                           owned_only: bool = True):
+    """Attach synthetic affine constraints x_i = sum_j w_ij x_j (hanging-node-like rows
+    with 2-4 masters) and zero constraints, masters always unconstrained."""
+    rng = np.random.default_rng(seed)
+    hi = mesh.n_owned if owned_only else mesh.n_dofs
+    cand = rng.permutation(hi)
+    already = set(mesh.constraints.keys())
+    cand = [int(c) for c in cand if int(c) not in already]
+    chosen = cand[: n_weighted + n_zero]
+    cset = set(chosen) | already
+    free = np.array([i for i in range(hi) if i not in cset], dtype=np.int64)
+    for t, dof in enumerate(chosen):
+        if t < n_weighted:
+            m = rng.choice(free, size=int(rng.integers(2, 5)), replace=False)
+            w = rng.uniform(-0.5, 1.0, size=len(m))
+            mesh.constraints[dof] = [(int(a), float(b)) for a, b in zip(m, w)]
+        else:
+            mesh.constraints[dof] = []
+    return mesh
+
+
+def general_geometry(mesh: Mesh, n_q_1d: int | None = None):
+    """J^{-T} and JxW at the quadrature points from the mapping support points
+    (what MatrixFree's MappingInfo stores for 'general' cells).
+
+    Returns inv_jac[k, q, e, j] = (J^-1)_{e j} and jxw[k, q]."""
+    dim, kdeg = mesh.dim, mesh.mapping_degree
+    nq = (mesh.degree + 1) if n_q_1d is None else n_q_1d
+    xg, wg = np.polynomial.legendre.leggauss(nq)
+    xg = 0.5 * (xg + 1.0)
+    wg = 0.5 * wg
+    nodes = gauss_lobatto_points(kdeg)
+
+    def lag(x):
+        m = len(nodes)
+        V = np.ones((len(x), m))
+        D = np.zeros((len(x), m))
+        for i in range(m):
+            for a in range(m):
+                if a != i:
+                    V[:, i] *= (x - nodes[a]) / (nodes[i] - nodes[a])
+            for l in range(m):
+                if l == i:
+                    continue
+                t = np.ones(len(x)) / (nodes[i] - nodes[l])
+                for a in range(m):
+                    if a != i and a != l:
+                        t *= (x - nodes[a]) / (nodes[i] - nodes[a])
+                D[:, i] += t
+        return V, D
+
+    V, D = lag(xg)
+    J = np.zeros((mesh.n_cells, nq ** dim, dim, dim))
+    for e in range(dim):
+        mats = [V] * dim
+        mats[e] = D
+        T = mats[0]
+        for mtx in mats[1:]:
+            T = np.kron(mtx, T)
+        J[:, :, :, e] = np.einsum("qm,kmi->kqi", T, mesh.cell_points)
+    w = wg
+    for _ in range(dim - 1):
+        w = np.kron(wg, w)
+    return np.linalg.inv(J), np.linalg.det(J) * w[None, :]
