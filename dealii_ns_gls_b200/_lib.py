@@ -1,0 +1,94 @@
+"""ctypes binding of include/glsb200.h.  Fails loudly when libglsb200.so is missing:
+there is no CPU or PyTorch fallback for the operator."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libglsb200.so")
+
+GLSB_ABI_VERSION = 1
+GLSB_F64, GLSB_F32 = 0, 1
+GLSB_GEOM_CARTESIAN, GLSB_GEOM_GENERAL = 0, 2
+GLSB_CELLS_ALL, GLSB_CELLS_INTERIOR, GLSB_CELLS_BOUNDARY = 0, 1, 2
+GLSB_CONSTRAINED_BIT = 0x80000000
+
+
+class GlsbDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("device", C.c_int32),
+        ("dim", C.c_int32), ("degree", C.c_int32), ("number_type", C.c_int32),
+        ("increment_form", C.c_int32), ("consider_time_derivative", C.c_int32),
+        ("cell_wise_stabilization", C.c_int32), ("time_order", C.c_int32),
+        ("nu", C.c_double), ("c1", C.c_double), ("c2", C.c_double), ("theta", C.c_double),
+        ("n_cells", C.c_uint64), ("n_owned", C.c_uint64), ("n_ghost", C.c_uint64),
+        ("dof_indices", C.c_void_p),
+        ("n_constraint_rows", C.c_uint32),
+        ("row_dof", C.c_void_p), ("row_ptr", C.c_void_p), ("entry_col", C.c_void_p), ("entry_val", C.c_void_p),
+        ("n_constrained_indices", C.c_uint32), ("constrained_indices", C.c_void_p),
+        ("geometry_type", C.c_int32), ("inv_jac", C.c_void_p), ("jxw", C.c_void_p),
+        ("cell_h_min", C.c_void_p), ("cell_measure", C.c_void_p),
+        ("n_export", C.c_uint64), ("export_indices", C.c_void_p),
+    ]
+
+
+# every symbol include/glsb200.h declares: name -> (restype, argtypes)
+_P, _D, _I, _U64 = C.c_void_p, C.c_double, C.c_int, C.c_uint64
+SYMBOLS = {
+    "glsb_create": (_I, [C.POINTER(GlsbDesc), C.POINTER(_P)]),
+    "glsb_destroy": (None, [_P]),
+    "glsb_last_error": (C.c_char_p, [_P]),
+    "glsb_invalidate_system": (_I, [_P]),
+    "glsb_vmult": (_I, [_P, _P, _P, _D, _P]),
+    "glsb_vmult_begin": (_I, [_P, _P, _P]),
+    "glsb_vmult_cells": (_I, [_P, _P, _P, _D, _I, _P]),
+    "glsb_vmult_finish": (_I, [_P, _P, _P, _P]),
+    "glsb_evaluate_residual": (_I, [_P, _P, _P, _D, _P]),
+    "glsb_evaluate_residual_cells": (_I, [_P, _P, _P, _D, _I, _P]),
+    "glsb_set_linearization_point": (_I, [_P, _P, _D, _P]),
+    "glsb_set_previous_solution": (_I, [_P, C.POINTER(_P), C.POINTER(_D), _I, _P]),
+    "glsb_compute_inverse_diagonal": (_I, [_P, _P, _D, _P]),
+    "glsb_diagonal_cells": (_I, [_P, _P, _D, _P]),
+    "glsb_diagonal_finish": (_I, [_P, _P, _P]),
+    "glsb_get_max_u": (_I, [_P, _P, C.POINTER(_D), _P]),
+    "glsb_pack_export": (_I, [_P, _P, _P, _P]),
+    "glsb_unpack_add": (_I, [_P, _P, _P, _P]),
+    "glsb_n_cells": (_U64, [_P]),
+    "glsb_n_local": (_U64, [_P]),
+    "glsb_n_interior_cells": (_U64, [_P]),
+    "glsb_get_table": (_I, [_P, C.c_char_p, _P, _U64, _P]),
+    "glsb_launch_count": (_U64, [_P]),
+    "glsb_vmult_variant": (C.c_char_p, [_P]),
+    "glsb_set_variant": (_I, [_P, _I]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libglsb200.so and bind every declared symbol; raise if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C dealii_ns_gls_b200/csrc`. The operator has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class GlsbError(RuntimeError):
+    pass
+
+
+def check(lib, op, rc, what):
+    if rc != 0:
+        msg = lib.glsb_last_error(op)
+        raise GlsbError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")

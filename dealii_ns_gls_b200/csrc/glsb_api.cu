@@ -1,0 +1,991 @@
+// C ABI of libglsb200.so (include/glsb200.h): operator state, setup-time layout
+// transformations and dispatch to the kernels.  No CPU fallback anywhere.
+#include "../../include/glsb200.h"
+#include "glsb_common.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace glsb;
+
+namespace
+{
+std::string g_create_error;
+
+struct DevBuf
+{
+  void  *p     = nullptr;
+  size_t bytes = 0;
+  DevBuf()     = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p     = nullptr;
+    bytes = 0;
+  }
+  bool alloc(size_t b)
+  {
+    release();
+    if (b == 0)
+      return true;
+    if (cudaMalloc(&p, b) != cudaSuccess)
+      {
+        p = nullptr;
+        return false;
+      }
+    bytes = b;
+    return true;
+  }
+  template <typename U>
+  U *as() const
+  {
+    return static_cast<U *>(p);
+  }
+};
+
+__global__ void k_transpose_idx(const uint32_t *__restrict__ raw, const uint32_t *__restrict__ perm,
+                                uint32_t *__restrict__ out, uint32_t n_cells, uint32_t ndof, uint64_t ncp)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)ndof * ncp)
+    return;
+  const uint32_t i = t % ncp, d = t / ncp;
+  const uint32_t c = i < n_cells ? i : n_cells - 1; // padding repeats the last cell
+  out[t]           = raw[(uint64_t)perm[c] * ndof + d];
+}
+
+// general geometry [cell][q][e][j] (double) -> [e*dim+j][q][ncp] (T); jxw [cell][q] -> [q][ncp]
+template <typename T>
+__global__ void k_transpose_geom(const double *__restrict__ raw, const uint32_t *__restrict__ perm,
+                                 T *__restrict__ out, uint32_t n_cells, uint32_t per_cell_q, uint32_t inner,
+                                 uint64_t ncp)
+{
+  // raw[(cell*nq + q)*inner + f] -> out[(f*nq + q)*ncp + i]
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)inner * per_cell_q * ncp)
+    return;
+  const uint32_t i = t % ncp;
+  const uint64_t r = t / ncp;
+  const uint32_t q = r % per_cell_q, f = r / per_cell_q;
+  const uint32_t c = i < n_cells ? i : n_cells - 1;
+  out[t]           = (T)raw[((uint64_t)perm[c] * per_cell_q + q) * inner + f];
+}
+
+template <typename T>
+__global__ void k_copy_indexed(T *__restrict__ dst, const T *__restrict__ src, const uint32_t *__restrict__ idx,
+                               uint32_t n)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n)
+    dst[idx[t]] = src[idx[t]];
+}
+
+template <typename T>
+__global__ void k_pack(T *__restrict__ buf, const T *__restrict__ vec, const uint32_t *__restrict__ idx, uint64_t n)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n)
+    buf[t] = vec[idx[t]];
+}
+
+template <typename T>
+__global__ void k_unpack_add(T *__restrict__ vec, const T *__restrict__ buf, const uint32_t *__restrict__ idx,
+                             uint64_t n)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n)
+    atomicAdd(vec + idx[t], buf[t]);
+}
+
+// diag finish: constrained rows -> 1, then x -> |x| > 1e-10 ? 1/x : 1 (operator_ns.cc:220-224)
+template <typename T>
+__global__ void k_set_indexed(T *__restrict__ v, const uint32_t *__restrict__ idx, uint32_t n, T val)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n)
+    v[idx[t]] = val;
+}
+template <typename T>
+__global__ void k_invert_guarded(T *__restrict__ v, uint64_t n)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n)
+    {
+      const T x = v[t];
+      v[t]      = (fabs(x) > T(1.0e-10)) ? (T(1.0) / x) : T(1.0);
+    }
+}
+
+// table [f][q][ncp] (internal cell order) -> out [f][cell][q] (caller's order)
+template <typename T>
+__global__ void k_export_table(const T *__restrict__ tab, const uint32_t *__restrict__ perm, T *__restrict__ out,
+                               uint32_t n_cells, uint32_t nq, uint32_t nf, uint64_t ncp)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)nf * nq * n_cells)
+    return;
+  const uint32_t i = t % n_cells;
+  const uint64_t r = t / n_cells;
+  const uint32_t q = r % nq, f = r / nq;
+  out[((uint64_t)f * n_cells + perm[i]) * nq + q] = tab[((uint64_t)f * nq + q) * ncp + i];
+}
+} // namespace
+
+struct glsb_op
+{
+  int      dim = 0, degree = 0, n = 0, number_type = 0, C = 0, n_loc = 0, nq = 0;
+  int      increment_form = 0, ctd = 0, cell_wise = 0, time_order = 0, geom = 0, device = 0;
+  double   nu = 0, c1 = 0, c2 = 0, theta = 1;
+  uint64_t n_cells = 0, n_owned = 0, n_ghost = 0, ncp = 0;
+  uint32_t n_interior = 0;
+  uint32_t n_rows = 0, n_constrained = 0;
+  uint64_t n_export = 0;
+  size_t   tsize = 8;
+
+  DevBuf perm, idx, row_dof, row_ptr, ecol, eval, cidx, inv_jac, jxw, h_min, measure, export_idx;
+  DevBuf U, H, P, O, Gold, gold_p, R1, d1c, d2c, d1q, d2q, max_bits;
+  DevBuf diag_skip, dc_cell, dc_col_ptr, dc_col_dof, dc_ent_ptr, dc_ent_loc, dc_ent_val;
+  uint32_t dc_n_list = 0;
+
+  ShapeHost shape;
+  bool      lin_valid = false, prev_valid = false;
+  double    lin_dt = 0;
+  int       variant_forced = 0;
+  uint64_t  launches = 0;
+  std::string err;
+  std::string variant = "generic";
+};
+
+namespace
+{
+int fail(glsb_op *op, const std::string &msg)
+{
+  if (op)
+    op->err = msg;
+  else
+    g_create_error = msg;
+  return 1;
+}
+
+int cuda_fail(glsb_op *op, const char *what)
+{
+  cudaError_t e = cudaGetLastError();
+  char        b[512];
+  snprintf(b, sizeof b, "%s: %s", what, cudaGetErrorString(e));
+  return fail(op, b);
+}
+
+template <typename T>
+KParams<T> base_params(const glsb_op *op)
+{
+  KParams<T> p;
+  memset(&p, 0, sizeof p);
+  p.ncp        = op->ncp;
+  p.idx        = op->idx.as<uint32_t>();
+  p.row_dof    = op->row_dof.as<uint32_t>();
+  p.row_ptr    = op->row_ptr.as<uint32_t>();
+  p.ecol       = op->ecol.as<uint32_t>();
+  p.eval       = op->eval.as<T>();
+  p.geom       = op->geom;
+  p.inv_jac    = op->inv_jac.as<T>();
+  p.jxw        = op->jxw.as<T>();
+  p.h_min      = op->h_min.as<double>();
+  p.measure    = op->measure.as<double>();
+  p.U          = op->U.as<T>();
+  p.H          = op->H.as<T>();
+  p.P          = op->P.as<T>();
+  p.O          = op->O.as<T>();
+  p.Gold       = op->Gold.as<T>();
+  p.gold_p     = op->gold_p.as<T>();
+  p.R1         = op->R1.as<T>();
+  p.d1c        = op->d1c.as<T>();
+  p.d2c        = op->d2c.as<T>();
+  p.d1q        = op->d1q.as<T>();
+  p.d2q        = op->d2q.as<T>();
+  p.nu         = (T)op->nu;
+  p.theta      = (T)op->theta;
+  p.c1         = op->c1;
+  p.c2         = op->c2;
+  p.nu_d       = op->nu;
+  p.degree     = op->degree;
+  p.ctd        = op->ctd;
+  p.cell_wise  = op->cell_wise;
+  p.has_o      = op->prev_valid && op->O.p != nullptr;
+  p.theta_ne_1 = (op->theta != 1.0);
+  p.max_bits   = op->max_bits.as<unsigned long long>();
+  return p;
+}
+
+void cell_range(const glsb_op *op, int which, uint32_t &b, uint32_t &e)
+{
+  b = 0;
+  e = (uint32_t)op->n_cells;
+  if (which == GLSB_CELLS_INTERIOR)
+    e = op->n_interior;
+  else if (which == GLSB_CELLS_BOUNDARY)
+    b = op->n_interior;
+}
+
+#define GLSB_DISPATCH(op, CALL)                                   \
+  do                                                              \
+    {                                                             \
+      if ((op)->number_type == GLSB_F64)                          \
+        {                                                         \
+          if ((op)->dim == 2)                                     \
+            rc = CALL(2, double);                                 \
+          else                                                    \
+            rc = CALL(3, double);                                 \
+        }                                                         \
+      else                                                        \
+        {                                                         \
+          if ((op)->dim == 2)                                     \
+            rc = CALL(2, float);                                  \
+          else                                                    \
+            rc = CALL(3, float);                                  \
+        }                                                         \
+    }                                                             \
+  while (0)
+
+template <int dim, typename T>
+int do_cells(glsb_op *op, void *dst, const void *src, double weight, int which, int branch, cudaStream_t s)
+{
+  KParams<T> p = base_params<T>(op);
+  cell_range(op, which, p.cell_begin, p.cell_end);
+  p.src           = static_cast<const T *>(src);
+  p.dst           = static_cast<T *>(dst);
+  p.weight        = (T)weight;
+  p.sign_negative = (branch == BR_RESIDUAL);
+  if (p.cell_end <= p.cell_begin)
+    return 0;
+  op->launches++;
+  return Kernels<dim, T>::vmult(op->n, branch, p, op->shape, s);
+}
+
+template <int dim, typename T>
+int do_lin(glsb_op *op, const void *vec, double dt, cudaStream_t s)
+{
+  KParams<T> p = base_params<T>(op);
+  cell_range(op, GLSB_CELLS_ALL, p.cell_begin, p.cell_end);
+  p.src  = static_cast<const T *>(vec);
+  p.stau = (dt == 0.0) ? 0.0 : 1.0 / dt;
+  p.R1   = nullptr;
+  op->launches++;
+  return Kernels<dim, T>::linearization(op->n, p, op->shape, s);
+}
+
+template <int dim, typename T>
+int do_prev(glsb_op *op, const void *const *history, const double *weights, int order, cudaStream_t s)
+{
+  KParams<T> p = base_params<T>(op);
+  cell_range(op, GLSB_CELLS_ALL, p.cell_begin, p.cell_end);
+  p.hist_n = order;
+  for (int i = 0; i < order; ++i)
+    {
+      p.hist[i]   = static_cast<const T *>(history[i + 1]);
+      p.hist_w[i] = (T)weights[i + 1];
+    }
+  op->launches++;
+  int rc = Kernels<dim, T>::previous(op->n, 0, p, op->shape, s);
+  if (rc == 0 && op->theta != 1.0)
+    {
+      p.hist_n    = 1;
+      p.hist[0]   = static_cast<const T *>(history[1]);
+      p.hist_w[0] = (T)1;
+      op->launches++;
+      rc = Kernels<dim, T>::previous(op->n, 1, p, op->shape, s);
+    }
+  return rc;
+}
+
+template <int dim, typename T>
+int do_diag(glsb_op *op, void *diag, double weight, cudaStream_t s)
+{
+  KParams<T> p = base_params<T>(op);
+  cell_range(op, GLSB_CELLS_ALL, p.cell_begin, p.cell_end);
+  p.dst    = static_cast<T *>(diag);
+  p.weight = (T)weight;
+  DiagColumns dc;
+  dc.cell    = op->dc_cell.as<uint32_t>();
+  dc.col_ptr = op->dc_col_ptr.as<uint32_t>();
+  dc.col_dof = op->dc_col_dof.as<uint32_t>();
+  dc.ent_ptr = op->dc_ent_ptr.as<uint32_t>();
+  dc.ent_loc = op->dc_ent_loc.as<uint32_t>();
+  dc.ent_val = op->dc_ent_val.as<double>();
+  dc.n_list  = op->dc_n_list;
+  op->launches += 1 + (dc.n_list > 0);
+  return Kernels<dim, T>::diagonal(op->n, op->increment_form ? BR_NEWTON : BR_FIXED_POINT, p, op->shape,
+                                   op->diag_skip.as<uint8_t>(), dc, s);
+}
+
+template <int dim, typename T>
+int do_maxu(glsb_op *op, const void *vec, cudaStream_t s)
+{
+  KParams<T> p = base_params<T>(op);
+  cell_range(op, GLSB_CELLS_ALL, p.cell_begin, p.cell_end);
+  p.src = static_cast<const T *>(vec);
+  op->launches++;
+  return Kernels<dim, T>::max_u(op->n, p, op->shape, s);
+}
+
+bool upload(DevBuf &b, const void *host, size_t bytes)
+{
+  if (!b.alloc(bytes))
+    return false;
+  if (bytes)
+    return cudaMemcpy(b.p, host, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+  return true;
+}
+
+template <typename T>
+bool upload_converted(DevBuf &b, const double *host, size_t count)
+{
+  std::vector<T> tmp(count);
+  for (size_t i = 0; i < count; ++i)
+    tmp[i] = (T)host[i];
+  return upload(b, tmp.data(), count * sizeof(T));
+}
+
+bool ensure_tables(glsb_op *op, bool lin, bool prev)
+{
+  const size_t per_field = (size_t)op->nq * op->ncp * op->tsize;
+  const int    d         = op->dim;
+  if (lin)
+    {
+      if (!op->U.p && !(op->U.alloc(d * per_field) && op->H.alloc(d * d * per_field) &&
+                        op->P.alloc(d * per_field) && op->d1c.alloc(op->ncp * op->tsize) &&
+                        op->d2c.alloc(op->ncp * op->tsize) && op->d1q.alloc(per_field) &&
+                        op->d2q.alloc(per_field)))
+        return false;
+    }
+  if (prev)
+    {
+      if (!op->O.p && !op->O.alloc(d * per_field))
+        return false;
+      if (op->theta != 1.0 && !op->Gold.p &&
+          !(op->Gold.alloc(d * d * per_field) && op->gold_p.alloc(d * per_field)))
+        return false;
+    }
+  return true;
+}
+} // namespace
+
+extern "C" {
+
+int glsb_create(const glsb_desc *d, glsb_op **out)
+{
+  if (!d || !out)
+    return fail(nullptr, "glsb_create: null argument");
+  *out = nullptr;
+  if (d->abi_version != GLSB_ABI_VERSION)
+    return fail(nullptr, "glsb_create: ABI version mismatch");
+  if (d->dim != 2 && d->dim != 3)
+    return fail(nullptr, "glsb_create: dim must be 2 or 3");
+  if (d->degree < 1 || d->degree > 4)
+    return fail(nullptr, "glsb_create: degree must be 1..4");
+  if (d->number_type != GLSB_F64 && d->number_type != GLSB_F32)
+    return fail(nullptr, "glsb_create: unknown number_type");
+  if (d->geometry_type != GLSB_GEOM_CARTESIAN && d->geometry_type != GLSB_GEOM_GENERAL)
+    return fail(nullptr, "glsb_create: unknown geometry_type");
+  if (d->n_cells == 0 || d->n_cells > 0x7fffffffull)
+    return fail(nullptr, "glsb_create: n_cells out of range");
+  if (d->n_owned + d->n_ghost >= 0x80000000ull)
+    return fail(nullptr, "glsb_create: local vector too long for 31-bit indices");
+  if (d->consider_time_derivative && d->time_order > 0 && d->theta != 1.0)
+    return fail(nullptr, "glsb_create: consider_time_derivative requires theta == 1 (operator_ns.cc:126-129)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, "glsb_create: no CUDA device available (there is no CPU fallback)");
+  if (d->device < 0 || d->device >= ndev)
+    return fail(nullptr, "glsb_create: bad device ordinal");
+  if (cudaSetDevice(d->device) != cudaSuccess)
+    return cuda_fail(nullptr, "cudaSetDevice");
+
+  glsb_op *op          = new glsb_op;
+  op->dim              = d->dim;
+  op->degree           = d->degree;
+  op->n                = d->degree + 1;
+  op->C                = d->dim + 1;
+  op->n_loc            = (d->dim == 2) ? op->n * op->n : op->n * op->n * op->n;
+  op->nq               = op->n_loc;
+  op->number_type      = d->number_type;
+  op->tsize            = d->number_type == GLSB_F64 ? 8 : 4;
+  op->increment_form   = d->increment_form;
+  op->time_order       = d->time_order;
+  op->ctd              = d->consider_time_derivative && d->time_order > 0; // operator_ns.cc:97-98
+  op->cell_wise        = d->cell_wise_stabilization;
+  op->nu               = d->nu;
+  op->c1               = d->c1;
+  op->c2               = d->c2;
+  op->theta            = d->theta;
+  op->geom             = d->geometry_type;
+  op->device           = d->device;
+  op->n_cells          = d->n_cells;
+  op->n_owned          = d->n_owned;
+  op->n_ghost          = d->n_ghost;
+  op->ncp              = (d->n_cells + 127) / 128 * 128;
+  op->n_rows           = d->n_constraint_rows;
+  op->n_constrained    = d->n_constrained_indices;
+  op->n_export         = d->n_export;
+  compute_shape_host(d->degree, op->shape);
+
+  const uint32_t ndof    = op->C * op->n_loc;
+  const uint64_t n_local = d->n_owned + d->n_ghost;
+  const uint32_t nc      = (uint32_t)d->n_cells;
+  bool           ok      = true;
+  std::string    why;
+
+  // ---- validate indices; classify cells: interior first, then cells touching ghosts ----
+  std::vector<uint8_t> row_ghost(d->n_constraint_rows, 0), row_weighted(d->n_constraint_rows, 0);
+  for (uint32_t r = 0; r < d->n_constraint_rows && ok; ++r)
+    {
+      if (d->row_dof[r] >= n_local)
+        {
+          ok  = false;
+          why = "constraint row_dof out of range";
+        }
+      for (uint32_t e = d->row_ptr[r]; e < d->row_ptr[r + 1]; ++e)
+        {
+          if (d->entry_col[e] >= n_local)
+            {
+              ok  = false;
+              why = "constraint entry_col out of range";
+              break;
+            }
+          if (d->entry_col[e] >= d->n_owned)
+            row_ghost[r] = 1;
+          row_weighted[r] = 1;
+        }
+      if (d->row_dof[r] >= d->n_owned)
+        row_ghost[r] = 1;
+    }
+  std::vector<uint8_t> is_boundary(nc, 0), has_weighted(nc, 0);
+  for (uint32_t k = 0; k < nc && ok; ++k)
+    {
+      const uint32_t *row = d->dof_indices + (uint64_t)k * ndof;
+      for (uint32_t j = 0; j < ndof; ++j)
+        {
+          const uint32_t iv = row[j];
+          if (iv & GLSB_CONSTRAINED_BIT)
+            {
+              const uint32_t r = iv & ~GLSB_CONSTRAINED_BIT;
+              if (r >= d->n_constraint_rows)
+                {
+                  ok  = false;
+                  why = "dof_indices refers to a constraint row that does not exist";
+                  break;
+                }
+              is_boundary[k] |= row_ghost[r];
+              has_weighted[k] |= row_weighted[r];
+            }
+          else
+            {
+              if (iv >= n_local)
+                {
+                  ok  = false;
+                  why = "dof_indices out of range";
+                  break;
+                }
+              if (iv >= d->n_owned)
+                is_boundary[k] = 1;
+            }
+        }
+    }
+  if (!ok)
+    {
+      delete op;
+      return fail(nullptr, "glsb_create: " + why);
+    }
+  std::vector<uint32_t> perm;
+  perm.reserve(nc);
+  for (uint32_t k = 0; k < nc; ++k)
+    if (!is_boundary[k])
+      perm.push_back(k);
+  op->n_interior = (uint32_t)perm.size();
+  for (uint32_t k = 0; k < nc; ++k)
+    if (is_boundary[k])
+      perm.push_back(k);
+
+  ok = ok && upload(op->perm, perm.data(), perm.size() * 4);
+
+  // ---- dof indices: [cell][dof] -> [dof][ncp] in internal order -------------------------
+  {
+    DevBuf raw;
+    ok = ok && upload(raw, d->dof_indices, (size_t)nc * ndof * 4);
+    ok = ok && op->idx.alloc((size_t)ndof * op->ncp * 4);
+    if (ok)
+      {
+        const uint64_t tot = (uint64_t)ndof * op->ncp;
+        k_transpose_idx<<<(unsigned)((tot + 255) / 256), 256>>>(raw.as<uint32_t>(), op->perm.as<uint32_t>(),
+                                                                 op->idx.as<uint32_t>(), nc, ndof, op->ncp);
+        ok = cudaDeviceSynchronize() == cudaSuccess;
+      }
+  }
+
+  // ---- constraints ----------------------------------------------------------------------
+  {
+    const uint32_t              nr = d->n_constraint_rows;
+    static const uint32_t       zero2[2] = {0, 0};
+    const uint32_t              ne = nr ? d->row_ptr[nr] : 0;
+    ok = ok && upload(op->row_dof, nr ? d->row_dof : zero2, (nr ? nr : 1) * 4);
+    ok = ok && upload(op->row_ptr, nr ? d->row_ptr : zero2, (size_t)(nr + 1) * 4);
+    ok = ok && upload(op->ecol, ne ? d->entry_col : zero2, (ne ? ne : 1) * 4);
+    const double zd = 0;
+    if (op->number_type == GLSB_F64)
+      ok = ok && upload(op->eval, ne ? d->entry_val : &zd, (ne ? ne : 1) * 8);
+    else
+      ok = ok && upload_converted<float>(op->eval, ne ? d->entry_val : &zd, ne ? ne : 1);
+    ok = ok && upload(op->cidx, d->n_constrained_indices ? d->constrained_indices : zero2,
+                      (size_t)(d->n_constrained_indices ? d->n_constrained_indices : 1) * 4);
+    ok = ok && upload(op->export_idx, d->n_export ? d->export_indices : zero2,
+                      (size_t)(d->n_export ? d->n_export : 1) * 4);
+  }
+
+  // ---- columns of C_cell for compute_diagonal on cells with weighted rows ---------------
+  {
+    std::vector<uint8_t>  skip(op->ncp, 0);
+    std::vector<uint32_t> l_cell, col_ptr(1, 0), col_dof, ent_ptr(1, 0), ent_loc;
+    std::vector<double>   ent_val;
+    for (uint32_t i = 0; i < nc; ++i)
+      {
+        const uint32_t k = perm[i];
+        if (!has_weighted[k])
+          continue;
+        skip[i] = 1;
+        l_cell.push_back(i);
+        // gather (g, local, weight) triples, then group by g
+        std::vector<std::pair<uint32_t, std::pair<uint32_t, double>>> tr;
+        const uint32_t *row = d->dof_indices + (uint64_t)k * ndof;
+        for (uint32_t j = 0; j < ndof; ++j)
+          {
+            const uint32_t iv = row[j];
+            if (iv & GLSB_CONSTRAINED_BIT)
+              {
+                const uint32_t r = iv & ~GLSB_CONSTRAINED_BIT;
+                for (uint32_t e = d->row_ptr[r]; e < d->row_ptr[r + 1]; ++e)
+                  tr.push_back({d->entry_col[e], {j, d->entry_val[e]}});
+              }
+            else
+              tr.push_back({iv, {j, 1.0}});
+          }
+        std::stable_sort(tr.begin(), tr.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+        for (size_t t = 0; t < tr.size(); ++t)
+          {
+            if (t == 0 || tr[t].first != tr[t - 1].first)
+              {
+                if (t)
+                  ent_ptr.push_back((uint32_t)ent_loc.size());
+                col_dof.push_back(tr[t].first);
+              }
+            ent_loc.push_back(tr[t].second.first);
+            ent_val.push_back(tr[t].second.second);
+          }
+        if (!tr.empty())
+          ent_ptr.push_back((uint32_t)ent_loc.size());
+        col_ptr.push_back((uint32_t)col_dof.size());
+      }
+    op->dc_n_list = (uint32_t)l_cell.size();
+    ok            = ok && upload(op->diag_skip, skip.data(), skip.size());
+    if (op->dc_n_list)
+      {
+        ok = ok && upload(op->dc_cell, l_cell.data(), l_cell.size() * 4);
+        ok = ok && upload(op->dc_col_ptr, col_ptr.data(), col_ptr.size() * 4);
+        ok = ok && upload(op->dc_col_dof, col_dof.data(), col_dof.size() * 4);
+        ok = ok && upload(op->dc_ent_ptr, ent_ptr.data(), ent_ptr.size() * 4);
+        ok = ok && upload(op->dc_ent_loc, ent_loc.data(), ent_loc.size() * 4);
+        ok = ok && upload(op->dc_ent_val, ent_val.data(), ent_val.size() * 8);
+      }
+  }
+
+  // ---- geometry -------------------------------------------------------------------------
+  {
+    const int dm = op->dim;
+    // per-cell scalars in internal order, padded
+    std::vector<double> hm(op->ncp), ms(op->ncp);
+    for (uint64_t i = 0; i < op->ncp; ++i)
+      {
+        const uint32_t k = perm[i < nc ? i : nc - 1];
+        hm[i]            = d->cell_h_min[k];
+        ms[i]            = d->cell_measure[k];
+      }
+    ok = ok && upload(op->h_min, hm.data(), hm.size() * 8) && upload(op->measure, ms.data(), ms.size() * 8);
+    if (op->geom == GLSB_GEOM_CARTESIAN)
+      {
+        std::vector<double> ij((size_t)dm * op->ncp), dj(op->ncp);
+        for (uint64_t i = 0; i < op->ncp; ++i)
+          {
+            const uint32_t k = perm[i < nc ? i : nc - 1];
+            for (int e = 0; e < dm; ++e)
+              ij[e * op->ncp + i] = d->inv_jac[(uint64_t)k * dm + e];
+            dj[i] = d->jxw[k];
+          }
+        if (op->number_type == GLSB_F64)
+          ok = ok && upload(op->inv_jac, ij.data(), ij.size() * 8) && upload(op->jxw, dj.data(), dj.size() * 8);
+        else
+          ok = ok && upload_converted<float>(op->inv_jac, ij.data(), ij.size()) &&
+               upload_converted<float>(op->jxw, dj.data(), dj.size());
+      }
+    else
+      {
+        const uint32_t inner = dm * dm;
+        DevBuf         raw;
+        ok = ok && upload(raw, d->inv_jac, (size_t)nc * op->nq * inner * 8);
+        ok = ok && op->inv_jac.alloc((size_t)inner * op->nq * op->ncp * op->tsize);
+        if (ok)
+          {
+            const uint64_t tot = (uint64_t)inner * op->nq * op->ncp;
+            if (op->number_type == GLSB_F64)
+              k_transpose_geom<double><<<(unsigned)((tot + 255) / 256), 256>>>(
+                raw.as<double>(), op->perm.as<uint32_t>(), op->inv_jac.as<double>(), nc, op->nq, inner, op->ncp);
+            else
+              k_transpose_geom<float><<<(unsigned)((tot + 255) / 256), 256>>>(
+                raw.as<double>(), op->perm.as<uint32_t>(), op->inv_jac.as<float>(), nc, op->nq, inner, op->ncp);
+            ok = cudaDeviceSynchronize() == cudaSuccess;
+          }
+        ok = ok && upload(raw, d->jxw, (size_t)nc * op->nq * 8);
+        ok = ok && op->jxw.alloc((size_t)op->nq * op->ncp * op->tsize);
+        if (ok)
+          {
+            const uint64_t tot = (uint64_t)op->nq * op->ncp;
+            if (op->number_type == GLSB_F64)
+              k_transpose_geom<double><<<(unsigned)((tot + 255) / 256), 256>>>(
+                raw.as<double>(), op->perm.as<uint32_t>(), op->jxw.as<double>(), nc, op->nq, 1, op->ncp);
+            else
+              k_transpose_geom<float><<<(unsigned)((tot + 255) / 256), 256>>>(
+                raw.as<double>(), op->perm.as<uint32_t>(), op->jxw.as<float>(), nc, op->nq, 1, op->ncp);
+            ok = cudaDeviceSynchronize() == cudaSuccess;
+          }
+      }
+  }
+  ok = ok && op->max_bits.alloc(8);
+
+  if (!ok)
+    {
+      cudaError_t e = cudaGetLastError();
+      std::string m = std::string("glsb_create: device setup failed: ") + cudaGetErrorString(e);
+      delete op;
+      return fail(nullptr, m);
+    }
+  *out = op;
+  return 0;
+}
+
+void glsb_destroy(glsb_op *op)
+{
+  if (op)
+    {
+      cudaSetDevice(op->device);
+      delete op;
+    }
+}
+
+const char *glsb_last_error(const glsb_op *op) { return op ? op->err.c_str() : g_create_error.c_str(); }
+
+int glsb_invalidate_system(glsb_op *op)
+{
+  if (!op)
+    return 1;
+  return 0; // the assembled system matrix stays with the retained CPU operator (coarse level)
+}
+
+int glsb_vmult_begin(glsb_op *op, void *dst, void *stream)
+{
+  if (!op || !dst)
+    return fail(op, "glsb_vmult_begin: null argument");
+  if (cudaMemsetAsync(dst, 0, (op->n_owned + op->n_ghost) * op->tsize, (cudaStream_t)stream) != cudaSuccess)
+    return cuda_fail(op, "glsb_vmult_begin: memset");
+  op->launches++;
+  return 0;
+}
+
+int glsb_vmult_cells(glsb_op *op, void *dst, const void *src, double weight, int which, void *stream)
+{
+  if (!op || !dst || !src)
+    return fail(op, "glsb_vmult_cells: null argument");
+  if (!op->lin_valid)
+    return fail(op, "glsb_vmult: set_linearization_point has not been called");
+  if (op->increment_form && op->ctd && !op->prev_valid)
+    return fail(op, "glsb_vmult: set_previous_solution has not been called");
+  const int branch = op->increment_form ? BR_NEWTON : BR_FIXED_POINT;
+  int       rc     = 0;
+#define CALL(D, T) do_cells<D, T>(op, dst, src, weight, which, branch, (cudaStream_t)stream)
+  GLSB_DISPATCH(op, CALL);
+#undef CALL
+  if (rc)
+    return cuda_fail(op, "glsb_vmult_cells: launch");
+  return 0;
+}
+
+int glsb_vmult_finish(glsb_op *op, void *dst, const void *src, void *stream)
+{
+  if (!op || !dst || !src)
+    return fail(op, "glsb_vmult_finish: null argument");
+  if (op->n_constrained == 0)
+    return 0;
+  const unsigned g = (op->n_constrained + 255) / 256;
+  if (op->number_type == GLSB_F64)
+    k_copy_indexed<double><<<g, 256, 0, (cudaStream_t)stream>>>((double *)dst, (const double *)src,
+                                                                op->cidx.as<uint32_t>(), op->n_constrained);
+  else
+    k_copy_indexed<float><<<g, 256, 0, (cudaStream_t)stream>>>((float *)dst, (const float *)src,
+                                                               op->cidx.as<uint32_t>(), op->n_constrained);
+  op->launches++;
+  if (cudaGetLastError() != cudaSuccess)
+    return cuda_fail(op, "glsb_vmult_finish");
+  return 0;
+}
+
+int glsb_vmult(glsb_op *op, void *dst, const void *src, double weight, void *stream)
+{
+  int rc = glsb_vmult_begin(op, dst, stream);
+  if (rc == 0)
+    rc = glsb_vmult_cells(op, dst, src, weight, GLSB_CELLS_ALL, stream);
+  if (rc == 0)
+    rc = glsb_vmult_finish(op, dst, src, stream);
+  return rc;
+}
+
+int glsb_evaluate_residual_cells(glsb_op *op, void *dst, const void *src, double weight, int which, void *stream)
+{
+  if (!op || !dst || !src)
+    return fail(op, "glsb_evaluate_residual: null argument");
+  if (!op->lin_valid)
+    return fail(op, "glsb_evaluate_residual: set_linearization_point has not been called");
+  int rc = 0;
+#define CALL(D, T) do_cells<D, T>(op, dst, src, weight, which, BR_RESIDUAL, (cudaStream_t)stream)
+  GLSB_DISPATCH(op, CALL);
+#undef CALL
+  if (rc)
+    return cuda_fail(op, "glsb_evaluate_residual: launch");
+  return 0;
+}
+
+int glsb_evaluate_residual(glsb_op *op, void *dst, const void *src, double weight, void *stream)
+{
+  int rc = glsb_vmult_begin(op, dst, stream);
+  if (rc == 0)
+    rc = glsb_evaluate_residual_cells(op, dst, src, weight, GLSB_CELLS_ALL, stream);
+  // constrained rows receive nothing from the scatter, so set_zero (operator_ns.cc:678) is implied
+  return rc;
+}
+
+int glsb_set_linearization_point(glsb_op *op, const void *vec, double dt, void *stream)
+{
+  if (!op || !vec)
+    return fail(op, "glsb_set_linearization_point: null argument");
+  if (!ensure_tables(op, true, false))
+    return cuda_fail(op, "glsb_set_linearization_point: table allocation");
+  int rc = 0;
+#define CALL(D, T) do_lin<D, T>(op, vec, dt, (cudaStream_t)stream)
+  GLSB_DISPATCH(op, CALL);
+#undef CALL
+  if (rc)
+    return cuda_fail(op, "glsb_set_linearization_point: launch");
+  op->lin_valid = true;
+  op->lin_dt    = dt;
+  return 0;
+}
+
+int glsb_set_previous_solution(glsb_op *op, const void *const *history, const double *weights, int order,
+                               void *stream)
+{
+  if (!op)
+    return 1;
+  if (op->time_order == 0) // operator_ns.cc:242-243
+    return 0;
+  if (!history || !weights)
+    return fail(op, "glsb_set_previous_solution: null argument");
+  if (order != op->time_order || order > 3)
+    return fail(op, "glsb_set_previous_solution: order does not match the operator's time_order");
+  if (!ensure_tables(op, false, true))
+    return cuda_fail(op, "glsb_set_previous_solution: table allocation");
+  int rc = 0;
+#define CALL(D, T) do_prev<D, T>(op, history, weights, order, (cudaStream_t)stream)
+  GLSB_DISPATCH(op, CALL);
+#undef CALL
+  if (rc)
+    return cuda_fail(op, "glsb_set_previous_solution: launch");
+  op->prev_valid = true;
+  return 0;
+}
+
+int glsb_diagonal_cells(glsb_op *op, void *diag, double weight, void *stream)
+{
+  if (!op || !diag)
+    return fail(op, "glsb_diagonal_cells: null argument");
+  if (!op->lin_valid)
+    return fail(op, "glsb_compute_inverse_diagonal: set_linearization_point has not been called");
+  int rc = glsb_vmult_begin(op, diag, stream);
+  if (rc)
+    return rc;
+#define CALL(D, T) do_diag<D, T>(op, diag, weight, (cudaStream_t)stream)
+  GLSB_DISPATCH(op, CALL);
+#undef CALL
+  if (rc)
+    return cuda_fail(op, "glsb_diagonal_cells: launch");
+  return 0;
+}
+
+int glsb_diagonal_finish(glsb_op *op, void *diag, void *stream)
+{
+  if (!op || !diag)
+    return fail(op, "glsb_diagonal_finish: null argument");
+  cudaStream_t   s = (cudaStream_t)stream;
+  const uint64_t n = op->n_owned; // ghosts carry nothing after compress
+  if (op->number_type == GLSB_F64)
+    {
+      if (op->n_constrained)
+        k_set_indexed<double><<<(op->n_constrained + 255) / 256, 256, 0, s>>>(
+          (double *)diag, op->cidx.as<uint32_t>(), op->n_constrained, 1.0);
+      k_invert_guarded<double><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((double *)diag, n);
+    }
+  else
+    {
+      if (op->n_constrained)
+        k_set_indexed<float><<<(op->n_constrained + 255) / 256, 256, 0, s>>>(
+          (float *)diag, op->cidx.as<uint32_t>(), op->n_constrained, 1.0f);
+      k_invert_guarded<float><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((float *)diag, n);
+    }
+  op->launches += 1 + (op->n_constrained > 0);
+  if (cudaGetLastError() != cudaSuccess)
+    return cuda_fail(op, "glsb_diagonal_finish");
+  return 0;
+}
+
+int glsb_compute_inverse_diagonal(glsb_op *op, void *diag, double weight, void *stream)
+{
+  int rc = glsb_diagonal_cells(op, diag, weight, stream);
+  if (rc == 0)
+    rc = glsb_diagonal_finish(op, diag, stream);
+  return rc;
+}
+
+int glsb_get_max_u(glsb_op *op, const void *vec, double *out_host, void *stream)
+{
+  if (!op || !vec || !out_host)
+    return fail(op, "glsb_get_max_u: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(op->max_bits.p, 0, 8, s) != cudaSuccess)
+    return cuda_fail(op, "glsb_get_max_u: memset");
+  int rc = 0;
+#define CALL(D, T) do_maxu<D, T>(op, vec, s)
+  GLSB_DISPATCH(op, CALL);
+#undef CALL
+  if (rc)
+    return cuda_fail(op, "glsb_get_max_u: launch");
+  unsigned long long bits = 0;
+  if (cudaMemcpyAsync(&bits, op->max_bits.p, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      cudaStreamSynchronize(s) != cudaSuccess)
+    return cuda_fail(op, "glsb_get_max_u: readback");
+  memcpy(out_host, &bits, 8);
+  return 0;
+}
+
+int glsb_pack_export(glsb_op *op, void *buf, const void *vec, void *stream)
+{
+  if (!op || (op->n_export && (!buf || !vec)))
+    return fail(op, "glsb_pack_export: null argument");
+  if (op->n_export == 0)
+    return 0;
+  const unsigned g = (unsigned)((op->n_export + 255) / 256);
+  if (op->number_type == GLSB_F64)
+    k_pack<double><<<g, 256, 0, (cudaStream_t)stream>>>((double *)buf, (const double *)vec,
+                                                        op->export_idx.as<uint32_t>(), op->n_export);
+  else
+    k_pack<float><<<g, 256, 0, (cudaStream_t)stream>>>((float *)buf, (const float *)vec,
+                                                       op->export_idx.as<uint32_t>(), op->n_export);
+  op->launches++;
+  if (cudaGetLastError() != cudaSuccess)
+    return cuda_fail(op, "glsb_pack_export");
+  return 0;
+}
+
+int glsb_unpack_add(glsb_op *op, void *vec, const void *buf, void *stream)
+{
+  if (!op || (op->n_export && (!buf || !vec)))
+    return fail(op, "glsb_unpack_add: null argument");
+  if (op->n_export == 0)
+    return 0;
+  const unsigned g = (unsigned)((op->n_export + 255) / 256);
+  if (op->number_type == GLSB_F64)
+    k_unpack_add<double><<<g, 256, 0, (cudaStream_t)stream>>>((double *)vec, (const double *)buf,
+                                                              op->export_idx.as<uint32_t>(), op->n_export);
+  else
+    k_unpack_add<float><<<g, 256, 0, (cudaStream_t)stream>>>((float *)vec, (const float *)buf,
+                                                             op->export_idx.as<uint32_t>(), op->n_export);
+  op->launches++;
+  if (cudaGetLastError() != cudaSuccess)
+    return cuda_fail(op, "glsb_unpack_add");
+  return 0;
+}
+
+uint64_t glsb_n_cells(const glsb_op *op) { return op ? op->n_cells : 0; }
+uint64_t glsb_n_local(const glsb_op *op) { return op ? op->n_owned + op->n_ghost : 0; }
+uint64_t glsb_n_interior_cells(const glsb_op *op) { return op ? op->n_interior : 0; }
+uint64_t glsb_launch_count(const glsb_op *op) { return op ? op->launches : 0; }
+const char *glsb_vmult_variant(const glsb_op *op) { return op ? op->variant.c_str() : ""; }
+
+int glsb_set_variant(glsb_op *op, int variant)
+{
+  if (!op)
+    return 1;
+  op->variant_forced = variant;
+  return 0;
+}
+
+int glsb_get_table(glsb_op *op, const char *name, void *out, uint64_t out_count, void *stream)
+{
+  if (!op || !name || !out)
+    return fail(op, "glsb_get_table: null argument");
+  const DevBuf *b  = nullptr;
+  uint32_t      nf = 0, nq = op->nq;
+  const int     d  = op->dim;
+  const std::string s(name);
+  if (s == "u_star_value")
+    b = &op->U, nf = d;
+  else if (s == "u_star_gradient")
+    b = &op->H, nf = d * d;
+  else if (s == "p_star_gradient")
+    b = &op->P, nf = d;
+  else if (s == "u_time_derivative_old")
+    b = &op->O, nf = d;
+  else if (s == "u_old_gradient")
+    b = &op->Gold, nf = d * d;
+  else if (s == "p_old_gradient")
+    b = &op->gold_p, nf = d;
+  else if (s == "delta_1")
+    b = &op->d1c, nf = 1, nq = 1;
+  else if (s == "delta_2")
+    b = &op->d2c, nf = 1, nq = 1;
+  else if (s == "delta_1_q")
+    b = &op->d1q, nf = 1;
+  else if (s == "delta_2_q")
+    b = &op->d2q, nf = 1;
+  else
+    return fail(op, "glsb_get_table: unknown table " + s);
+  if (!b->p)
+    return fail(op, "glsb_get_table: table " + s + " has not been computed");
+  const uint64_t tot = (uint64_t)nf * nq * op->n_cells;
+  if (out_count != tot)
+    return fail(op, "glsb_get_table: wrong output size for " + s);
+  const unsigned g = (unsigned)((tot + 255) / 256);
+  if (op->number_type == GLSB_F64)
+    k_export_table<double><<<g, 256, 0, (cudaStream_t)stream>>>(b->as<double>(), op->perm.as<uint32_t>(),
+                                                                (double *)out, (uint32_t)op->n_cells, nq, nf,
+                                                                op->ncp);
+  else
+    k_export_table<float><<<g, 256, 0, (cudaStream_t)stream>>>(b->as<float>(), op->perm.as<uint32_t>(),
+                                                               (float *)out, (uint32_t)op->n_cells, nq, nf, op->ncp);
+  if (cudaGetLastError() != cudaSuccess)
+    return cuda_fail(op, "glsb_get_table");
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,99 @@
+// Internal declarations shared by the C-ABI layer and the kernel translation units.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace glsb
+{
+constexpr int MAX_N = 5; // degree 4
+
+// 1-D tables, passed by value as a kernel parameter => they live in the constant bank
+// and compile-time-indexed entries become immediate constant operands of DFMA/FFMA.
+template <typename T, int n>
+struct Shape
+{
+  T S[n * n];  // S[q*n + i]  = phi_i(x_q)          (FE_Q Lagrange basis at Gauss points)
+  T D[n * n];  // D[q*n + q'] = collocation derivative on the Gauss points
+  T w[n];      // 1-D Gauss weights on [0,1]
+};
+
+struct ShapeHost
+{
+  int    n;
+  double S[MAX_N * MAX_N];
+  double G[MAX_N * MAX_N];
+  double D[MAX_N * MAX_N];
+  double w[MAX_N];
+  double xq[MAX_N];
+  double nodes[MAX_N];
+};
+void compute_shape_host(int degree, ShapeHost &out);
+
+enum Branch : int
+{
+  BR_NEWTON      = 0, // do_vmult_cell<false>, increment_form (operator_ns.cc:1067-1182)
+  BR_FIXED_POINT = 1, // do_vmult_cell<false>, !increment_form (operator_ns.cc:955-1066)
+  BR_RESIDUAL    = 2  // do_vmult_cell<true> (same block, evaluate_residual terms on)
+};
+
+// Everything a cell kernel needs; T = Number. All pointers are device pointers.
+template <typename T>
+struct KParams
+{
+  // cells [cell_begin, cell_end) in internal order; ncp = padded cell stride of all SoA arrays
+  uint32_t cell_begin, cell_end;
+  uint64_t ncp;
+  const uint32_t *idx; // [C*n_loc][ncp]
+  // constraint rows
+  const uint32_t *row_dof, *row_ptr, *ecol;
+  const T        *eval;
+  // geometry
+  int      geom;    // 0 Cartesian, 2 general
+  const T *inv_jac; // Cartesian [dim][ncp]; general [dim*dim][nq][ncp]
+  const T *jxw;     // Cartesian [ncp]; general [nq][ncp]
+  const double *h_min, *measure; // [ncp]
+  // q-point tables [field][nq][ncp]
+  T *U, *H, *P, *O, *Gold, *gold_p, *R1;
+  T *d1c, *d2c; // [ncp]
+  T *d1q, *d2q; // [nq][ncp]
+  // scalars
+  T      weight, nu, theta;
+  double c1, c2, stau, nu_d;
+  int    degree;
+  int    ctd, cell_wise, has_o, theta_ne_1;
+  int    sign_negative; // scatter -value (evaluate_residual "dst *= -1")
+  // set_previous_solution
+  const T *hist[4];
+  T        hist_w[4];
+  int      hist_n;
+  // outputs / inputs
+  const T *src;
+  T       *dst;
+  unsigned long long *max_bits; // get_max_u
+};
+
+// columns of C_cell for cells with weighted constraint rows (compute_diagonal)
+struct DiagColumns
+{
+  const uint32_t *cell;    // [n_list] internal cell index
+  const uint32_t *col_ptr; // [n_list + 1] -> columns
+  const uint32_t *col_dof; // [n_cols] vector index g
+  const uint32_t *ent_ptr; // [n_cols + 1] -> entries
+  const uint32_t *ent_loc; // local dof index (c*n_loc + l)
+  const double   *ent_val; // weight
+  uint32_t        n_list;
+};
+
+// dispatch entry points implemented per (dim, T) translation unit
+template <int dim, typename T>
+struct Kernels
+{
+  static int vmult(int n, int branch, const KParams<T> &p, const ShapeHost &sh, cudaStream_t s);
+  static int linearization(int n, const KParams<T> &p, const ShapeHost &sh, cudaStream_t s);
+  static int previous(int n, int with_gradients, const KParams<T> &p, const ShapeHost &sh, cudaStream_t s);
+  static int diagonal(int n, int branch, const KParams<T> &p, const ShapeHost &sh, const uint8_t *skip_cell,
+                      const DiagColumns &dc, cudaStream_t s);
+  static int max_u(int n, const KParams<T> &p, const ShapeHost &sh, cudaStream_t s);
+};
+
+} // namespace glsb

@@ -1,0 +1,207 @@
+// One translation unit per (dim, Number): compile with -DGLSB_DIM=2|3 -DGLSB_REAL=double|float.
+#include "glsb_kernels.cuh"
+#ifdef GLSB_WITH_Q2
+#include "glsb_q2.cuh"
+#endif
+
+#ifndef GLSB_DIM
+#error "define GLSB_DIM"
+#endif
+#ifndef GLSB_REAL
+#error "define GLSB_REAL"
+#endif
+
+namespace glsb
+{
+template <typename T, int n>
+static Shape<T, n> to_shape(const ShapeHost &h)
+{
+  Shape<T, n> s;
+  for (int i = 0; i < n * n; ++i)
+    {
+      s.S[i] = (T)h.S[i];
+      s.D[i] = (T)h.D[i];
+    }
+  for (int i = 0; i < n; ++i)
+    s.w[i] = (T)h.w[i];
+  return s;
+}
+
+template <typename K>
+static int ensure_smem(K kernel, size_t bytes)
+{
+  if (bytes > 48 * 1024)
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+      return 1;
+  return 0;
+}
+
+#define GLSB_GRID(G, p) (unsigned)(((p).cell_end - (p).cell_begin + G::CPB - 1) / G::CPB)
+
+template <int dim, int n, typename T>
+static int launch_vmult(int branch, const KParams<T> &p, const ShapeHost &sh, cudaStream_t s)
+{
+  using G = Geo<dim, n>;
+  if (p.cell_end <= p.cell_begin)
+    return 0;
+  const size_t sm = generic_smem_bytes<dim, n, T>();
+  const auto   S  = to_shape<T, n>(sh);
+  switch (branch)
+    {
+      case BR_NEWTON:
+        if (ensure_smem(k_vmult_generic<dim, n, T, BR_NEWTON>, sm))
+          return 1;
+        k_vmult_generic<dim, n, T, BR_NEWTON><<<GLSB_GRID(G, p), G::THREADS, sm, s>>>(p, S);
+        break;
+      case BR_FIXED_POINT:
+        if (ensure_smem(k_vmult_generic<dim, n, T, BR_FIXED_POINT>, sm))
+          return 1;
+        k_vmult_generic<dim, n, T, BR_FIXED_POINT><<<GLSB_GRID(G, p), G::THREADS, sm, s>>>(p, S);
+        break;
+      default:
+        if (ensure_smem(k_vmult_generic<dim, n, T, BR_RESIDUAL>, sm))
+          return 1;
+        k_vmult_generic<dim, n, T, BR_RESIDUAL><<<GLSB_GRID(G, p), G::THREADS, sm, s>>>(p, S);
+    }
+  return cudaGetLastError() != cudaSuccess;
+}
+
+template <int dim, int n, typename T>
+static int launch_lin(const KParams<T> &p, const ShapeHost &sh, cudaStream_t s)
+{
+  using G = Geo<dim, n>;
+  if (p.cell_end <= p.cell_begin)
+    return 0;
+  const size_t sm = generic_smem_bytes<dim, n, T>();
+  if (ensure_smem(k_linearization<dim, n, T>, sm))
+    return 1;
+  k_linearization<dim, n, T><<<GLSB_GRID(G, p), G::THREADS, sm, s>>>(p, to_shape<T, n>(sh));
+  return cudaGetLastError() != cudaSuccess;
+}
+
+template <int dim, int n, typename T>
+static int launch_prev(int grad, const KParams<T> &p, const ShapeHost &sh, cudaStream_t s)
+{
+  using G = Geo<dim, n>;
+  if (p.cell_end <= p.cell_begin)
+    return 0;
+  const size_t sm = generic_smem_bytes<dim, n, T>();
+  if (grad)
+    {
+      if (ensure_smem(k_previous<dim, n, T, true>, sm))
+        return 1;
+      k_previous<dim, n, T, true><<<GLSB_GRID(G, p), G::THREADS, sm, s>>>(p, to_shape<T, n>(sh));
+    }
+  else
+    {
+      if (ensure_smem(k_previous<dim, n, T, false>, sm))
+        return 1;
+      k_previous<dim, n, T, false><<<GLSB_GRID(G, p), G::THREADS, sm, s>>>(p, to_shape<T, n>(sh));
+    }
+  return cudaGetLastError() != cudaSuccess;
+}
+
+template <int dim, int n, typename T>
+static int launch_maxu(const KParams<T> &p, const ShapeHost &sh, cudaStream_t s)
+{
+  using G = Geo<dim, n>;
+  if (p.cell_end <= p.cell_begin)
+    return 0;
+  const size_t sm = generic_smem_bytes<dim, n, T>();
+  if (ensure_smem(k_max_u<dim, n, T>, sm))
+    return 1;
+  k_max_u<dim, n, T><<<GLSB_GRID(G, p), G::THREADS, sm, s>>>(p, to_shape<T, n>(sh));
+  return cudaGetLastError() != cudaSuccess;
+}
+
+template <int dim, int n, typename T, int BR>
+static int launch_diag_br(const KParams<T> &p, const ShapeHost &sh, const uint8_t *skip, const DiagColumns &dc,
+                          cudaStream_t s)
+{
+  using G         = Geo<dim, n>;
+  const size_t sm = generic_smem_bytes<dim, n, T>();
+  const auto   S  = to_shape<T, n>(sh);
+  if (p.cell_end > p.cell_begin)
+    {
+      if (ensure_smem(k_diag_generic<dim, n, T, BR>, sm))
+        return 1;
+      k_diag_generic<dim, n, T, BR><<<GLSB_GRID(G, p), G::THREADS, sm, s>>>(p, S, skip);
+    }
+  if (dc.n_list > 0)
+    {
+      if (ensure_smem(k_diag_columns<dim, n, T, BR>, sm))
+        return 1;
+      k_diag_columns<dim, n, T, BR><<<dc.n_list, G::THREADS, sm, s>>>(p, S, dc);
+    }
+  return cudaGetLastError() != cudaSuccess;
+}
+
+template <int dim, int n, typename T>
+static int launch_diag(int branch, const KParams<T> &p, const ShapeHost &sh, const uint8_t *skip,
+                       const DiagColumns &dc, cudaStream_t s)
+{
+  if (branch == BR_NEWTON)
+    return launch_diag_br<dim, n, T, BR_NEWTON>(p, sh, skip, dc, s);
+  return launch_diag_br<dim, n, T, BR_FIXED_POINT>(p, sh, skip, dc, s);
+}
+
+#define GLSB_SWITCH_N(call)          \
+  switch (n)                         \
+    {                                \
+      case 2:                        \
+        return call(2);              \
+      case 3:                        \
+        return call(3);              \
+      case 4:                        \
+        return call(4);              \
+      case 5:                        \
+        return call(5);              \
+      default:                       \
+        return 2;                    \
+    }
+
+template <>
+int Kernels<GLSB_DIM, GLSB_REAL>::vmult(int n, int branch, const KParams<GLSB_REAL> &p, const ShapeHost &sh,
+                                        cudaStream_t s)
+{
+#define CALL(N) launch_vmult<GLSB_DIM, N, GLSB_REAL>(branch, p, sh, s)
+  GLSB_SWITCH_N(CALL)
+#undef CALL
+}
+
+template <>
+int Kernels<GLSB_DIM, GLSB_REAL>::linearization(int n, const KParams<GLSB_REAL> &p, const ShapeHost &sh,
+                                                cudaStream_t s)
+{
+#define CALL(N) launch_lin<GLSB_DIM, N, GLSB_REAL>(p, sh, s)
+  GLSB_SWITCH_N(CALL)
+#undef CALL
+}
+
+template <>
+int Kernels<GLSB_DIM, GLSB_REAL>::previous(int n, int with_gradients, const KParams<GLSB_REAL> &p,
+                                           const ShapeHost &sh, cudaStream_t s)
+{
+#define CALL(N) launch_prev<GLSB_DIM, N, GLSB_REAL>(with_gradients, p, sh, s)
+  GLSB_SWITCH_N(CALL)
+#undef CALL
+}
+
+template <>
+int Kernels<GLSB_DIM, GLSB_REAL>::diagonal(int n, int branch, const KParams<GLSB_REAL> &p, const ShapeHost &sh,
+                                           const uint8_t *skip_cell, const DiagColumns &dc, cudaStream_t s)
+{
+#define CALL(N) launch_diag<GLSB_DIM, N, GLSB_REAL>(branch, p, sh, skip_cell, dc, s)
+  GLSB_SWITCH_N(CALL)
+#undef CALL
+}
+
+template <>
+int Kernels<GLSB_DIM, GLSB_REAL>::max_u(int n, const KParams<GLSB_REAL> &p, const ShapeHost &sh, cudaStream_t s)
+{
+#define CALL(N) launch_maxu<GLSB_DIM, N, GLSB_REAL>(p, sh, s)
+  GLSB_SWITCH_N(CALL)
+#undef CALL
+}
+
+} // namespace glsb

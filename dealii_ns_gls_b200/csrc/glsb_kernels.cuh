@@ -1,0 +1,750 @@
+// Generic cell kernels: any dim in {2,3}, degree 1..4, Number in {double,float},
+// Cartesian or general geometry, all three branches of do_vmult_cell, constraints.
+//
+// Thread mapping: one thread per (cell, quadrature point / node); CPB cells per CTA,
+// thread t -> (cb = t % CPB, l = t / CPB) so that the [field][q][cell] SoA tables and the
+// [dof][cell] index array are read with CPB consecutive cells per request.  Sum
+// factorisation sweeps go through shared memory.  This is the reference-complete
+// fallback path; the register-tiled Q2 kernel in glsb_q2.cuh is the fast path.
+#pragma once
+#include "glsb_common.h"
+#include "../../include/glsb200.h"
+
+namespace glsb
+{
+template <int dim, int n>
+struct Geo
+{
+  static constexpr int n_loc = (dim == 2) ? n * n : n * n * n;
+  static constexpr int C     = dim + 1;
+  static constexpr int nq    = n_loc;
+  static constexpr int cpb()
+  {
+    int c = 1;
+    while (2 * c * n_loc <= 256)
+      c *= 2;
+    return c;
+  }
+  static constexpr int CPB     = cpb();
+  static constexpr int THREADS = CPB * n_loc;
+};
+
+__device__ __forceinline__ void atomic_add(double *a, double v) { atomicAdd(a, v); }
+__device__ __forceinline__ void atomic_add(float *a, float v) { atomicAdd(a, v); }
+
+template <typename T>
+__device__ __forceinline__ T gather_resolved(const KParams<T> &p, const T *__restrict__ src, uint32_t iv)
+{
+  if (!(iv & GLSB_CONSTRAINED_BIT))
+    return src[iv];
+  const uint32_t r = iv & ~GLSB_CONSTRAINED_BIT;
+  T              s = 0;
+  for (uint32_t e = p.row_ptr[r]; e < p.row_ptr[r + 1]; ++e)
+    s += p.eval[e] * src[p.ecol[e]];
+  return s;
+}
+
+template <typename T>
+__device__ __forceinline__ uint32_t plain_index(const KParams<T> &p, uint32_t iv)
+{
+  return (iv & GLSB_CONSTRAINED_BIT) ? p.row_dof[iv & ~GLSB_CONSTRAINED_BIT] : iv;
+}
+
+template <typename T>
+__device__ __forceinline__ void scatter_resolved(const KParams<T> &p, T *__restrict__ dst, uint32_t iv, T v)
+{
+  if (!(iv & GLSB_CONSTRAINED_BIT))
+    {
+      atomic_add(dst + iv, v);
+      return;
+    }
+  const uint32_t r = iv & ~GLSB_CONSTRAINED_BIT;
+  for (uint32_t e = p.row_ptr[r]; e < p.row_ptr[r + 1]; ++e)
+    atomic_add(dst + p.ecol[e], p.eval[e] * v);
+}
+
+// ---------------------------------------------------------------------------------------
+// per-thread context of the generic kernels
+// ---------------------------------------------------------------------------------------
+template <int dim, int n, typename T>
+struct Ctx
+{
+  using G                    = Geo<dim, n>;
+  static constexpr int n_loc = G::n_loc, C = G::C, CPB = G::CPB;
+
+  T  *v;  // [C][n_loc][CPB]
+  T  *sg; // [C*dim][n_loc][CPB]
+  T  *sS, *sD;
+  int cb, l, ii[3];
+
+  __device__ __forceinline__ int at(int c, int ll) const { return (c * n_loc + ll) * CPB + cb; }
+  __device__ __forceinline__ int stride(int e) const { return e == 0 ? 1 : (e == 1 ? n : n * n); }
+
+  __device__ void init(unsigned char *smem, const Shape<T, n> &sh)
+  {
+    v  = reinterpret_cast<T *>(smem);
+    sg = v + C * n_loc * CPB;
+    sS = sg + C * dim * n_loc * CPB;
+    sD = sS + n * n;
+    cb = threadIdx.x % CPB;
+    l  = threadIdx.x / CPB;
+    ii[0] = l % n;
+    ii[1] = (l / n) % n;
+    ii[2] = l / (n * n);
+    for (int k = threadIdx.x; k < n * n; k += blockDim.x)
+      {
+        sS[k] = sh.S[k];
+        sD[k] = sh.D[k];
+      }
+  }
+
+  // one 1-D sweep over all C components, in place in v.  transpose = false: out_q = sum_i M[q][i] in_i
+  __device__ void sweep(const T *M, int e, bool transpose)
+  {
+    const int ie = ii[e], st = stride(e), base = l - ie * st;
+    T         out[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      {
+        T s = 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+          s += (transpose ? M[i * n + ie] : M[ie * n + i]) * v[at(c, base + i * st)];
+        out[c] = s;
+      }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      v[at(c, l)] = out[c];
+    __syncthreads();
+  }
+
+  // v holds dof values on entry (after a __syncthreads); on exit v holds the values at the
+  // quadrature points, val[c] the value and rg[c][e] the reference-cell gradient at point l.
+  __device__ void evaluate(T (&val)[C], T (&rg)[C][dim])
+  {
+#pragma unroll
+    for (int e = 0; e < dim; ++e)
+      sweep(sS, e, false);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      val[c] = v[at(c, l)];
+#pragma unroll
+    for (int e = 0; e < dim; ++e)
+      {
+        const int ie = ii[e], st = stride(e), base = l - ie * st;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          {
+            T s = 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i)
+              s += sD[ie * n + i] * v[at(c, base + i * st)];
+            rg[c][e] = s;
+          }
+      }
+  }
+
+  // vq[c] (already times JxW) and rgq[c][e] (reference gradient, times JxW) at point l
+  // -> v holds the local result vector (tested with all basis functions) on exit.
+  __device__ void integrate(const T (&vq)[C], const T (&rgq)[C][dim])
+  {
+    __syncthreads(); // everyone is done reading v
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int e = 0; e < dim; ++e)
+        sg[((c * dim + e) * n_loc + l) * CPB + cb] = rgq[c][e];
+    __syncthreads();
+    T out[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      out[c] = vq[c];
+#pragma unroll
+    for (int e = 0; e < dim; ++e)
+      {
+        const int ie = ii[e], st = stride(e), base = l - ie * st;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          {
+            T s = 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i)
+              s += sD[i * n + ie] * sg[((c * dim + e) * n_loc + base + i * st) * CPB + cb];
+            out[c] += s;
+          }
+      }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      v[at(c, l)] = out[c];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < dim; ++e)
+      sweep(sS, e, true);
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// geometry: reference gradient <-> physical gradient
+// ---------------------------------------------------------------------------------------
+template <int dim, int n, typename T>
+struct GeomQ
+{
+  T ij[dim][dim]; // (J^-1)_{e j}; Cartesian: only the diagonal is used
+  T jxw;
+  int cart;
+
+  __device__ __forceinline__ void load(const KParams<T> &p, const Shape<T, n> &sh, uint32_t cell, int q, const int (&qi)[3])
+  {
+    cart = (p.geom == GLSB_GEOM_CARTESIAN);
+    if (cart)
+      {
+        T w = sh.w[qi[0]] * sh.w[qi[1]];
+        if (dim == 3)
+          w *= sh.w[qi[2]];
+#pragma unroll
+        for (int e = 0; e < dim; ++e)
+          ij[e][e] = p.inv_jac[e * p.ncp + cell];
+        jxw = p.jxw[cell] * w;
+      }
+    else
+      {
+        constexpr int nq = Geo<dim, n>::nq;
+#pragma unroll
+        for (int e = 0; e < dim; ++e)
+#pragma unroll
+          for (int j = 0; j < dim; ++j)
+            ij[e][j] = p.inv_jac[((uint64_t)(e * dim + j) * nq + q) * p.ncp + cell];
+        jxw = p.jxw[(uint64_t)q * p.ncp + cell];
+      }
+  }
+  template <int C>
+  __device__ __forceinline__ void to_physical(const T (&rg)[C][dim], T (&g)[C][dim]) const
+  {
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int j = 0; j < dim; ++j)
+        {
+          if (cart)
+            g[c][j] = rg[c][j] * ij[j][j];
+          else
+            {
+              T s = 0;
+#pragma unroll
+              for (int e = 0; e < dim; ++e)
+                s += ij[e][j] * rg[c][e];
+              g[c][j] = s;
+            }
+        }
+  }
+  // test side: rgq[c][e] = sum_j (J^-1)_{e j} gout[c][j] * JxW
+  template <int C>
+  __device__ __forceinline__ void to_reference(const T (&gout)[C][dim], T (&rgq)[C][dim]) const
+  {
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int e = 0; e < dim; ++e)
+        {
+          if (cart)
+            rgq[c][e] = gout[c][e] * ij[e][e] * jxw;
+          else
+            {
+              T s = 0;
+#pragma unroll
+              for (int j = 0; j < dim; ++j)
+                s += ij[e][j] * gout[c][j];
+              rgq[c][e] = s * jxw;
+            }
+        }
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// quadrature-point physics (operator_ns.cc:949-1182), one point
+// ---------------------------------------------------------------------------------------
+template <int dim, typename T>
+__device__ __forceinline__ void symm_add(T (&gout)[dim + 1][dim], const T (&B)[dim][dim], T factor)
+{
+  // operator_ns.cc:899-916
+#pragma unroll
+  for (int d = 0; d < dim; ++d)
+    gout[d][d] += B[d][d] * factor;
+#pragma unroll
+  for (int e = 0; e < dim; ++e)
+#pragma unroll
+    for (int d = e + 1; d < dim; ++d)
+      {
+        const T tmp = (B[d][e] + B[e][d]) * (factor * T(0.5));
+        gout[d][e] += tmp;
+        gout[e][d] += tmp;
+      }
+}
+
+template <int dim, typename T, int BR>
+__device__ __forceinline__ void qpoint_physics(const KParams<T> &p, uint64_t tq, uint32_t cell, uint64_t fs,
+                                               const T (&val)[dim + 1], const T (&g)[dim + 1][dim],
+                                               T (&vout)[dim + 1], T (&gout)[dim + 1][dim])
+{
+  const T d1 = p.cell_wise ? p.d1c[cell] : p.d1q[tq];
+  const T d2 = p.cell_wise ? p.d2c[cell] : p.d2q[tq];
+  const T w  = p.weight;
+  T       U[dim];
+#pragma unroll
+  for (int j = 0; j < dim; ++j)
+    U[j] = p.U[j * fs + tq];
+#pragma unroll
+  for (int c = 0; c <= dim; ++c)
+#pragma unroll
+    for (int j = 0; j < dim; ++j)
+      gout[c][j] = 0;
+
+  if (BR == BR_NEWTON)
+    {
+      T H[dim][dim], P[dim];
+#pragma unroll
+      for (int c = 0; c < dim; ++c)
+        {
+          P[c] = p.P[c * fs + tq];
+#pragma unroll
+          for (int j = 0; j < dim; ++j)
+            H[c][j] = p.H[(c * dim + j) * fs + tq];
+        }
+      T Gm[dim][dim];
+      T div = 0;
+#pragma unroll
+      for (int c = 0; c < dim; ++c)
+        {
+#pragma unroll
+          for (int j = 0; j < dim; ++j)
+            Gm[c][j] = g[c][j];
+          div += g[c][c];
+        }
+      T r0[dim], r1[dim];
+#pragma unroll
+      for (int c = 0; c < dim; ++c)
+        {
+          T sgu = 0, ugs = 0, sgs = 0;
+#pragma unroll
+          for (int j = 0; j < dim; ++j)
+            {
+              sgu += Gm[c][j] * U[j];
+              ugs += H[c][j] * val[j];
+              sgs += H[c][j] * U[j];
+            }
+          const T td = val[c] * w;
+          vout[c]    = td + sgu + ugs;
+          T a        = g[dim][c] + sgu + ugs;
+          T b        = P[c] + sgs;
+          if (p.ctd)
+            {
+              a = td + a;
+              b = (U[c] * w + p.O[c * fs + tq]) + b;
+            }
+          r0[c] = d1 * a;
+          r1[c] = d1 * b;
+        }
+#pragma unroll
+      for (int d = 0; d < dim; ++d)
+        gout[d][d] -= val[dim];
+      symm_add<dim, T>(gout, Gm, p.nu * T(2));
+#pragma unroll
+      for (int d0 = 0; d0 < dim; ++d0)
+#pragma unroll
+        for (int d1i = 0; d1i < dim; ++d1i)
+          gout[d0][d1i] += U[d1i] * r0[d0] + val[d1i] * r1[d0];
+#pragma unroll
+      for (int d = 0; d < dim; ++d)
+        gout[d][d] += d2 * div;
+      vout[dim] = div;
+#pragma unroll
+      for (int j = 0; j < dim; ++j)
+        gout[dim][j] = r0[j];
+    }
+  else
+    {
+      constexpr bool res = (BR == BR_RESIDUAL);
+      const T        th  = p.theta;
+      T              B[dim][dim], pbar[dim], td[dim];
+#pragma unroll
+      for (int c = 0; c < dim; ++c)
+        {
+          td[c]   = val[c] * w;
+          pbar[c] = th * g[dim][c];
+#pragma unroll
+          for (int j = 0; j < dim; ++j)
+            B[c][j] = th * g[c][j];
+        }
+      if (res && p.has_o)
+#pragma unroll
+        for (int c = 0; c < dim; ++c)
+          td[c] += p.O[c * fs + tq];
+      if (res && p.theta_ne_1)
+        {
+          const T omt = T(1) - th;
+#pragma unroll
+          for (int c = 0; c < dim; ++c)
+            {
+              pbar[c] += omt * p.gold_p[c * fs + tq];
+#pragma unroll
+              for (int j = 0; j < dim; ++j)
+                B[c][j] += omt * p.Gold[(c * dim + j) * fs + tq];
+            }
+        }
+      T divb = 0;
+#pragma unroll
+      for (int c = 0; c < dim; ++c)
+        divb += B[c][c];
+      T sgb[dim];
+#pragma unroll
+      for (int c = 0; c < dim; ++c)
+        {
+          T s = 0;
+#pragma unroll
+          for (int j = 0; j < dim; ++j)
+            s += B[c][j] * U[j];
+          sgb[c]  = s;
+          vout[c] = td[c] + s;
+        }
+#pragma unroll
+      for (int d = 0; d < dim; ++d)
+        gout[d][d] -= val[dim];
+      symm_add<dim, T>(gout, B, p.nu * T(2));
+#pragma unroll
+      for (int d0 = 0; d0 < dim; ++d0)
+        {
+          const T tdc = p.ctd ? td[d0] : T(0);
+          const T r0  = d1 * (tdc + pbar[d0] + sgb[d0]);
+#pragma unroll
+          for (int d1i = 0; d1i < dim; ++d1i)
+            gout[d0][d1i] += U[d1i] * r0;
+          gout[dim][d0] = d1 * (tdc + g[dim][d0] + sgb[d0]);
+        }
+#pragma unroll
+      for (int d = 0; d < dim; ++d)
+        gout[d][d] += d2 * divb;
+      vout[dim] = divb;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------
+template <int dim, int n, typename T>
+constexpr size_t generic_smem_bytes()
+{
+  using G = Geo<dim, n>;
+  return sizeof(T) * ((size_t)(G::C + G::C * dim) * G::n_loc * G::CPB + 2 * n * n);
+}
+
+// full cell operator on the local vector in ctx.v (dof values in, tested result out)
+template <int dim, int n, typename T, int BR>
+__device__ __forceinline__ void cell_apply(Ctx<dim, n, T> &ctx, const KParams<T> &p, const Shape<T, n> &sh, uint32_t cell)
+{
+  constexpr int C = dim + 1;
+  T             val[C], rg[C][dim], g[C][dim], vout[C], gout[C][dim], rgq[C][dim];
+  ctx.evaluate(val, rg);
+  GeomQ<dim, n, T> geo;
+  geo.load(p, sh, cell, ctx.l, ctx.ii);
+  geo.template to_physical<C>(rg, g);
+  const uint64_t tq = (uint64_t)ctx.l * p.ncp + cell;
+  const uint64_t fs = (uint64_t)Geo<dim, n>::nq * p.ncp;
+  qpoint_physics<dim, T, BR>(p, tq, cell, fs, val, g, vout, gout);
+  geo.template to_reference<C>(gout, rgq);
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    vout[c] *= geo.jxw;
+  ctx.integrate(vout, rgq);
+}
+
+template <int dim, int n, typename T, int BR>
+__global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_vmult_generic(const KParams<T> p, const Shape<T, n> sh)
+{
+  using G = Geo<dim, n>;
+  extern __shared__ __align__(16) unsigned char smem[];
+  Ctx<dim, n, T> ctx;
+  ctx.init(smem, sh);
+  const uint32_t cell0  = p.cell_begin + blockIdx.x * G::CPB + ctx.cb;
+  const bool     active = cell0 < p.cell_end;
+  const uint32_t cell   = active ? cell0 : p.cell_end - 1;
+  uint32_t       iv[G::C];
+#pragma unroll
+  for (int c = 0; c < G::C; ++c)
+    {
+      iv[c] = p.idx[(uint64_t)(c * G::n_loc + ctx.l) * p.ncp + cell];
+      ctx.v[ctx.at(c, ctx.l)] =
+        (BR == BR_RESIDUAL) ? p.src[plain_index(p, iv[c])] : gather_resolved(p, p.src, iv[c]);
+    }
+  __syncthreads();
+  cell_apply<dim, n, T, BR>(ctx, p, sh, cell);
+  if (active)
+    {
+#pragma unroll
+      for (int c = 0; c < G::C; ++c)
+        {
+          T r = ctx.v[ctx.at(c, ctx.l)];
+          if (p.sign_negative)
+            r = -r;
+          scatter_resolved(p, p.dst, iv[c], r);
+        }
+    }
+}
+
+// set_linearization_point + compute_penalty_parameters (operator_ns.cc:570-620, :322-420)
+template <int dim, int n, typename T>
+__global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_linearization(const KParams<T> p, const Shape<T, n> sh)
+{
+  using G         = Geo<dim, n>;
+  constexpr int C = G::C;
+  extern __shared__ __align__(16) unsigned char smem[];
+  Ctx<dim, n, T> ctx;
+  ctx.init(smem, sh);
+  const uint32_t cell0  = p.cell_begin + blockIdx.x * G::CPB + ctx.cb;
+  const bool     active = cell0 < p.cell_end;
+  const uint32_t cell   = active ? cell0 : p.cell_end - 1;
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    ctx.v[ctx.at(c, ctx.l)] = p.src[plain_index(p, p.idx[(uint64_t)(c * G::n_loc + ctx.l) * p.ncp + cell])];
+  __syncthreads();
+  T val[C], rg[C][dim], g[C][dim];
+  ctx.evaluate(val, rg);
+  GeomQ<dim, n, T> geo;
+  geo.load(p, sh, cell, ctx.l, ctx.ii);
+  geo.template to_physical<C>(rg, g);
+  const uint64_t tq = (uint64_t)ctx.l * p.ncp + cell;
+  const uint64_t fs = (uint64_t)G::nq * p.ncp;
+  T              u2 = 0;
+#pragma unroll
+  for (int c = 0; c < dim; ++c)
+    u2 += val[c] * val[c];
+  // cell-wise u_max: reduce over the points of the cell through shared memory
+  ctx.sg[ctx.l * G::CPB + ctx.cb] = sqrt(u2);
+  __syncthreads();
+  T umax = 0;
+  for (int q = 0; q < G::nq; ++q)
+    umax = max(umax, ctx.sg[q * G::CPB + ctx.cb]);
+  const double h = p.h_min[cell];
+  double       d1c, d2c;
+  if (p.nu_d < h)
+    {
+      d1c = p.c1 / sqrt(p.stau * p.stau + (double)umax * (double)umax / (h * h));
+      d2c = p.c2 * h;
+    }
+  else
+    {
+      d1c = p.c1 * h * h;
+      d2c = p.c2 * h * h;
+    }
+  const double meas = p.measure[cell];
+  const T      hq   = (dim == 2) ? T(sqrt(4. * meas / 3.14159265358979323846) / p.degree) :
+                                   T(pow(6. * meas / 3.14159265358979323846, 1. / 3.) / p.degree);
+  const T      um2  = T(1e-12) + u2;
+  const T      x    = T(4) * p.nu / (hq * hq);
+  const T      d1q  = T(1) / sqrt(T(p.stau * p.stau) + T(4) * um2 / hq / hq + T(9) * (x * x));
+  const T      d2q  = sqrt(um2) * hq * T(0.5);
+  if (!active)
+    return;
+  if (ctx.l == 0)
+    {
+      p.d1c[cell] = T(d1c);
+      p.d2c[cell] = T(d2c);
+    }
+  p.d1q[tq] = d1q;
+  p.d2q[tq] = d2q;
+#pragma unroll
+  for (int c = 0; c < dim; ++c)
+    {
+      p.U[c * fs + tq] = val[c];
+      p.P[c * fs + tq] = g[dim][c];
+#pragma unroll
+      for (int j = 0; j < dim; ++j)
+        p.H[(c * dim + j) * fs + tq] = g[c][j];
+    }
+  if (p.R1 != nullptr)
+    {
+      const T d1 = p.cell_wise ? T(d1c) : d1q;
+#pragma unroll
+      for (int c = 0; c < dim; ++c)
+        {
+          T sgs = 0;
+#pragma unroll
+          for (int j = 0; j < dim; ++j)
+            sgs += g[c][j] * val[j];
+          T b = g[dim][c] + sgs;
+          if (p.ctd)
+            b = (val[c] * p.weight + p.O[c * fs + tq]) + b;
+          p.R1[c * fs + tq] = d1 * b;
+        }
+    }
+}
+
+// set_previous_solution (operator_ns.cc:234-320).  GRAD = false: u_time_derivative_old from
+// vec_old = sum_i w_i hist_i; GRAD = true: u_old_gradient, p_old_gradient from hist[0].
+template <int dim, int n, typename T, bool GRAD>
+__global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_previous(const KParams<T> p, const Shape<T, n> sh)
+{
+  using G         = Geo<dim, n>;
+  constexpr int C = G::C;
+  extern __shared__ __align__(16) unsigned char smem[];
+  Ctx<dim, n, T> ctx;
+  ctx.init(smem, sh);
+  const uint32_t cell0  = p.cell_begin + blockIdx.x * G::CPB + ctx.cb;
+  const bool     active = cell0 < p.cell_end;
+  const uint32_t cell   = active ? cell0 : p.cell_end - 1;
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    {
+      const uint32_t i = plain_index(p, p.idx[(uint64_t)(c * G::n_loc + ctx.l) * p.ncp + cell]);
+      T              s = 0;
+      for (int k = 0; k < p.hist_n; ++k)
+        s += p.hist_w[k] * p.hist[k][i];
+      ctx.v[ctx.at(c, ctx.l)] = s;
+    }
+  __syncthreads();
+  T val[C], rg[C][dim], g[C][dim];
+  ctx.evaluate(val, rg);
+  if (!active)
+    return;
+  const uint64_t tq = (uint64_t)ctx.l * p.ncp + cell;
+  const uint64_t fs = (uint64_t)G::nq * p.ncp;
+  if (!GRAD)
+    {
+#pragma unroll
+      for (int c = 0; c < dim; ++c)
+        p.O[c * fs + tq] = val[c];
+    }
+  else
+    {
+      GeomQ<dim, n, T> geo;
+      geo.load(p, sh, cell, ctx.l, ctx.ii);
+      geo.template to_physical<C>(rg, g);
+#pragma unroll
+      for (int c = 0; c < dim; ++c)
+        {
+          p.gold_p[c * fs + tq] = g[dim][c];
+#pragma unroll
+          for (int j = 0; j < dim; ++j)
+            p.Gold[(c * dim + j) * fs + tq] = g[c][j];
+        }
+    }
+}
+
+// get_max_u (operator_ns.cc:530-568)
+template <int dim, int n, typename T>
+__global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_max_u(const KParams<T> p, const Shape<T, n> sh)
+{
+  using G         = Geo<dim, n>;
+  constexpr int C = G::C;
+  extern __shared__ __align__(16) unsigned char smem[];
+  Ctx<dim, n, T> ctx;
+  ctx.init(smem, sh);
+  const uint32_t cell0  = p.cell_begin + blockIdx.x * G::CPB + ctx.cb;
+  const bool     active = cell0 < p.cell_end;
+  const uint32_t cell   = active ? cell0 : p.cell_end - 1;
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    ctx.v[ctx.at(c, ctx.l)] = p.src[plain_index(p, p.idx[(uint64_t)(c * G::n_loc + ctx.l) * p.ncp + cell])];
+  __syncthreads();
+  T val[C], rg[C][dim];
+  ctx.evaluate(val, rg);
+  T u2 = 0;
+#pragma unroll
+  for (int c = 0; c < dim; ++c)
+    u2 += val[c] * val[c];
+  // |u| >= 0: the bit pattern of a non-negative double orders like the value
+  __shared__ unsigned long long smax;
+  if (threadIdx.x == 0)
+    smax = 0ull;
+  __syncthreads();
+  const double m = active ? (double)sqrt(u2) : 0.0;
+  atomicMax(&smax, (unsigned long long)__double_as_longlong(m));
+  __syncthreads();
+  if (threadIdx.x == 0)
+    atomicMax(p.max_bits, smax);
+}
+
+// diag(A_cell) by unit vectors (MatrixFreeTools::compute_diagonal, operator_ns.cc:210-218) for
+// cells without weighted constraint rows; cells with weighted rows go through k_diag_columns.
+template <int dim, int n, typename T, int BR>
+__global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_diag_generic(const KParams<T> p, const Shape<T, n> sh,
+                                                                      const uint8_t *__restrict__ skip_cell)
+{
+  using G         = Geo<dim, n>;
+  constexpr int C = G::C;
+  extern __shared__ __align__(16) unsigned char smem[];
+  Ctx<dim, n, T> ctx;
+  ctx.init(smem, sh);
+  const uint32_t cell0  = p.cell_begin + blockIdx.x * G::CPB + ctx.cb;
+  const bool     active = cell0 < p.cell_end;
+  const uint32_t cell   = active ? cell0 : p.cell_end - 1;
+  T              mine[C];
+  for (int j = 0; j < C * G::n_loc; ++j)
+    {
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        ctx.v[ctx.at(c, ctx.l)] = (c * G::n_loc + ctx.l == j) ? T(1) : T(0);
+      __syncthreads();
+      cell_apply<dim, n, T, BR>(ctx, p, sh, cell);
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        if (c * G::n_loc + ctx.l == j)
+          mine[c] = ctx.v[ctx.at(c, ctx.l)];
+    }
+  if (!active || (skip_cell != nullptr && skip_cell[cell]))
+    return;
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    {
+      const uint32_t iv = p.idx[(uint64_t)(c * G::n_loc + ctx.l) * p.ncp + cell];
+      if (!(iv & GLSB_CONSTRAINED_BIT))
+        atomic_add(p.dst + iv, mine[c]);
+    }
+}
+
+// diag(C_cell^T A_cell C_cell) for cells with weighted constraint rows: one CTA handles CPB
+// slots of the same cell list entry; for every global column g of the cell, x = C_cell[:, g],
+// y = A_cell x, diag[g] += x . y.  Column data is CSR built on the host at create time.
+template <int dim, int n, typename T, int BR>
+__global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_diag_columns(const KParams<T> p, const Shape<T, n> sh,
+                                                                      const DiagColumns dc)
+{
+  using G         = Geo<dim, n>;
+  constexpr int C = G::C;
+  extern __shared__ __align__(16) unsigned char smem[];
+  Ctx<dim, n, T> ctx;
+  ctx.init(smem, sh);
+  // all CPB slots of the CTA work on the same cell, slot cb takes columns cb, cb + CPB, ...
+  const uint32_t li   = blockIdx.x;
+  const uint32_t cell = dc.cell[li];
+  const uint32_t c0 = dc.col_ptr[li], c1 = dc.col_ptr[li + 1];
+  const uint32_t nrounds = (c1 - c0 + G::CPB - 1) / G::CPB;
+  for (uint32_t r = 0; r < nrounds; ++r)
+    {
+      const uint32_t col = c0 + r * G::CPB + ctx.cb;
+      const bool     ok  = col < c1;
+      __syncthreads();
+      T x[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        {
+          x[c] = 0;
+          if (ok)
+            for (uint32_t e = dc.ent_ptr[col]; e < dc.ent_ptr[col + 1]; ++e)
+              if (dc.ent_loc[e] == (uint32_t)(c * G::n_loc + ctx.l))
+                x[c] += T(dc.ent_val[e]);
+          ctx.v[ctx.at(c, ctx.l)] = x[c];
+        }
+      __syncthreads();
+      cell_apply<dim, n, T, BR>(ctx, p, sh, cell);
+      T s = 0;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        s += x[c] * ctx.v[ctx.at(c, ctx.l)];
+      if (ok && s != T(0))
+        atomic_add(p.dst + dc.col_dof[col], s);
+    }
+}
+
+} // namespace glsb

@@ -1,0 +1,183 @@
+/* glsb200.h -- C ABI of libglsb200.so: the B200 (sm_100a) implementation of the
+ * matrix-free GLS/SUPG-PSPG Navier-Stokes operator of peterrum/dealii-ns-gls.
+ *
+ * Every entry point replaces one virtual of the reference's OperatorBase<Number>
+ * (include/operator_base.h:13-73) as implemented by NavierStokesOperator<dim,Number>
+ * (include/operator_ns.h:17-189, include/operator_ns.cc); the reference-side
+ * binding (a NavierStokesOperatorB200 subclass that forwards to these calls) is
+ * shown in INTEGRATION.md and dealii_ns_gls_b200/cpp/dealii_adapter.h.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.
+ *   - pointers in glsb_desc are HOST pointers, read during glsb_create() and not
+ *     retained; vectors passed to the compute calls are DEVICE pointers to
+ *     n_owned + n_ghost values of the operator's number type (the layout of
+ *     LinearAlgebra::distributed::Vector: owned block, then ghost block).
+ *   - every compute call enqueues work on the caller's stream (a cudaStream_t
+ *     passed as void*, NULL = default stream) and returns without synchronising
+ *     unless stated otherwise.
+ *   - return value 0 = ok; non-zero = error, text via glsb_last_error().
+ *     (The reference signals errors with AssertThrow, e.g. operator_ns.cc:287.)
+ *   - there is no CPU fallback: glsb_create() fails if no CUDA device is usable.
+ */
+#ifndef GLSB200_H
+#define GLSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLSB_ABI_VERSION 1
+
+typedef struct glsb_op glsb_op;
+
+enum { GLSB_F64 = 0, GLSB_F32 = 1 };
+enum { GLSB_GEOM_CARTESIAN = 0, GLSB_GEOM_GENERAL = 2 };
+enum { GLSB_CELLS_ALL = 0, GLSB_CELLS_INTERIOR = 1, GLSB_CELLS_BOUNDARY = 2 };
+
+/* A dof index with this bit set refers to constraint row (index & 0x7fffffff)
+ * instead of a vector entry (how read_dof_values / distribute_local_to_global
+ * resolve AffineConstraints, operator_ns.cc:819-828). */
+#define GLSB_CONSTRAINED_BIT 0x80000000u
+
+typedef struct glsb_desc
+{
+  int32_t abi_version; /* GLSB_ABI_VERSION */
+  int32_t device;      /* CUDA device ordinal */
+
+  /* discretisation: FESystem(FE_Q(degree), dim+1), QGauss(degree+1)
+   * (main.cc:251, performance.cc:33-38) */
+  int32_t dim;         /* 2 or 3 */
+  int32_t degree;      /* 1..4 */
+  int32_t number_type; /* GLSB_F64 (Krylov operator) or GLSB_F32 (multigrid levels, config.h:6-7) */
+
+  /* operator flags, ctor arguments of NavierStokesOperator (operator_ns.h:24-41) */
+  int32_t increment_form;
+  int32_t consider_time_derivative; /* as passed; the library ANDs it with time_order > 0 (operator_ns.cc:97-98) */
+  int32_t cell_wise_stabilization;
+  int32_t time_order; /* TimeIntegratorData::get_order(): 0 = "none" */
+  double  nu, c1, c2;
+  double  theta; /* TimeIntegratorData::get_theta() */
+
+  /* cells and dofs of this rank (MatrixFree / DoFHandler / Partitioner) */
+  uint64_t        n_cells;
+  uint64_t        n_owned;
+  uint64_t        n_ghost;
+  const uint32_t *dof_indices; /* [n_cells][(dim+1)*(degree+1)^dim], component-blocked,
+                                  lexicographic (x fastest) like FEEvaluation; local vector
+                                  indices, or GLSB_CONSTRAINED_BIT | row */
+
+  /* constraints_homogeneous (MatrixFree constraint index 0, operator_ns.cc:107-108) as CSR rows */
+  uint32_t        n_constraint_rows;
+  const uint32_t *row_dof;   /* [n_rows] vector index of the constrained dof */
+  const uint32_t *row_ptr;   /* [n_rows + 1] */
+  const uint32_t *entry_col; /* master vector indices */
+  const double   *entry_val; /* weights */
+  /* matrix_free.get_constrained_dofs() (operator_ns.cc:123-124): rows where vmult is the identity */
+  uint32_t        n_constrained_indices;
+  const uint32_t *constrained_indices;
+
+  /* geometry (MappingInfo): Cartesian -> inv_jac[n_cells][dim] (diagonal of J^-1),
+   * jxw[n_cells] (det J); general -> inv_jac[n_cells][n_q][dim][dim] with
+   * inv_jac[..][e][j] = (J^-1)_{e j}, jxw[n_cells][n_q] = det J * w_q */
+  int32_t       geometry_type;
+  const double *inv_jac;
+  const double *jxw;
+  /* cell->minimum_vertex_distance() and cell->measure() (operator_ns.cc:373-374, :399) */
+  const double *cell_h_min;
+  const double *cell_measure;
+
+  /* ghost exchange lists of the vector partitioner (owned-local indices this rank
+   * exports, concatenated over neighbours); may be empty */
+  uint64_t        n_export;
+  const uint32_t *export_indices;
+} glsb_desc;
+
+/* ---- life cycle -------------------------------------------------------- */
+
+/* replaces the constructor NavierStokesOperator::NavierStokesOperator (operator_ns.cc:68-153) */
+int  glsb_create(const glsb_desc *desc, glsb_op **out);
+void glsb_destroy(glsb_op *op);
+/* last error text of op (or of the last failed glsb_create when op == NULL) */
+const char *glsb_last_error(const glsb_op *op);
+/* invalidate_system (operator_ns.cc:227-232) */
+int glsb_invalidate_system(glsb_op *op);
+
+/* ---- operator application ---------------------------------------------- */
+
+/* vmult (operator_ns.cc:684-732): dst = A(U) src, identity on constrained rows.
+ * weight = time_integrator_data.get_primary_weight(), read at call time like
+ * the reference does (operator_ns.cc:958, :1071).  Single-rank form: zeroes dst,
+ * loops over all cells, copies the constrained rows. */
+int glsb_vmult(glsb_op *op, void *dst, const void *src, double weight, void *stream);
+
+/* The three pieces of cell_loop(..., zero_dst = true) for the host layer that
+ * overlaps the ghost exchange with the interior cells (operator_ns.cc:703-708):
+ *   glsb_vmult_begin  : zero dst (owned + ghost)
+ *   glsb_vmult_cells  : which = GLSB_CELLS_INTERIOR (cells without ghost dofs),
+ *                       GLSB_CELLS_BOUNDARY or GLSB_CELLS_ALL
+ *   glsb_vmult_finish : dst[constrained] = src[constrained] (operator_ns.cc:719-721) */
+int glsb_vmult_begin(glsb_op *op, void *dst, void *stream);
+int glsb_vmult_cells(glsb_op *op, void *dst, const void *src, double weight, int which, void *stream);
+int glsb_vmult_finish(glsb_op *op, void *dst, const void *src, void *stream);
+
+/* evaluate_residual (operator_ns.cc:648-682): src must already carry the
+ * inhomogeneous boundary values (constraints_inhomogeneous.distribute, :655-656)
+ * and imported ghost values; dst = -(C^T F(src)), zero on constrained rows.
+ * evaluate_rhs (:622-646) is the same call on distribute(0). */
+int glsb_evaluate_residual(glsb_op *op, void *dst, const void *src_with_bc, double weight, void *stream);
+int glsb_evaluate_residual_cells(glsb_op *op, void *dst, const void *src_with_bc, double weight,
+                                 int which, void *stream);
+
+/* ---- state -------------------------------------------------------------- */
+
+/* set_linearization_point (operator_ns.cc:570-620) + compute_penalty_parameters
+ * (:322-420): vec with imported ghost values; dt = get_current_dt(). */
+int glsb_set_linearization_point(glsb_op *op, const void *vec, double dt, void *stream);
+
+/* set_previous_solution (operator_ns.cc:234-320): history[i], i = 0..order, device
+ * vectors with imported ghosts; weights = get_weights(). No-op if time_order == 0. */
+int glsb_set_previous_solution(glsb_op *op, const void *const *history, const double *weights,
+                               int order, void *stream);
+
+/* compute_inverse_diagonal (operator_ns.cc:195-225): diag = (|d| > 1e-10 ? 1/d : 1) of
+ * diag(C^T A C), 1 on constrained rows.  With ghosts, call glsb_diagonal_cells then
+ * compress(add) then glsb_diagonal_finish. */
+int glsb_compute_inverse_diagonal(glsb_op *op, void *diag, double weight, void *stream);
+int glsb_diagonal_cells(glsb_op *op, void *diag, double weight, void *stream);
+int glsb_diagonal_finish(glsb_op *op, void *diag, void *stream);
+
+/* get_max_u (operator_ns.cc:530-568): max over the local quadrature points of |u|;
+ * synchronises the stream; the MPI::max over ranks stays with the caller. */
+int glsb_get_max_u(glsb_op *op, const void *vec, double *out_host, void *stream);
+
+/* ---- ghost exchange helpers (update_ghost_values / compress(add)) ------- */
+
+/* buf[i] = vec[export_indices[i]] */
+int glsb_pack_export(glsb_op *op, void *buf, const void *vec, void *stream);
+/* vec[export_indices[i]] += buf[i] */
+int glsb_unpack_add(glsb_op *op, void *vec, const void *buf, void *stream);
+
+/* ---- introspection (used by tests and the bench) ------------------------ */
+
+uint64_t glsb_n_cells(const glsb_op *op);
+uint64_t glsb_n_local(const glsb_op *op);     /* n_owned + n_ghost */
+uint64_t glsb_n_interior_cells(const glsb_op *op);
+/* copy a q-point table to a device buffer as [field][cell][q] in the caller's cell order;
+ * name: "u_star_value", "u_star_gradient", "p_star_gradient", "u_time_derivative_old",
+ * "delta_1", "delta_2", "delta_1_q", "delta_2_q" (operator_ns.h:114-132) */
+int glsb_get_table(glsb_op *op, const char *name, void *out_dev, uint64_t out_count, void *stream);
+/* kernel launches issued by this operator so far */
+uint64_t glsb_launch_count(const glsb_op *op);
+/* name of the kernel variant used for vmult ("generic" / "q2_regtile" ...) */
+const char *glsb_vmult_variant(const glsb_op *op);
+/* force a variant (testing): 0 = auto, 1 = generic */
+int glsb_set_variant(glsb_op *op, int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLSB200_H */

@@ -1,0 +1,86 @@
+"""CPU-side checks of the drop-in boundary: the library loads, exports every symbol
+include/glsb200.h declares, and fails loudly (no CPU fallback) without a device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from dealii_ns_gls_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ensure_built():
+    if not os.path.exists(L.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+
+
+def test_header_symbols_are_exported_and_bound():
+    _ensure_built()
+    hdr = open(os.path.join(ROOT, "include", "glsb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(glsb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    assert declared == set(L.SYMBOLS), (declared ^ set(L.SYMBOLS))
+    lib = L.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_desc_struct_matches_header_field_order():
+    hdr = open(os.path.join(ROOT, "include", "glsb200.h")).read()
+    body = hdr[hdr.index("typedef struct glsb_desc"):hdr.index("} glsb_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = decl.split("{")[-1]
+        for part in decl.split(","):
+            m = re.search(r"\*?\s*([A-Za-z_0-9]+)\s*$", part.strip())
+            if m:
+                names.append(m.group(1))
+    assert names == [f[0] for f in L.GlsbDesc._fields_]
+
+
+def test_create_fails_loudly_without_device_or_with_bad_desc():
+    _ensure_built()
+    lib = L.load()
+    d = L.GlsbDesc()
+    h = C.c_void_p()
+    d.abi_version = 99
+    assert lib.glsb_create(C.byref(d), C.byref(h)) != 0
+    assert b"ABI" in lib.glsb_last_error(None)
+    d.abi_version = L.GLSB_ABI_VERSION
+    d.dim = 5
+    assert lib.glsb_create(C.byref(d), C.byref(h)) != 0
+    assert b"dim" in lib.glsb_last_error(None)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        d.dim, d.degree, d.n_cells, d.n_owned = 2, 1, 1, 12
+        assert lib.glsb_create(C.byref(d), C.byref(h)) != 0
+        assert b"no CUDA device" in lib.glsb_last_error(None)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            from dealii_ns_gls_b200.operator import NavierStokesOperator
+            NavierStokesOperator(None, None, 0.1, 4, 2, None, False, True, True)
+
+
+def test_time_integrator_mirror_matches_oracle():
+    from dealii_ns_gls_b200.time_integration import TimeIntegratorDataBDF, TimeIntegratorDataNone
+    from oracle.gls_oracle import OracleBDF
+    for order in (1, 2, 3):
+        a, b = TimeIntegratorDataBDF(order), OracleBDF(order)
+        for dt in (0.1, 0.07, 0.2, 0.05):
+            a.update_dt(dt)
+            b.update_dt(dt)
+            assert a.get_weights() == b.weights
+            assert a.get_current_dt() == b.current_dt
+    n = TimeIntegratorDataNone()
+    assert (n.get_order(), n.get_primary_weight(), n.get_current_dt(), n.get_theta()) == (0, 0.0, 1.0, 1.0)

@@ -1,0 +1,215 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against the
+CPU oracle on the same seeded inputs.  Tolerances: 1e-12 relative l2 in FP64 (the
+north-star bar), 2e-5 in FP32 (multigrid level operators, config.h:7)."""
+import numpy as np
+import pytest
+
+from dealii_ns_gls_b200 import mesh as gm
+from tests.util import TI, make_gpu, make_oracle, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"double": 1e-12, "float": 2e-5}
+NPDT = {"double": np.float64, "float": np.float32}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _to_dev(a, number):
+    torch = _torch()
+    return torch.tensor(np.asarray(a), dtype=torch.float64 if number == "double" else torch.float32, device="cuda")
+
+
+def _mesh(kind, dim, degree, **kw):
+    if kind == "cube":
+        return gm.hypercube(dim, 4 if dim == 2 else 3, degree, **kw)
+    shape = (3, 6) if dim == 2 else (2, 5, 2)
+    return gm.cylinder_shell(shape, degree, **kw)
+
+
+def _setup(mesh, ti, number, seed=1234, **flags):
+    rng = np.random.default_rng(seed)
+    ora = make_oracle(mesh, ti, dtype=NPDT[number], **flags)
+    gpu = make_gpu(mesh, ti, number=number, **flags)
+    hist = [rng.uniform(-1, 1, mesh.n_dofs) for _ in range(ti.get_order() + 1)]
+    lin = rng.uniform(-1, 1, mesh.n_dofs)
+    src = rng.uniform(-1, 1, mesh.n_dofs)
+    if ti.get_order() > 0:
+        ora.set_previous_solution(hist, ti.get_weights())
+        gpu.set_previous_solution([_to_dev(h, number) for h in hist])
+    ora.set_linearization_point(lin, ti.get_current_dt())
+    gpu.set_linearization_point(_to_dev(lin, number))
+    return ora, gpu, src, rng
+
+
+@pytest.mark.parametrize("number", ["double", "float"])
+@pytest.mark.parametrize("kind", ["cube", "shell"])
+@pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (2, 3), (2, 4), (3, 1), (3, 2), (3, 3), (3, 4)])
+def test_vmult_newton(dim, degree, kind, number):
+    """performance.cc flags (cell-wise delta, no time derivative) on random vectors."""
+    mesh = _mesh(kind, dim, degree)
+    ti = TI(2, [10.0, -10.0, 0.0], 0.1)
+    ora, gpu, src, _ = _setup(mesh, ti, number)
+    ref = ora.vmult(src, 10.0)
+    dst = gpu.initialize_dof_vector()
+    gpu.vmult(dst, _to_dev(src, number))
+    assert rel_l2(dst.cpu().numpy(), ref) < TOL[number]
+
+
+@pytest.mark.parametrize("number", ["double", "float"])
+@pytest.mark.parametrize("dim,degree", [(2, 2), (3, 2), (3, 3)])
+def test_vmult_newton_turek_flags(dim, degree, number):
+    """input_turek_3D_Re100.json flags: BDF2, time derivative in the stabilization,
+    q-point-wise delta, curved cells, no-slip rows."""
+    mesh = _mesh("shell", dim, degree)
+    ti = TI(2, [15.0, -20.0, 5.0], 0.1)
+    ora, gpu, src, _ = _setup(mesh, ti, number, ctd=True, cell_wise=False, nu=0.001)
+    ref = ora.vmult(src, 15.0)
+    dst = gpu.initialize_dof_vector()
+    gpu.vmult(dst, _to_dev(src, number))
+    assert rel_l2(dst.cpu().numpy(), ref) < TOL[number]
+    cons = np.array(sorted(mesh.constraints.keys()))
+    assert np.array_equal(dst.cpu().numpy()[cons], src.astype(NPDT[number])[cons])  # identity rows, bit-exact
+
+
+@pytest.mark.parametrize("number", ["double", "float"])
+@pytest.mark.parametrize("name", ["u_star_value", "u_star_gradient", "p_star_gradient", "u_time_derivative_old",
+                                  "delta_1", "delta_2", "delta_1_q", "delta_2_q"])
+def test_tables(name, number):
+    mesh = _mesh("shell", 3, 2)
+    ti = TI(2, [15.0, -20.0, 5.0], 0.1)
+    ora, gpu, _, _ = _setup(mesh, ti, number, ctd=True, cell_wise=False, nu=0.001)
+    d = mesh.dim
+    got = gpu.get_table(name).cpu().numpy()
+    K = mesh.n_cells
+    ref = {"u_star_value": lambda: ora.U.transpose(1, 0, 2),
+           "u_star_gradient": lambda: ora.H.reshape(K, d * d, -1).transpose(1, 0, 2),
+           "p_star_gradient": lambda: ora.P.transpose(1, 0, 2),
+           "u_time_derivative_old": lambda: ora.o.transpose(1, 0, 2),
+           "delta_1": lambda: ora.delta1_cell.reshape(1, K, 1),
+           "delta_2": lambda: ora.delta2_cell.reshape(1, K, 1),
+           "delta_1_q": lambda: ora.delta1_q.reshape(1, K, -1),
+           "delta_2_q": lambda: ora.delta2_q.reshape(1, K, -1)}[name]()
+    assert rel_l2(got, ref) < TOL[number]
+
+
+@pytest.mark.parametrize("number", ["double", "float"])
+@pytest.mark.parametrize("dim,degree", [(2, 1), (3, 2)])
+@pytest.mark.parametrize("theta", [1.0, 0.5])
+def test_fixed_point_and_residual(dim, degree, theta, number):
+    """!increment_form vmult and evaluate_residual (operator_ns.cc:955-1066), BDF and theta schemes."""
+    mesh = _mesh("shell", dim, degree)
+    ti = TI(2, [15.0, -20.0, 5.0], 0.1) if theta == 1.0 else TI(1, [10.0, -10.0], 0.1, theta=theta)
+    ora, gpu, src, _ = _setup(mesh, ti, number, ctd=(theta == 1.0), cell_wise=False, increment_form=False)
+    ref = ora.vmult(src, ti.get_primary_weight())
+    dst = gpu.initialize_dof_vector()
+    gpu.vmult(dst, _to_dev(src, number))
+    assert rel_l2(dst.cpu().numpy(), ref) < TOL[number]
+    # residual: src with boundary values already distributed (zero-type rows: src entries = 0)
+    sb = src.copy()
+    sb[list(mesh.constraints.keys())] = 0.0
+    ref_r = ora.evaluate_residual(sb, ti.get_primary_weight())
+    gpu.evaluate_residual(dst, _to_dev(sb, number))
+    assert rel_l2(dst.cpu().numpy(), ref_r) < TOL[number]
+
+
+@pytest.mark.parametrize("number", ["double", "float"])
+def test_residual_increment_form(number):
+    """Newton configuration: vmult = linearized branch, residual = fixed-point branch (Appendix A)."""
+    mesh = _mesh("shell", 3, 2)
+    ti = TI(2, [15.0, -20.0, 5.0], 0.1)
+    ora, gpu, src, _ = _setup(mesh, ti, number, ctd=True, cell_wise=False, increment_form=True)
+    ref_r = ora.evaluate_residual(src, 15.0)
+    dst = gpu.initialize_dof_vector()
+    gpu.evaluate_residual(dst, _to_dev(src, number))
+    assert rel_l2(dst.cpu().numpy(), ref_r) < TOL[number]
+
+
+@pytest.mark.parametrize("number", ["double", "float"])
+@pytest.mark.parametrize("dim,degree,kind", [(2, 2, "cube"), (3, 2, "shell"), (3, 1, "cube")])
+def test_weighted_constraints_and_component_numbering(dim, degree, kind, number):
+    """General affine rows (hanging-node-like) + component-major numbering (general index path)."""
+    mesh = _mesh(kind, dim, degree, numbering="component")
+    gm.add_random_constraints(mesh, n_weighted=12, n_zero=7, seed=11)
+    ti = TI(2, [10.0, -10.0, 0.0], 0.1)
+    ora, gpu, src, _ = _setup(mesh, ti, number)
+    ref = ora.vmult(src, 10.0)
+    dst = gpu.initialize_dof_vector()
+    gpu.vmult(dst, _to_dev(src, number))
+    assert rel_l2(dst.cpu().numpy(), ref) < TOL[number]
+    ref_r = ora.evaluate_residual(src, 10.0)
+    gpu.evaluate_residual(dst, _to_dev(src, number))
+    assert rel_l2(dst.cpu().numpy(), ref_r) < TOL[number]
+
+
+@pytest.mark.parametrize("number", ["double", "float"])
+@pytest.mark.parametrize("dim,degree,kind,constrained", [(2, 1, "cube", False), (2, 3, "shell", True),
+                                                         (3, 2, "cube", True), (3, 2, "shell", False)])
+def test_inverse_diagonal(dim, degree, kind, constrained, number):
+    mesh = _mesh(kind, dim, degree)
+    if constrained:
+        gm.add_random_constraints(mesh, n_weighted=8, n_zero=5, seed=5)
+    ti = TI(2, [15.0, -20.0, 5.0], 0.1)
+    ora, gpu, _, _ = _setup(mesh, ti, number, ctd=True, cell_wise=False)
+    ref = ora.compute_inverse_diagonal(15.0)
+    diag = gpu.initialize_dof_vector()
+    gpu.compute_inverse_diagonal(diag)
+    assert rel_l2(diag.cpu().numpy(), ref) < (1e-11 if number == "double" else 5e-5)
+
+
+@pytest.mark.parametrize("number", ["double", "float"])
+def test_get_max_u(number):
+    mesh = _mesh("shell", 3, 2)
+    ti = TI(0, [], 1.0)
+    ora, gpu, src, _ = _setup(mesh, ti, number)
+    got = gpu.get_max_u(_to_dev(src, number))
+    assert abs(got - ora.get_max_u(src)) < TOL[number] * 10
+
+
+def test_stationary_configuration():
+    """'time intration: none' => order 0, weight 0, dt 1 (time_integration.cc:141-178)."""
+    mesh = _mesh("shell", 2, 2)
+    ti = TI(0, [], 1.0)
+    ora, gpu, src, _ = _setup(mesh, ti, "double", ctd=True, cell_wise=False)
+    ref = ora.vmult(src, 0.0)
+    dst = gpu.initialize_dof_vector()
+    gpu.vmult(dst, _to_dev(src, "double"))
+    assert rel_l2(dst.cpu().numpy(), ref) < 1e-12
+
+
+def test_errors_are_loud():
+    from dealii_ns_gls_b200._lib import GlsbError
+    mesh = _mesh("cube", 2, 1)
+    gpu = make_gpu(mesh, TI(2, [10.0, -10.0, 0.0], 0.1))
+    v = gpu.initialize_dof_vector()
+    with pytest.raises(GlsbError, match="set_linearization_point"):
+        gpu.vmult(v, v.clone())
+    with pytest.raises(ValueError):
+        gpu.vmult(v[:-1], v)
+
+
+def test_vmult_linearity_and_repeatability_large():
+    """Size-independent properties at a size the oracle does not reach: linearity and
+    zero -> zero (the reference's own benchmark vectors, performance.cc:66-79)."""
+    torch = _torch()
+    mesh = gm.hypercube(3, 24, 2)
+    ti = TI(2, [10.0, -10.0, 0.0], 0.1)
+    gpu = make_gpu(mesh, ti)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    lin = torch.rand(mesh.n_dofs, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    gpu.set_linearization_point(lin)
+    x = torch.rand(mesh.n_dofs, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    y = torch.rand(mesh.n_dofs, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    ax, ay, axy, z = (gpu.initialize_dof_vector() for _ in range(4))
+    gpu.vmult(ax, x)
+    gpu.vmult(ay, y)
+    gpu.vmult(axy, 2.0 * x - 3.0 * y)
+    assert float(torch.linalg.norm(axy - (2.0 * ax - 3.0 * ay)) / torch.linalg.norm(axy)) < 1e-13
+    gpu.vmult(z, torch.zeros_like(x))
+    assert float(z.abs().max()) == 0.0
+    ax2 = gpu.initialize_dof_vector()
+    gpu.vmult(ax2, x)
+    assert float(torch.linalg.norm(ax2 - ax) / torch.linalg.norm(ax)) < 1e-14
