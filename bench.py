@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- GLS Navier-Stokes operator vmult throughput (GDoF/s), the reference's
+performance.cc recipe re-created on synthetic meshes.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
+                                                           # algorithm on the host cores
+
+A "step" is one operator application (vmult) on the configured mesh.  At N = 1 the workload
+is BASELINE.json's config "performance.cc synthetic 3D hypercube operator vmult, degree 2":
+Cartesian cells, no constraints, nu = 0.1, c1 = 4, c2 = 2, BDF(2) after one update_dt(0.1)
+(weight 10), Newton form, cell-wise stabilization, no time-derivative term
+(performance.cc:16-24, :44-62), with >= 1e8 DoFs per GPU and random vectors (seed 1234)
+instead of the reference's zero vectors.  N > 1: weak scaling, one box of the same size per
+rank stacked in z, ghost planes exchanged over NCCL (update_ghost_values / compress(add)).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+NU, C1, C2, DT = 0.1, 4.0, 2.0, 0.1
+SEED = 1234
+
+
+def algorithmic_bytes_per_cell(dim, degree, number_bytes, *, newton=True, ctd=False, q_wise=False,
+                               general=False):
+    """SURVEY.md section 8d / BASELINE.md section 3: the contract figure."""
+    n_q = (degree + 1) ** dim
+    C = dim + 1
+    T_U = dim * dim + 2 * dim if newton else dim
+    T_t = dim if ctd else 0
+    T_dq = 2 if q_wise else 0
+    T_G = dim * dim + 1 if general else 0
+    T_cell = (0 if q_wise else 2) + (0 if general else dim + 1)
+    D_cell = C * degree ** dim
+    s = number_bytes
+    return s * (n_q * (T_U + T_t + T_dq + T_G) + T_cell) + 4 * C * n_q + 2 * s * D_cell
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.active = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            if self.active.is_set():
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the C restatement of the reference algorithm on the host cores
+# --------------------------------------------------------------------------------------
+def cpu_vmult_gdofs(cells_per_dir, degree, steps, warmup, budget_s=25.0):
+    """Time oracle/gls_oracle_c on a bounded sample of the workload (same flags, smaller cube)."""
+    from dealii_ns_gls_b200 import mesh as gm
+    from oracle import gls_oracle as go
+    from oracle.gls_oracle_c import COracle, max_threads
+
+    mesh = gm.hypercube(3, cells_per_dir, degree)
+    K = mesh.n_cells
+    rng = np.random.default_rng(SEED)
+    ora = go.OracleOperator(dim=3, degree=degree, cell_dofs=mesh.cell_dofs, n_dofs=mesh.n_dofs,
+                            cell_points=mesh.cell_points, mapping_degree=1, constraints={}, nu=NU, c1=C1,
+                            c2=C2, theta=1.0, order=2, consider_time_derivative=False, increment_form=True,
+                            cell_wise_stabilization=True, path="sumfac")
+    ora.set_linearization_point(rng.uniform(-1, 1, mesh.n_dofs), DT)
+    basis = ora.tb.b
+    co = COracle(dim=3, degree=degree, cell_dofs=mesh.cell_dofs, n_dofs=mesh.n_dofs, S=basis.S, D=basis.D,
+                 w=basis.wq, cartesian=True, inv_jac=mesh.cart_inv_jac, jxw=mesh.cart_det, nu=NU, theta=1.0,
+                 branch=COracle.BR_NEWTON, ctd=False, cell_wise=True)
+    co.set_tables(ora.U, ora.H.reshape(K, 9, -1), ora.P, None, None, None,
+                  ora.delta1_cell.reshape(K, 1), ora.delta2_cell.reshape(K, 1))
+    del ora
+    src = rng.uniform(-1, 1, mesh.n_dofs)
+    dst = np.empty_like(src)
+    nt = max_threads()
+    for _ in range(max(1, warmup)):
+        co.apply_into(dst, src, 10.0, nt)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        co.apply_into(dst, src, 10.0, nt)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=mesh.n_dofs * done / dt / 1e9, steps=done, seconds=dt, cores=nt, n_dofs=mesh.n_dofs,
+                sample=f"{cells_per_dir}^3 cells Q{degree} hypercube ({mesh.n_dofs} DoFs), {done} vmults, "
+                       f"{nt} OpenMP threads, same flags as the GPU workload")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_vmult_gdofs(args.cpu_cells, args.degree, args.steps, args.warmup, budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": "GLS NS operator vmult throughput", "value": r["value"], "unit": "GDoF/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
+        "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": r["value"], "unit": "GDoF/s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement of the reference algorithm (oracle/gls_oracle_c.c), not deal.II: the "
+                "reference cannot be built without deal.II/p4est/Trilinos/MPI",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n_gpus):
+    return {"workload": f"performance.cc: 3D hypercube, Q{args.degree}, {args.cells}^3 cells per GPU, "
+                        "Cartesian, no constraints, Newton form, cell-wise delta, BDF2 weight 10, "
+                        "random U/src seed 1234",
+            "cells_per_gpu": args.cells ** 3, "degree": args.degree, "dim": 3,
+            "parallelism": f"domain decomposition, {n_gpus} z-slab(s)",
+            "l2_policy": "inputs larger than L2 (tables + vectors >> 126 MB), no flush"}
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from dealii_ns_gls_b200 import mesh as gm
+    from dealii_ns_gls_b200.operator import NavierStokesOperator
+    from dealii_ns_gls_b200.time_integration import TimeIntegratorDataBDF
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    exchange = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from dealii_ns_gls_b200.distributed import GhostExchange
+        mesh = gm.hypercube_slab(args.cells, args.degree, n_ranks=world, rank=rank)
+        exchange = GhostExchange(mesh.partition, dev)
+    else:
+        mesh = gm.hypercube(3, args.cells, args.degree)
+
+    ti = TimeIntegratorDataBDF(2)
+    ti.update_dt(DT)  # performance.cc:44-46: weights (10, -10, 0)
+    op = NavierStokesOperator(mesh, None, NU, C1, C2, ti, False, True, True, number="double", device=dev,
+                              exchange=exchange)
+    n_local, n_owned = mesh.n_dofs, mesh.n_owned
+    n_global = mesh.n_global_dofs
+    n_cells = mesh.n_cells
+    del mesh
+
+    g = torch.Generator(device=dev).manual_seed(SEED + rank)
+    hist = [torch.zeros(n_local, dtype=torch.float64, device=dev) for _ in range(3)]
+    op.set_previous_solution(hist)  # performance.cc:66-69
+    del hist
+    lin = torch.rand(n_local, dtype=torch.float64, device=dev, generator=g) * 2 - 1
+    op.set_linearization_point(lin)
+    del lin
+    src = torch.rand(n_local, dtype=torch.float64, device=dev, generator=g) * 2 - 1
+    if n_local > n_owned:
+        src[n_owned:] = 0
+    dst = op.initialize_dof_vector()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- device-resident timed region -------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        op.vmult(dst, src)
+    barrier()
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = op.launch_count()
+    sampler.active.set()
+    e0.record()
+    for i in range(args.steps):
+        op.vmult(dst, src, kernel_events=k_ev[i])
+    e1.record()
+    barrier()
+    sampler.active.clear()
+    launches = op.launch_count() - l0
+    t_ms = e0.elapsed_time(e1)
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    checksum = float(dst[:n_owned].double().abs().sum())
+
+    # ---- end to end: host vectors in, host vector out, every step ----------------------
+    h_src = torch.empty(n_local, dtype=torch.float64, pin_memory=True)
+    h_dst = torch.empty(n_local, dtype=torch.float64, pin_memory=True)
+    h_src.copy_(src)
+    e2e_steps = max(2, min(args.steps, 10))
+    for _ in range(2):
+        op.vmult_host(h_dst, h_src)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.active.set()
+    f0.record()
+    for _ in range(e2e_steps):
+        op.vmult_host(h_dst, h_src)
+    f1.record()
+    barrier()
+    sampler.active.clear()
+    sampler.stop()
+    e2e_ms = f0.elapsed_time(f1)
+
+    if world > 1:
+        t = torch.tensor([t_ms, e2e_ms, k_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms, e2e_ms, k_ms = [float(x) for x in t]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    peaks_src = "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+        peaks_src = "measured"
+    except Exception:
+        peaks = {"hbm_gbs": 6650.0}
+    bpc = algorithmic_bytes_per_cell(3, args.degree, 8)
+    achieved = n_cells * bpc / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr_path):
+        try:
+            with open(tr_path) as f:
+                tj = json.load(f)
+            if tj.get("cells") == n_cells:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    value = n_global * args.steps / (t_ms * 1e-3) / 1e9
+    line = {
+        "metric": "GLS NS operator vmult throughput", "value": value, "unit": "GDoF/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": t_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(workload_config(args, world), n_dofs_global=n_global, kernel_variant=op.vmult_variant(),
+                       checksum_abs_sum=checksum),
+        "e2e": {"value": n_global * e2e_steps / (e2e_ms * 1e-3) / 1e9, "unit": "GDoF/s",
+                "h2d_bytes_per_step": n_local * 8, "d2h_bytes_per_step": n_local * 8, "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                     "frac": achieved / peaks.get("hbm_gbs"), "traffic": traffic,
+                     "peak_source": peaks_src, "kernel": op.vmult_variant(), "kernel_ms": k_ms,
+                     "algorithmic_bytes_per_cell": bpc, "cells_per_launch": n_cells},
+        "clocks": sampler.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_vmult_gdofs(args.cpu_cells, args.degree, 10, 2)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "GDoF/s", "cores": r["cores"], "kind": "port",
+                                "sample": r["sample"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=160, help="cells per direction per GPU (160 -> 1.32e8 DoFs)")
+    ap.add_argument("--degree", type=int, default=2)
+    ap.add_argument("--cpu-cells", type=int, default=64, help="cells per direction of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

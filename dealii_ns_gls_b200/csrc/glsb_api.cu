@@ -701,8 +701,7 @@ int glsb_vmult_begin(glsb_op *op, void *dst, void *stream)
     return fail(op, "glsb_vmult_begin: null argument");
   if (cudaMemsetAsync(dst, 0, (op->n_owned + op->n_ghost) * op->tsize, (cudaStream_t)stream) != cudaSuccess)
     return cuda_fail(op, "glsb_vmult_begin: memset");
-  op->launches++;
-  return 0;
+  return 0; // a memset node, not one of our kernels: not counted in launches
 }
 
 int glsb_vmult_cells(glsb_op *op, void *dst, const void *src, double weight, int which, void *stream)

@@ -215,16 +215,21 @@ def structured_mesh(dim, shape, degree, *, deform=None, mapping_degree=1, period
     owned_lo = owned_off_nodes[rank] * C
     owned_hi = owned_off_nodes[rank + 1] * C
     n_owned = int(owned_hi - owned_lo)
-    uniq = np.unique(cell_gdofs)
-    ghosts = uniq[(uniq < owned_lo) | (uniq >= owned_hi)]
-    n_ghost = len(ghosts)
-    # local index map
-    is_owned = (cell_gdofs >= owned_lo) & (cell_gdofs < owned_hi)
-    local = np.where(is_owned, cell_gdofs - owned_lo, 0)
-    if n_ghost:
-        gpos = np.searchsorted(ghosts, cell_gdofs)
-        gpos = np.clip(gpos, 0, n_ghost - 1)
-        local = np.where(is_owned, local, n_owned + gpos)
+    if n_ranks == 1:
+        ghosts = np.zeros(0, dtype=np.int64)
+        n_ghost = 0
+        local = cell_gdofs
+    else:
+        uniq = np.unique(cell_gdofs)
+        ghosts = uniq[(uniq < owned_lo) | (uniq >= owned_hi)]
+        n_ghost = len(ghosts)
+        # local index map
+        is_owned = (cell_gdofs >= owned_lo) & (cell_gdofs < owned_hi)
+        local = np.where(is_owned, cell_gdofs - owned_lo, 0)
+        if n_ghost:
+            gpos = np.searchsorted(ghosts, cell_gdofs)
+            gpos = np.clip(gpos, 0, n_ghost - 1)
+            local = np.where(is_owned, local, n_owned + gpos)
     n_local = n_owned + n_ghost
 
     part = None
@@ -255,7 +260,11 @@ def structured_mesh(dim, shape, degree, *, deform=None, mapping_degree=1, period
     ref = origin[None, None, :] + (cc[my_cells][:, None, :] + mp[mloc][None, :, :]) * hcell[None, None, :]
     pts = deform(ref) if deform is not None else ref
     verts_idx = [sum((k * ((v >> e) & 1)) * (k + 1) ** e for e in range(dim)) for v in range(2 ** dim)]
-    h_min, meas = _vertex_geometry(pts[:, verts_idx, :], dim)
+    if deform is None:
+        h_min = np.full(ncell_loc, float(hcell.min()))
+        meas = np.full(ncell_loc, float(np.prod(hcell)))
+    else:
+        h_min, meas = _vertex_geometry(pts[:, verts_idx, :], dim)
 
     mesh = Mesh(dim=dim, degree=p, n_cells=ncell_loc, n_dofs=n_local, n_owned=n_owned,
                 cell_dofs=local.astype(index_dtype), geometry_type=0 if deform is None else 2,

@@ -230,14 +230,22 @@ class NavierStokesOperator:
     def invalidate_system(self):
         self._chk(self._lib.glsb_invalidate_system(self._op), "invalidate_system")
 
-    def vmult(self, dst: torch.Tensor, src: torch.Tensor):
-        """operator_ns.cc:684-732."""
+    def vmult(self, dst: torch.Tensor, src: torch.Tensor, kernel_events=None):
+        """operator_ns.cc:684-732.  kernel_events = (start, end) torch.cuda.Event pair recorded
+        around the cell kernel on the launching stream (bench.py's roofline timing)."""
         w = self.time_integrator_data.get_primary_weight()
         s = self._stream()
-        if self.exchange is None:
+        if self.exchange is not None:
+            self.exchange.vmult(self, dst, src, w, kernel_events)
+        elif kernel_events is None:
             self._chk(self._lib.glsb_vmult(self._op, self._vec(dst, "dst"), self._vec(src, "src"), w, s), "vmult")
         else:
-            self.exchange.vmult(self, dst, src, w)
+            d, x = self._vec(dst, "dst"), self._vec(src, "src")
+            self._chk(self._lib.glsb_vmult_begin(self._op, d, s), "vmult")
+            kernel_events[0].record()
+            self._chk(self._lib.glsb_vmult_cells(self._op, d, x, w, L.GLSB_CELLS_ALL, s), "vmult")
+            kernel_events[1].record()
+            self._chk(self._lib.glsb_vmult_finish(self._op, d, x, s), "vmult")
 
     def Tvmult(self, dst, src):
         """operator_base.cc:12-18: Tvmult forwards to vmult."""

@@ -242,3 +242,25 @@ def test_rank_count_invariance():
         cons = np.array(sorted(full.constraints.keys()))
         acc[cons] = src_g[cons]
         assert np.linalg.norm(acc - ref) <= 1e-13 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("dim,degree", [(2, 1), (2, 4), (3, 2), (3, 3)])
+@pytest.mark.parametrize("branch", [0, 1, 2])
+def test_c_restatement_matches_numpy_oracle(dim, degree, branch):
+    """Third, independently written path: C, SIMD over cell batches, OpenMP, atomics on shared dofs."""
+    from oracle.gls_oracle_c import COracle
+    m = gm.cylinder_shell((3, 5) if dim == 2 else (2, 5, 3), degree, no_slip=False)
+    rng = np.random.default_rng(3)
+    theta = 0.5 if branch else 1.0
+    op = make_op(m, theta=theta, order=1 if branch else 2, consider_time_derivative=(branch == 0),
+                 increment_form=(branch == 0), cell_wise_stabilization=(branch == 1), path="naive")
+    hist = [rng.standard_normal(m.n_dofs) for _ in range(3)]
+    op.set_previous_solution(hist, [15.0, -20.0, 5.0] if branch == 0 else [10.0, -10.0])
+    op.set_linearization_point(rng.standard_normal(m.n_dofs), 0.1)
+    src = rng.standard_normal(m.n_dofs)
+    w = 15.0 if branch == 0 else 10.0
+    ref = op._scatter(op._apply_cells(op._gather(src), w, residual=(branch == 2)))
+    co = COracle.from_numpy_oracle(op, branch)
+    for nt in (1, 3):
+        got = co.apply(src, w, n_threads=nt)
+        assert np.linalg.norm(got - ref) <= 1e-13 * np.linalg.norm(ref)
