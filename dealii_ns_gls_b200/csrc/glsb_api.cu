@@ -58,8 +58,7 @@ __global__ void k_transpose_idx(const uint32_t *__restrict__ raw, const uint32_t
   if (t >= (uint64_t)ndof * ncp)
     return;
   const uint32_t i = t % ncp, d = t / ncp;
-  const uint32_t c = i < n_cells ? i : n_cells - 1; // padding repeats the last cell
-  out[t]           = raw[(uint64_t)perm[c] * ndof + d];
+  out[t]           = raw[(uint64_t)perm[i] * ndof + d]; // perm is defined for every slot (padding repeats a cell)
 }
 
 // general geometry [cell][q][e][j] (double) -> [e*dim+j][q][ncp] (T); jxw [cell][q] -> [q][ncp]
@@ -75,8 +74,7 @@ __global__ void k_transpose_geom(const double *__restrict__ raw, const uint32_t 
   const uint32_t i = t % ncp;
   const uint64_t r = t / ncp;
   const uint32_t q = r % per_cell_q, f = r / per_cell_q;
-  const uint32_t c = i < n_cells ? i : n_cells - 1;
-  out[t]           = (T)raw[((uint64_t)perm[c] * per_cell_q + q) * inner + f];
+  out[t]           = (T)raw[((uint64_t)perm[i] * per_cell_q + q) * inner + f];
 }
 
 template <typename T>
@@ -127,13 +125,16 @@ __global__ void k_invert_guarded(T *__restrict__ v, uint64_t n)
 // table [f][q][ncp] (internal cell order) -> out [f][cell][q] (caller's order)
 template <typename T>
 __global__ void k_export_table(const T *__restrict__ tab, const uint32_t *__restrict__ perm, T *__restrict__ out,
-                               uint32_t n_cells, uint32_t nq, uint32_t nf, uint64_t ncp)
+                               uint32_t n_cells, uint32_t n_slots, uint32_t hole_begin, uint32_t hole_end,
+                               uint32_t nq, uint32_t nf, uint64_t ncp)
 {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (uint64_t)nf * nq * n_cells)
+  if (t >= (uint64_t)nf * nq * n_slots)
     return;
-  const uint32_t i = t % n_cells;
-  const uint64_t r = t / n_cells;
+  const uint32_t i = t % n_slots;
+  if (i >= hole_begin && i < hole_end)
+    return;
+  const uint64_t r = t / n_slots;
   const uint32_t q = r % nq, f = r / nq;
   out[((uint64_t)f * n_cells + perm[i]) * nq + q] = tab[((uint64_t)f * nq + q) * ncp + i];
 }
@@ -145,7 +146,7 @@ struct glsb_op
   int      increment_form = 0, ctd = 0, cell_wise = 0, time_order = 0, geom = 0, device = 0;
   double   nu = 0, c1 = 0, c2 = 0, theta = 1;
   uint64_t n_cells = 0, n_owned = 0, n_ghost = 0, ncp = 0;
-  uint32_t n_interior = 0;
+  uint32_t n_interior = 0, n_int_pad = 0, n_slots = 0;
   uint32_t n_rows = 0, n_constrained = 0;
   uint64_t n_export = 0;
   size_t   tsize = 8;
@@ -224,14 +225,23 @@ KParams<T> base_params(const glsb_op *op)
   return p;
 }
 
-void cell_range(const glsb_op *op, int which, uint32_t &b, uint32_t &e)
+template <typename T>
+void cell_range(const glsb_op *op, int which, KParams<T> &p)
 {
-  b = 0;
-  e = (uint32_t)op->n_cells;
+  p.cell_begin = 0;
+  p.cell_end   = op->n_slots;
+  p.hole_begin = op->n_interior;
+  p.hole_end   = op->n_int_pad;
   if (which == GLSB_CELLS_INTERIOR)
-    e = op->n_interior;
+    {
+      p.cell_end   = op->n_interior;
+      p.hole_begin = p.hole_end = 0;
+    }
   else if (which == GLSB_CELLS_BOUNDARY)
-    b = op->n_interior;
+    {
+      p.cell_begin = op->n_int_pad;
+      p.hole_begin = p.hole_end = 0;
+    }
 }
 
 #define GLSB_DISPATCH(op, CALL)                                   \
@@ -258,7 +268,7 @@ template <int dim, typename T>
 int do_cells(glsb_op *op, void *dst, const void *src, double weight, int which, int branch, cudaStream_t s)
 {
   KParams<T> p = base_params<T>(op);
-  cell_range(op, which, p.cell_begin, p.cell_end);
+  cell_range(op, which, p);
   p.src           = static_cast<const T *>(src);
   p.dst           = static_cast<T *>(dst);
   p.weight        = (T)weight;
@@ -266,6 +276,44 @@ int do_cells(glsb_op *op, void *dst, const void *src, double weight, int which, 
   if (p.cell_end <= p.cell_begin)
     return 0;
   op->launches++;
+  if (dim == 3 && op->n == 3 && branch == BR_NEWTON && op->variant_forced != 1)
+    {
+      Q2Stage<T> sd;
+      memset(&sd, 0, sizeof sd);
+      int g = 0, f = 0;
+      auto add = [&](const DevBuf &b, int nf) {
+        sd.base[g] = b.as<T>();
+        sd.nf[g]   = nf;
+        ++g;
+        const int o = f;
+        f += nf;
+        return o;
+      };
+      sd.oU = add(op->U, 3);
+      sd.oH = add(op->H, 9);
+      sd.oP = add(op->P, 3);
+      if (op->ctd)
+        sd.oO = add(op->O, 3);
+      if (!op->cell_wise)
+        {
+          sd.od1q = add(op->d1q, 1);
+          sd.od2q = add(op->d2q, 1);
+        }
+      if (op->geom == GLSB_GEOM_GENERAL)
+        {
+          sd.oJ   = add(op->inv_jac, 9);
+          sd.ojxw = add(op->jxw, 1);
+        }
+      sd.n_groups = g;
+      sd.F        = f;
+      const int rc = Kernels<dim, T>::vmult_q2(p, op->shape, sd, op->geom == GLSB_GEOM_GENERAL, s);
+      if (rc >= 0)
+        {
+          op->variant = "q2_regtile_tma";
+          return rc;
+        }
+    }
+  op->variant = "generic";
   return Kernels<dim, T>::vmult(op->n, branch, p, op->shape, s);
 }
 
@@ -273,7 +321,7 @@ template <int dim, typename T>
 int do_lin(glsb_op *op, const void *vec, double dt, cudaStream_t s)
 {
   KParams<T> p = base_params<T>(op);
-  cell_range(op, GLSB_CELLS_ALL, p.cell_begin, p.cell_end);
+  cell_range(op, GLSB_CELLS_ALL, p);
   p.src  = static_cast<const T *>(vec);
   p.stau = (dt == 0.0) ? 0.0 : 1.0 / dt;
   p.R1   = nullptr;
@@ -285,7 +333,7 @@ template <int dim, typename T>
 int do_prev(glsb_op *op, const void *const *history, const double *weights, int order, cudaStream_t s)
 {
   KParams<T> p = base_params<T>(op);
-  cell_range(op, GLSB_CELLS_ALL, p.cell_begin, p.cell_end);
+  cell_range(op, GLSB_CELLS_ALL, p);
   p.hist_n = order;
   for (int i = 0; i < order; ++i)
     {
@@ -309,7 +357,7 @@ template <int dim, typename T>
 int do_diag(glsb_op *op, void *diag, double weight, cudaStream_t s)
 {
   KParams<T> p = base_params<T>(op);
-  cell_range(op, GLSB_CELLS_ALL, p.cell_begin, p.cell_end);
+  cell_range(op, GLSB_CELLS_ALL, p);
   p.dst    = static_cast<T *>(diag);
   p.weight = (T)weight;
   DiagColumns dc;
@@ -329,7 +377,7 @@ template <int dim, typename T>
 int do_maxu(glsb_op *op, const void *vec, cudaStream_t s)
 {
   KParams<T> p = base_params<T>(op);
-  cell_range(op, GLSB_CELLS_ALL, p.cell_begin, p.cell_end);
+  cell_range(op, GLSB_CELLS_ALL, p);
   p.src = static_cast<const T *>(vec);
   op->launches++;
   return Kernels<dim, T>::max_u(op->n, p, op->shape, s);
@@ -430,7 +478,6 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
   op->n_cells          = d->n_cells;
   op->n_owned          = d->n_owned;
   op->n_ghost          = d->n_ghost;
-  op->ncp              = (d->n_cells + 127) / 128 * 128;
   op->n_rows           = d->n_constraint_rows;
   op->n_constrained    = d->n_constrained_indices;
   op->n_export         = d->n_export;
@@ -503,15 +550,25 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
       delete op;
       return fail(nullptr, "glsb_create: " + why);
     }
+  // internal slots: [interior cells | padding up to a multiple of 32 | boundary cells | padding];
+  // padding slots repeat a real cell (safe to read) and are never scattered
   std::vector<uint32_t> perm;
-  perm.reserve(nc);
+  perm.reserve(nc + 160);
   for (uint32_t k = 0; k < nc; ++k)
     if (!is_boundary[k])
       perm.push_back(k);
   op->n_interior = (uint32_t)perm.size();
+  while (perm.size() % 32 != 0)
+    perm.push_back(perm.empty() ? 0 : perm.back());
+  op->n_int_pad = (uint32_t)perm.size();
   for (uint32_t k = 0; k < nc; ++k)
     if (is_boundary[k])
       perm.push_back(k);
+  op->n_slots = (uint32_t)perm.size();
+  op->ncp     = ((uint64_t)op->n_slots + 127) / 128 * 128;
+  while (perm.size() < op->ncp)
+    perm.push_back(perm.back());
+  auto slot_is_real = [&](uint64_t i) { return i < op->n_interior || (i >= op->n_int_pad && i < op->n_slots); };
 
   ok = ok && upload(op->perm, perm.data(), perm.size() * 4);
 
@@ -553,10 +610,10 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
     std::vector<uint8_t>  skip(op->ncp, 0);
     std::vector<uint32_t> l_cell, col_ptr(1, 0), col_dof, ent_ptr(1, 0), ent_loc;
     std::vector<double>   ent_val;
-    for (uint32_t i = 0; i < nc; ++i)
+    for (uint32_t i = 0; i < op->n_slots; ++i)
       {
         const uint32_t k = perm[i];
-        if (!has_weighted[k])
+        if (!slot_is_real(i) || !has_weighted[k])
           continue;
         skip[i] = 1;
         l_cell.push_back(i);
@@ -611,7 +668,7 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
     std::vector<double> hm(op->ncp), ms(op->ncp);
     for (uint64_t i = 0; i < op->ncp; ++i)
       {
-        const uint32_t k = perm[i < nc ? i : nc - 1];
+        const uint32_t k = perm[i];
         hm[i]            = d->cell_h_min[k];
         ms[i]            = d->cell_measure[k];
       }
@@ -621,7 +678,7 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
         std::vector<double> ij((size_t)dm * op->ncp), dj(op->ncp);
         for (uint64_t i = 0; i < op->ncp; ++i)
           {
-            const uint32_t k = perm[i < nc ? i : nc - 1];
+            const uint32_t k = perm[i];
             for (int e = 0; e < dm; ++e)
               ij[e * op->ncp + i] = d->inv_jac[(uint64_t)k * dm + e];
             dj[i] = d->jxw[k];
@@ -971,17 +1028,18 @@ int glsb_get_table(glsb_op *op, const char *name, void *out, uint64_t out_count,
     return fail(op, "glsb_get_table: unknown table " + s);
   if (!b->p)
     return fail(op, "glsb_get_table: table " + s + " has not been computed");
-  const uint64_t tot = (uint64_t)nf * nq * op->n_cells;
-  if (out_count != tot)
+  if (out_count != (uint64_t)nf * nq * op->n_cells)
     return fail(op, "glsb_get_table: wrong output size for " + s);
-  const unsigned g = (unsigned)((tot + 255) / 256);
+  const uint64_t tot = (uint64_t)nf * nq * op->n_slots;
+  const unsigned g   = (unsigned)((tot + 255) / 256);
   if (op->number_type == GLSB_F64)
     k_export_table<double><<<g, 256, 0, (cudaStream_t)stream>>>(b->as<double>(), op->perm.as<uint32_t>(),
-                                                                (double *)out, (uint32_t)op->n_cells, nq, nf,
-                                                                op->ncp);
+                                                                (double *)out, (uint32_t)op->n_cells, op->n_slots,
+                                                                op->n_interior, op->n_int_pad, nq, nf, op->ncp);
   else
     k_export_table<float><<<g, 256, 0, (cudaStream_t)stream>>>(b->as<float>(), op->perm.as<uint32_t>(),
-                                                               (float *)out, (uint32_t)op->n_cells, nq, nf, op->ncp);
+                                                               (float *)out, (uint32_t)op->n_cells, op->n_slots,
+                                                               op->n_interior, op->n_int_pad, nq, nf, op->ncp);
   if (cudaGetLastError() != cudaSuccess)
     return cuda_fail(op, "glsb_get_table");
   return 0;

@@ -14,6 +14,7 @@ struct Shape
 {
   T S[n * n];  // S[q*n + i]  = phi_i(x_q)          (FE_Q Lagrange basis at Gauss points)
   T D[n * n];  // D[q*n + q'] = collocation derivative on the Gauss points
+  T G[n * n];  // G[q*n + i]  = phi_i'(x_q) (= D S)
   T w[n];      // 1-D Gauss weights on [0,1]
 };
 
@@ -42,6 +43,7 @@ struct KParams
 {
   // cells [cell_begin, cell_end) in internal order; ncp = padded cell stride of all SoA arrays
   uint32_t cell_begin, cell_end;
+  uint32_t hole_begin, hole_end; // padding slots between the interior and the boundary range
   uint64_t ncp;
   const uint32_t *idx; // [C*n_loc][ncp]
   // constraint rows
@@ -72,6 +74,22 @@ struct KParams
   unsigned long long *max_bits; // get_max_u
 };
 
+template <typename T>
+__host__ __device__ inline bool cell_active(const KParams<T> &p, uint32_t cell)
+{
+  return cell < p.cell_end && !(cell >= p.hole_begin && cell < p.hole_end);
+}
+
+// tables staged through shared memory by the Q2 kernel: groups of contiguous [nf][27][ncp] arrays
+template <typename T>
+struct Q2Stage
+{
+  const T *base[8];
+  int      nf[8];
+  int      n_groups, F;
+  int      oU, oH, oP, oO, od1q, od2q, oJ, ojxw; // field offsets inside a stage
+};
+
 // columns of C_cell for cells with weighted constraint rows (compute_diagonal)
 struct DiagColumns
 {
@@ -94,6 +112,8 @@ struct Kernels
   static int diagonal(int n, int branch, const KParams<T> &p, const ShapeHost &sh, const uint8_t *skip_cell,
                       const DiagColumns &dc, cudaStream_t s);
   static int max_u(int n, const KParams<T> &p, const ShapeHost &sh, cudaStream_t s);
+  // register-tiled Q2 (dim 3, degree 2) Newton-branch vmult; returns -1 if not applicable
+  static int vmult_q2(const KParams<T> &p, const ShapeHost &sh, const Q2Stage<T> &sd, int general, cudaStream_t s);
 };
 
 } // namespace glsb

@@ -21,6 +21,7 @@ static Shape<T, n> to_shape(const ShapeHost &h)
     {
       s.S[i] = (T)h.S[i];
       s.D[i] = (T)h.D[i];
+      s.G[i] = (T)h.G[i];
     }
   for (int i = 0; i < n; ++i)
     s.w[i] = (T)h.w[i];
@@ -194,6 +195,23 @@ int Kernels<GLSB_DIM, GLSB_REAL>::diagonal(int n, int branch, const KParams<GLSB
 #define CALL(N) launch_diag<GLSB_DIM, N, GLSB_REAL>(branch, p, sh, skip_cell, dc, s)
   GLSB_SWITCH_N(CALL)
 #undef CALL
+}
+
+template <>
+int Kernels<GLSB_DIM, GLSB_REAL>::vmult_q2(const KParams<GLSB_REAL> &p, const ShapeHost &sh,
+                                           const Q2Stage<GLSB_REAL> &sd, int general, cudaStream_t s)
+{
+#if GLSB_DIM == 3 && defined(GLSB_WITH_Q2)
+  const auto   S      = to_shape<GLSB_REAL, 3>(sh);
+  const size_t stage  = q2::stage_elems<GLSB_REAL>(sd.F) * sizeof(GLSB_REAL);
+  const bool   three  = 2 * (3 * stage + 64) <= 220 * 1024; // two CTAs per SM with a 3-deep ring?
+  if (general)
+    return three ? q2::launch<GLSB_REAL, true, 3>(p, S, sd, s) : q2::launch<GLSB_REAL, true, 2>(p, S, sd, s);
+  return three ? q2::launch<GLSB_REAL, false, 3>(p, S, sd, s) : q2::launch<GLSB_REAL, false, 2>(p, S, sd, s);
+#else
+  (void)p, (void)sh, (void)sd, (void)general, (void)s;
+  return -1;
+#endif
 }
 
 template <>

@@ -466,8 +466,8 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_vmult_generic(const KP
   Ctx<dim, n, T> ctx;
   ctx.init(smem, sh);
   const uint32_t cell0  = p.cell_begin + blockIdx.x * G::CPB + ctx.cb;
-  const bool     active = cell0 < p.cell_end;
-  const uint32_t cell   = active ? cell0 : p.cell_end - 1;
+  const bool     active = cell_active(p, cell0);
+  const uint32_t cell   = cell0 < p.cell_end ? cell0 : p.cell_end - 1;
   uint32_t       iv[G::C];
 #pragma unroll
   for (int c = 0; c < G::C; ++c)
@@ -501,8 +501,8 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_linearization(const KP
   Ctx<dim, n, T> ctx;
   ctx.init(smem, sh);
   const uint32_t cell0  = p.cell_begin + blockIdx.x * G::CPB + ctx.cb;
-  const bool     active = cell0 < p.cell_end;
-  const uint32_t cell   = active ? cell0 : p.cell_end - 1;
+  const bool     active = cell_active(p, cell0);
+  const uint32_t cell   = cell0 < p.cell_end ? cell0 : p.cell_end - 1;
 #pragma unroll
   for (int c = 0; c < C; ++c)
     ctx.v[ctx.at(c, ctx.l)] = p.src[plain_index(p, p.idx[(uint64_t)(c * G::n_loc + ctx.l) * p.ncp + cell])];
@@ -590,8 +590,8 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_previous(const KParams
   Ctx<dim, n, T> ctx;
   ctx.init(smem, sh);
   const uint32_t cell0  = p.cell_begin + blockIdx.x * G::CPB + ctx.cb;
-  const bool     active = cell0 < p.cell_end;
-  const uint32_t cell   = active ? cell0 : p.cell_end - 1;
+  const bool     active = cell_active(p, cell0);
+  const uint32_t cell   = cell0 < p.cell_end ? cell0 : p.cell_end - 1;
 #pragma unroll
   for (int c = 0; c < C; ++c)
     {
@@ -640,8 +640,8 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_max_u(const KParams<T>
   Ctx<dim, n, T> ctx;
   ctx.init(smem, sh);
   const uint32_t cell0  = p.cell_begin + blockIdx.x * G::CPB + ctx.cb;
-  const bool     active = cell0 < p.cell_end;
-  const uint32_t cell   = active ? cell0 : p.cell_end - 1;
+  const bool     active = cell_active(p, cell0);
+  const uint32_t cell   = cell0 < p.cell_end ? cell0 : p.cell_end - 1;
 #pragma unroll
   for (int c = 0; c < C; ++c)
     ctx.v[ctx.at(c, ctx.l)] = p.src[plain_index(p, p.idx[(uint64_t)(c * G::n_loc + ctx.l) * p.ncp + cell])];
@@ -676,8 +676,8 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_diag_generic(const KPa
   Ctx<dim, n, T> ctx;
   ctx.init(smem, sh);
   const uint32_t cell0  = p.cell_begin + blockIdx.x * G::CPB + ctx.cb;
-  const bool     active = cell0 < p.cell_end;
-  const uint32_t cell   = active ? cell0 : p.cell_end - 1;
+  const bool     active = cell_active(p, cell0);
+  const uint32_t cell   = cell0 < p.cell_end ? cell0 : p.cell_end - 1;
   T              mine[C];
   for (int j = 0; j < C * G::n_loc; ++j)
     {

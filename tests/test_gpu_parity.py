@@ -213,3 +213,27 @@ def test_vmult_linearity_and_repeatability_large():
     ax2 = gpu.initialize_dof_vector()
     gpu.vmult(ax2, x)
     assert float(torch.linalg.norm(ax2 - ax) / torch.linalg.norm(ax)) < 1e-14
+
+
+@pytest.mark.parametrize("number", ["double", "float"])
+@pytest.mark.parametrize("kind,ctd,cell_wise", [("cube", False, True), ("shell", True, False), ("shell", False, True),
+                                                ("cube", True, False)])
+def test_q2_fast_kernel_matches_generic_and_oracle(kind, ctd, cell_wise, number):
+    """The register-tiled Q2 kernel (3-D, degree 2, Newton branch) is the variant vmult picks; it
+    must agree with the oracle and with the generic kernel, on meshes whose cell count is not a
+    multiple of the 32-cell batch and with Dirichlet rows."""
+    mesh = gm.hypercube(3, 5, 2) if kind == "cube" else gm.cylinder_shell((3, 7, 3), 2)
+    ti = TI(2, [15.0, -20.0, 5.0], 0.1)
+    ora, gpu, src, _ = _setup(mesh, ti, number, ctd=ctd, cell_wise=cell_wise, nu=0.01)
+    ref = ora.vmult(src, 15.0)
+    x = _to_dev(src, number)
+    dst = gpu.initialize_dof_vector()
+    gpu.vmult(dst, x)
+    assert gpu.vmult_variant() == "q2_regtile_tma"
+    assert rel_l2(dst.cpu().numpy(), ref) < TOL[number]
+    gpu.set_variant(1)
+    dst2 = gpu.initialize_dof_vector()
+    gpu.vmult(dst2, x)
+    assert gpu.vmult_variant() == "generic"
+    assert rel_l2(dst2.cpu().numpy(), ref) < TOL[number]
+    assert rel_l2(dst.cpu().numpy(), dst2.cpu().numpy()) < TOL[number]
