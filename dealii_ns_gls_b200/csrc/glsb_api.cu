@@ -61,20 +61,21 @@ __global__ void k_transpose_idx(const uint32_t *__restrict__ raw, const uint32_t
   out[t]           = raw[(uint64_t)perm[i] * ndof + d]; // perm is defined for every slot (padding repeats a cell)
 }
 
-// general geometry [cell][q][e][j] (double) -> [e*dim+j][q][ncp] (T); jxw [cell][q] -> [q][ncp]
+// general geometry raw[(cell*nq + q)*inner + f] (double, caller's cell order) -> blocked q-point
+// array field f0 + f (see KParams::Q)
 template <typename T>
-__global__ void k_transpose_geom(const double *__restrict__ raw, const uint32_t *__restrict__ perm,
-                                 T *__restrict__ out, uint32_t n_cells, uint32_t per_cell_q, uint32_t inner,
-                                 uint64_t ncp)
+__global__ void k_fill_geom(const double *__restrict__ raw, const uint32_t *__restrict__ perm, T *__restrict__ Q,
+                            uint32_t nq, uint32_t inner, uint64_t ncp, int FT, int NL, int QG, int f0)
 {
-  // raw[(cell*nq + q)*inner + f] -> out[(f*nq + q)*ncp + i]
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (uint64_t)inner * per_cell_q * ncp)
+  if (t >= (uint64_t)inner * nq * ncp)
     return;
   const uint32_t i = t % ncp;
   const uint64_t r = t / ncp;
-  const uint32_t q = r % per_cell_q, f = r / per_cell_q;
-  out[t]           = (T)raw[((uint64_t)perm[i] * per_cell_q + q) * inner + f];
+  const uint32_t q = r % nq, f = r / nq;
+  const uint32_t layer = q / QG, ql = q - layer * QG;
+  const uint64_t o = ((((uint64_t)(i >> 5) * NL + layer) * FT + (f0 + f)) * QG + ql) * 32 + (i & 31);
+  Q[o] = (T)raw[((uint64_t)perm[i] * nq + q) * inner + f];
 }
 
 template <typename T>
@@ -122,11 +123,12 @@ __global__ void k_invert_guarded(T *__restrict__ v, uint64_t n)
     }
 }
 
-// table [f][q][ncp] (internal cell order) -> out [f][cell][q] (caller's order)
+// blocked q-point fields f0 .. f0+nf-1 (internal cell order) -> out [f][cell][q] (caller's order);
+// per-cell arrays: nq = 1 and Q = the plain [ncp] array (FT = NL = QG = 1 addressing degenerates)
 template <typename T>
-__global__ void k_export_table(const T *__restrict__ tab, const uint32_t *__restrict__ perm, T *__restrict__ out,
+__global__ void k_export_table(const T *__restrict__ Q, const uint32_t *__restrict__ perm, T *__restrict__ out,
                                uint32_t n_cells, uint32_t n_slots, uint32_t hole_begin, uint32_t hole_end,
-                               uint32_t nq, uint32_t nf, uint64_t ncp)
+                               uint32_t nq, uint32_t nf, int FT, int NL, int QG, int f0, int per_cell)
 {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (uint64_t)nf * nq * n_slots)
@@ -136,7 +138,15 @@ __global__ void k_export_table(const T *__restrict__ tab, const uint32_t *__rest
     return;
   const uint64_t r = t / n_slots;
   const uint32_t q = r % nq, f = r / nq;
-  out[((uint64_t)f * n_cells + perm[i]) * nq + q] = tab[((uint64_t)f * nq + q) * ncp + i];
+  uint64_t       o;
+  if (per_cell)
+    o = i;
+  else
+    {
+      const uint32_t layer = q / QG, ql = q - layer * QG;
+      o = ((((uint64_t)(i >> 5) * NL + layer) * FT + (f0 + f)) * QG + ql) * 32 + (i & 31);
+    }
+  out[((uint64_t)f * n_cells + perm[i]) * nq + q] = Q[o];
 }
 } // namespace
 
@@ -152,7 +162,9 @@ struct glsb_op
   size_t   tsize = 8;
 
   DevBuf perm, idx, row_dof, row_ptr, ecol, eval, cidx, inv_jac, jxw, h_min, measure, export_idx;
-  DevBuf U, H, P, O, Gold, gold_p, R1, d1c, d2c, d1q, d2q, max_bits;
+  DevBuf Q, d1c, d2c, max_bits;
+  int    FT = 0, NL = 1, QG = 1, F_stage = 0;
+  int    fU = -1, fH = -1, fP = -1, fO = -1, fd1q = -1, fd2q = -1, fJ = -1, fjxw = -1, fGold = -1, fgoldp = -1;
   DevBuf diag_skip, dc_cell, dc_col_ptr, dc_col_dof, dc_ent_ptr, dc_ent_loc, dc_ent_val;
   uint32_t dc_n_list = 0;
 
@@ -200,17 +212,22 @@ KParams<T> base_params(const glsb_op *op)
   p.jxw        = op->jxw.as<T>();
   p.h_min      = op->h_min.as<double>();
   p.measure    = op->measure.as<double>();
-  p.U          = op->U.as<T>();
-  p.H          = op->H.as<T>();
-  p.P          = op->P.as<T>();
-  p.O          = op->O.as<T>();
-  p.Gold       = op->Gold.as<T>();
-  p.gold_p     = op->gold_p.as<T>();
-  p.R1         = op->R1.as<T>();
+  p.Q          = op->Q.as<T>();
+  p.FT         = op->FT;
+  p.NL         = op->NL;
+  p.QG         = op->QG;
+  p.fU         = op->fU;
+  p.fH         = op->fH;
+  p.fP         = op->fP;
+  p.fO         = op->fO;
+  p.fd1q       = op->fd1q;
+  p.fd2q       = op->fd2q;
+  p.fJ         = op->fJ;
+  p.fjxw       = op->fjxw;
+  p.fGold      = op->fGold;
+  p.fgoldp     = op->fgoldp;
   p.d1c        = op->d1c.as<T>();
   p.d2c        = op->d2c.as<T>();
-  p.d1q        = op->d1q.as<T>();
-  p.d2q        = op->d2q.as<T>();
   p.nu         = (T)op->nu;
   p.theta      = (T)op->theta;
   p.c1         = op->c1;
@@ -219,7 +236,7 @@ KParams<T> base_params(const glsb_op *op)
   p.degree     = op->degree;
   p.ctd        = op->ctd;
   p.cell_wise  = op->cell_wise;
-  p.has_o      = op->prev_valid && op->O.p != nullptr;
+  p.has_o      = op->prev_valid && op->fO >= 0;
   p.theta_ne_1 = (op->theta != 1.0);
   p.max_bits   = op->max_bits.as<unsigned long long>();
   return p;
@@ -278,35 +295,7 @@ int do_cells(glsb_op *op, void *dst, const void *src, double weight, int which, 
   op->launches++;
   if (dim == 3 && op->n == 3 && branch == BR_NEWTON && op->variant_forced != 1)
     {
-      Q2Stage<T> sd;
-      memset(&sd, 0, sizeof sd);
-      int g = 0, f = 0;
-      auto add = [&](const DevBuf &b, int nf) {
-        sd.base[g] = b.as<T>();
-        sd.nf[g]   = nf;
-        ++g;
-        const int o = f;
-        f += nf;
-        return o;
-      };
-      sd.oU = add(op->U, 3);
-      sd.oH = add(op->H, 9);
-      sd.oP = add(op->P, 3);
-      if (op->ctd)
-        sd.oO = add(op->O, 3);
-      if (!op->cell_wise)
-        {
-          sd.od1q = add(op->d1q, 1);
-          sd.od2q = add(op->d2q, 1);
-        }
-      if (op->geom == GLSB_GEOM_GENERAL)
-        {
-          sd.oJ   = add(op->inv_jac, 9);
-          sd.ojxw = add(op->jxw, 1);
-        }
-      sd.n_groups = g;
-      sd.F        = f;
-      const int rc = Kernels<dim, T>::vmult_q2(p, op->shape, sd, op->geom == GLSB_GEOM_GENERAL, s);
+      const int rc = Kernels<dim, T>::vmult_q2(p, op->shape, op->F_stage, s);
       if (rc >= 0)
         {
           op->variant = "q2_regtile_tma";
@@ -324,7 +313,6 @@ int do_lin(glsb_op *op, const void *vec, double dt, cudaStream_t s)
   cell_range(op, GLSB_CELLS_ALL, p);
   p.src  = static_cast<const T *>(vec);
   p.stau = (dt == 0.0) ? 0.0 : 1.0 / dt;
-  p.R1   = nullptr;
   op->launches++;
   return Kernels<dim, T>::linearization(op->n, p, op->shape, s);
 }
@@ -401,28 +389,7 @@ bool upload_converted(DevBuf &b, const double *host, size_t count)
   return upload(b, tmp.data(), count * sizeof(T));
 }
 
-bool ensure_tables(glsb_op *op, bool lin, bool prev)
-{
-  const size_t per_field = (size_t)op->nq * op->ncp * op->tsize;
-  const int    d         = op->dim;
-  if (lin)
-    {
-      if (!op->U.p && !(op->U.alloc(d * per_field) && op->H.alloc(d * d * per_field) &&
-                        op->P.alloc(d * per_field) && op->d1c.alloc(op->ncp * op->tsize) &&
-                        op->d2c.alloc(op->ncp * op->tsize) && op->d1q.alloc(per_field) &&
-                        op->d2q.alloc(per_field)))
-        return false;
-    }
-  if (prev)
-    {
-      if (!op->O.p && !op->O.alloc(d * per_field))
-        return false;
-      if (op->theta != 1.0 && !op->Gold.p &&
-          !(op->Gold.alloc(d * d * per_field) && op->gold_p.alloc(d * per_field)))
-        return false;
-    }
-  return true;
-}
+bool ensure_tables(glsb_op *, bool, bool) { return true; } // the q-point array is allocated in glsb_create
 } // namespace
 
 extern "C" {
@@ -661,6 +628,61 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
       }
   }
 
+  // ---- q-point data layout: the fields the Newton-branch vmult streams come first ----------
+  {
+    const int dm = op->dim;
+    int       f  = 0;
+    auto take = [&](int nf) {
+      const int o = f;
+      f += nf;
+      return o;
+    };
+    const bool general = op->geom == GLSB_GEOM_GENERAL;
+    op->fU = take(dm);
+    op->fH = take(dm * dm);
+    op->fP = take(dm);
+    if (op->ctd)
+      op->fO = take(dm);
+    if (!op->cell_wise)
+      {
+        op->fd1q = take(1);
+        op->fd2q = take(1);
+      }
+    if (general)
+      {
+        op->fJ   = take(dm * dm);
+        op->fjxw = take(1);
+      }
+    op->F_stage = f;
+    if (!op->ctd && op->time_order > 0)
+      op->fO = take(dm);
+    if (op->cell_wise)
+      {
+        op->fd1q = take(1);
+        op->fd2q = take(1);
+      }
+    if (op->theta != 1.0)
+      {
+        op->fGold  = take(dm * dm);
+        op->fgoldp = take(dm);
+      }
+    op->FT = f;
+    if (op->dim == 3 && op->n == 3)
+      {
+        op->NL = 3;
+        op->QG = 9;
+      }
+    else
+      {
+        op->NL = 1;
+        op->QG = op->nq;
+      }
+    const size_t bytes = (size_t)op->FT * op->nq * op->ncp * op->tsize;
+    ok = ok && op->Q.alloc(bytes) && op->d1c.alloc(op->ncp * op->tsize) && op->d2c.alloc(op->ncp * op->tsize);
+    if (ok)
+      ok = cudaMemset(op->Q.p, 0, bytes) == cudaSuccess;
+  }
+
   // ---- geometry -------------------------------------------------------------------------
   {
     const int dm = op->dim;
@@ -693,30 +715,31 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
       {
         const uint32_t inner = dm * dm;
         DevBuf         raw;
+        const uint64_t tot1 = (uint64_t)inner * op->nq * op->ncp, tot2 = (uint64_t)op->nq * op->ncp;
         ok = ok && upload(raw, d->inv_jac, (size_t)nc * op->nq * inner * 8);
-        ok = ok && op->inv_jac.alloc((size_t)inner * op->nq * op->ncp * op->tsize);
         if (ok)
           {
-            const uint64_t tot = (uint64_t)inner * op->nq * op->ncp;
             if (op->number_type == GLSB_F64)
-              k_transpose_geom<double><<<(unsigned)((tot + 255) / 256), 256>>>(
-                raw.as<double>(), op->perm.as<uint32_t>(), op->inv_jac.as<double>(), nc, op->nq, inner, op->ncp);
+              k_fill_geom<double><<<(unsigned)((tot1 + 255) / 256), 256>>>(raw.as<double>(), op->perm.as<uint32_t>(),
+                                                                           op->Q.as<double>(), op->nq, inner, op->ncp,
+                                                                           op->FT, op->NL, op->QG, op->fJ);
             else
-              k_transpose_geom<float><<<(unsigned)((tot + 255) / 256), 256>>>(
-                raw.as<double>(), op->perm.as<uint32_t>(), op->inv_jac.as<float>(), nc, op->nq, inner, op->ncp);
+              k_fill_geom<float><<<(unsigned)((tot1 + 255) / 256), 256>>>(raw.as<double>(), op->perm.as<uint32_t>(),
+                                                                          op->Q.as<float>(), op->nq, inner, op->ncp,
+                                                                          op->FT, op->NL, op->QG, op->fJ);
             ok = cudaDeviceSynchronize() == cudaSuccess;
           }
         ok = ok && upload(raw, d->jxw, (size_t)nc * op->nq * 8);
-        ok = ok && op->jxw.alloc((size_t)op->nq * op->ncp * op->tsize);
         if (ok)
           {
-            const uint64_t tot = (uint64_t)op->nq * op->ncp;
             if (op->number_type == GLSB_F64)
-              k_transpose_geom<double><<<(unsigned)((tot + 255) / 256), 256>>>(
-                raw.as<double>(), op->perm.as<uint32_t>(), op->jxw.as<double>(), nc, op->nq, 1, op->ncp);
+              k_fill_geom<double><<<(unsigned)((tot2 + 255) / 256), 256>>>(raw.as<double>(), op->perm.as<uint32_t>(),
+                                                                           op->Q.as<double>(), op->nq, 1, op->ncp,
+                                                                           op->FT, op->NL, op->QG, op->fjxw);
             else
-              k_transpose_geom<float><<<(unsigned)((tot + 255) / 256), 256>>>(
-                raw.as<double>(), op->perm.as<uint32_t>(), op->jxw.as<float>(), nc, op->nq, 1, op->ncp);
+              k_fill_geom<float><<<(unsigned)((tot2 + 255) / 256), 256>>>(raw.as<double>(), op->perm.as<uint32_t>(),
+                                                                          op->Q.as<float>(), op->nq, 1, op->ncp,
+                                                                          op->FT, op->NL, op->QG, op->fjxw);
             ok = cudaDeviceSynchronize() == cudaSuccess;
           }
       }
@@ -1000,46 +1023,48 @@ int glsb_get_table(glsb_op *op, const char *name, void *out, uint64_t out_count,
 {
   if (!op || !name || !out)
     return fail(op, "glsb_get_table: null argument");
-  const DevBuf *b  = nullptr;
   uint32_t      nf = 0, nq = op->nq;
   const int     d  = op->dim;
+  int           f0 = -1, per_cell = 0;
+  const void   *base = op->Q.p;
   const std::string s(name);
   if (s == "u_star_value")
-    b = &op->U, nf = d;
+    f0 = op->fU, nf = d;
   else if (s == "u_star_gradient")
-    b = &op->H, nf = d * d;
+    f0 = op->fH, nf = d * d;
   else if (s == "p_star_gradient")
-    b = &op->P, nf = d;
+    f0 = op->fP, nf = d;
   else if (s == "u_time_derivative_old")
-    b = &op->O, nf = d;
+    f0 = op->fO, nf = d;
   else if (s == "u_old_gradient")
-    b = &op->Gold, nf = d * d;
+    f0 = op->fGold, nf = d * d;
   else if (s == "p_old_gradient")
-    b = &op->gold_p, nf = d;
-  else if (s == "delta_1")
-    b = &op->d1c, nf = 1, nq = 1;
-  else if (s == "delta_2")
-    b = &op->d2c, nf = 1, nq = 1;
+    f0 = op->fgoldp, nf = d;
   else if (s == "delta_1_q")
-    b = &op->d1q, nf = 1;
+    f0 = op->fd1q, nf = 1;
   else if (s == "delta_2_q")
-    b = &op->d2q, nf = 1;
+    f0 = op->fd2q, nf = 1;
+  else if (s == "delta_1")
+    f0 = 0, nf = 1, nq = 1, per_cell = 1, base = op->d1c.p;
+  else if (s == "delta_2")
+    f0 = 0, nf = 1, nq = 1, per_cell = 1, base = op->d2c.p;
   else
     return fail(op, "glsb_get_table: unknown table " + s);
-  if (!b->p)
+  const bool is_prev = (s == "u_time_derivative_old" || s == "u_old_gradient" || s == "p_old_gradient");
+  if (f0 < 0 || (is_prev && !op->prev_valid) || (!is_prev && !op->lin_valid))
     return fail(op, "glsb_get_table: table " + s + " has not been computed");
   if (out_count != (uint64_t)nf * nq * op->n_cells)
     return fail(op, "glsb_get_table: wrong output size for " + s);
   const uint64_t tot = (uint64_t)nf * nq * op->n_slots;
   const unsigned g   = (unsigned)((tot + 255) / 256);
   if (op->number_type == GLSB_F64)
-    k_export_table<double><<<g, 256, 0, (cudaStream_t)stream>>>(b->as<double>(), op->perm.as<uint32_t>(),
-                                                                (double *)out, (uint32_t)op->n_cells, op->n_slots,
-                                                                op->n_interior, op->n_int_pad, nq, nf, op->ncp);
+    k_export_table<double><<<g, 256, 0, (cudaStream_t)stream>>>(
+      (const double *)base, op->perm.as<uint32_t>(), (double *)out, (uint32_t)op->n_cells, op->n_slots,
+      op->n_interior, op->n_int_pad, nq, nf, op->FT, op->NL, op->QG, f0, per_cell);
   else
-    k_export_table<float><<<g, 256, 0, (cudaStream_t)stream>>>(b->as<float>(), op->perm.as<uint32_t>(),
-                                                               (float *)out, (uint32_t)op->n_cells, op->n_slots,
-                                                               op->n_interior, op->n_int_pad, nq, nf, op->ncp);
+    k_export_table<float><<<g, 256, 0, (cudaStream_t)stream>>>(
+      (const float *)base, op->perm.as<uint32_t>(), (float *)out, (uint32_t)op->n_cells, op->n_slots,
+      op->n_interior, op->n_int_pad, nq, nf, op->FT, op->NL, op->QG, f0, per_cell);
   if (cudaGetLastError() != cudaSuccess)
     return cuda_fail(op, "glsb_get_table");
   return 0;

@@ -51,13 +51,21 @@ struct KParams
   const T        *eval;
   // geometry
   int      geom;    // 0 Cartesian, 2 general
-  const T *inv_jac; // Cartesian [dim][ncp]; general [dim*dim][nq][ncp]
-  const T *jxw;     // Cartesian [ncp]; general [nq][ncp]
+  const T *inv_jac; // Cartesian only: [dim][ncp] diagonal of J^-1
+  const T *jxw;     // Cartesian only: [ncp] det J
   const double *h_min, *measure; // [ncp]
-  // q-point tables [field][nq][ncp]
-  T *U, *H, *P, *O, *Gold, *gold_p, *R1;
-  T *d1c, *d2c; // [ncp]
-  T *d1q, *d2q; // [nq][ncp]
+  // q-point data, one blocked array: element (field f, point q, cell) lives at
+  //   ((((cell >> 5) * NL + q / QG) * FT + f) * QG + q % QG) * 32 + (cell & 31)
+  // i.e. [batch of 32 cells][layer of QG points][field][point in layer][cell in batch], so that
+  // the fields of one layer of one batch are one contiguous block (a single TMA bulk copy) and
+  // 32 consecutive cells of a (field, point) row are contiguous (coalesced in every kernel).
+  T  *Q;
+  int FT, NL, QG;
+  // field offsets (-1 = not stored): u_star_value, u_star_gradient, p_star_gradient,
+  // u_time_derivative_old, delta_1_q, delta_2_q, J^-1 (general), JxW (general), u_old_gradient,
+  // p_old_gradient (operator_ns.h:117-132)
+  int fU, fH, fP, fO, fd1q, fd2q, fJ, fjxw, fGold, fgoldp;
+  T  *d1c, *d2c; // [ncp] cell-wise delta_1, delta_2
   // scalars
   T      weight, nu, theta;
   double c1, c2, stau, nu_d;
@@ -80,15 +88,22 @@ __host__ __device__ inline bool cell_active(const KParams<T> &p, uint32_t cell)
   return cell < p.cell_end && !(cell >= p.hole_begin && cell < p.hole_end);
 }
 
-// tables staged through shared memory by the Q2 kernel: groups of contiguous [nf][27][ncp] arrays
+// position of (point q, cell) in the blocked q-point array; field f adds f * fstride
 template <typename T>
-struct Q2Stage
+struct QPos
 {
-  const T *base[8];
-  int      nf[8];
-  int      n_groups, F;
-  int      oU, oH, oP, oO, od1q, od2q, oJ, ojxw; // field offsets inside a stage
+  uint64_t base;
+  uint32_t fstride;
 };
+template <typename T>
+__host__ __device__ inline QPos<T> qpos(const KParams<T> &p, uint32_t q, uint32_t cell)
+{
+  QPos<T> r;
+  const uint32_t layer = q / (uint32_t)p.QG, ql = q - layer * (uint32_t)p.QG;
+  r.base    = ((((uint64_t)(cell >> 5) * p.NL + layer) * p.FT) * p.QG + ql) * 32 + (cell & 31);
+  r.fstride = (uint32_t)p.QG * 32;
+  return r;
+}
 
 // columns of C_cell for cells with weighted constraint rows (compute_diagonal)
 struct DiagColumns
@@ -113,7 +128,7 @@ struct Kernels
                       const DiagColumns &dc, cudaStream_t s);
   static int max_u(int n, const KParams<T> &p, const ShapeHost &sh, cudaStream_t s);
   // register-tiled Q2 (dim 3, degree 2) Newton-branch vmult; returns -1 if not applicable
-  static int vmult_q2(const KParams<T> &p, const ShapeHost &sh, const Q2Stage<T> &sd, int general, cudaStream_t s);
+  static int vmult_q2(const KParams<T> &p, const ShapeHost &sh, int n_stage_fields, cudaStream_t s);
 };
 
 } // namespace glsb

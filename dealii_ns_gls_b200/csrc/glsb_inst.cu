@@ -198,18 +198,16 @@ int Kernels<GLSB_DIM, GLSB_REAL>::diagonal(int n, int branch, const KParams<GLSB
 }
 
 template <>
-int Kernels<GLSB_DIM, GLSB_REAL>::vmult_q2(const KParams<GLSB_REAL> &p, const ShapeHost &sh,
-                                           const Q2Stage<GLSB_REAL> &sd, int general, cudaStream_t s)
+int Kernels<GLSB_DIM, GLSB_REAL>::vmult_q2(const KParams<GLSB_REAL> &p, const ShapeHost &sh, int F, cudaStream_t s)
 {
 #if GLSB_DIM == 3 && defined(GLSB_WITH_Q2)
-  const auto   S      = to_shape<GLSB_REAL, 3>(sh);
-  const size_t stage  = q2::stage_elems<GLSB_REAL>(sd.F) * sizeof(GLSB_REAL);
-  const bool   three  = 2 * (3 * stage + 64) <= 220 * 1024; // two CTAs per SM with a 3-deep ring?
-  if (general)
-    return three ? q2::launch<GLSB_REAL, true, 3>(p, S, sd, s) : q2::launch<GLSB_REAL, true, 2>(p, S, sd, s);
-  return three ? q2::launch<GLSB_REAL, false, 3>(p, S, sd, s) : q2::launch<GLSB_REAL, false, 2>(p, S, sd, s);
+  const auto S     = to_shape<GLSB_REAL, 3>(sh);
+  const bool three = 2 * q2::smem_bytes<GLSB_REAL>(F, 3) <= 224 * 1024; // two CTAs per SM with a 3-deep ring?
+  if (p.geom == GLSB_GEOM_GENERAL)
+    return three ? q2::launch_flags<GLSB_REAL, true, 3>(p, S, F, s) : q2::launch_flags<GLSB_REAL, true, 2>(p, S, F, s);
+  return three ? q2::launch_flags<GLSB_REAL, false, 3>(p, S, F, s) : q2::launch_flags<GLSB_REAL, false, 2>(p, S, F, s);
 #else
-  (void)p, (void)sh, (void)sd, (void)general, (void)s;
+  (void)p, (void)sh, (void)F, (void)s;
   return -1;
 #endif
 }

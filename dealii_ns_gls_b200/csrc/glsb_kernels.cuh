@@ -32,16 +32,31 @@ struct Geo
 __device__ __forceinline__ void atomic_add(double *a, double v) { atomicAdd(a, v); }
 __device__ __forceinline__ void atomic_add(float *a, float v) { atomicAdd(a, v); }
 
+// slow paths (constrained dofs are rare): kept out of line so that the hot kernels stay small
+template <typename T>
+__device__ __noinline__ T gather_constrained(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ ecol,
+                                             const T *__restrict__ eval, const T *__restrict__ src, uint32_t r)
+{
+  T s = 0;
+  for (uint32_t e = row_ptr[r]; e < row_ptr[r + 1]; ++e)
+    s += eval[e] * src[ecol[e]];
+  return s;
+}
+
+template <typename T>
+__device__ __noinline__ void scatter_constrained(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ ecol,
+                                                 const T *__restrict__ eval, T *__restrict__ dst, uint32_t r, T v)
+{
+  for (uint32_t e = row_ptr[r]; e < row_ptr[r + 1]; ++e)
+    atomic_add(dst + ecol[e], eval[e] * v);
+}
+
 template <typename T>
 __device__ __forceinline__ T gather_resolved(const KParams<T> &p, const T *__restrict__ src, uint32_t iv)
 {
   if (!(iv & GLSB_CONSTRAINED_BIT))
     return src[iv];
-  const uint32_t r = iv & ~GLSB_CONSTRAINED_BIT;
-  T              s = 0;
-  for (uint32_t e = p.row_ptr[r]; e < p.row_ptr[r + 1]; ++e)
-    s += p.eval[e] * src[p.ecol[e]];
-  return s;
+  return gather_constrained<T>(p.row_ptr, p.ecol, p.eval, src, iv & ~GLSB_CONSTRAINED_BIT);
 }
 
 template <typename T>
@@ -58,9 +73,7 @@ __device__ __forceinline__ void scatter_resolved(const KParams<T> &p, T *__restr
       atomic_add(dst + iv, v);
       return;
     }
-  const uint32_t r = iv & ~GLSB_CONSTRAINED_BIT;
-  for (uint32_t e = p.row_ptr[r]; e < p.row_ptr[r + 1]; ++e)
-    atomic_add(dst + p.ecol[e], p.eval[e] * v);
+  scatter_constrained<T>(p.row_ptr, p.ecol, p.eval, dst, iv & ~GLSB_CONSTRAINED_BIT, v);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -209,13 +222,13 @@ struct GeomQ
       }
     else
       {
-        constexpr int nq = Geo<dim, n>::nq;
+        const QPos<T> qp = qpos(p, (uint32_t)q, cell);
 #pragma unroll
         for (int e = 0; e < dim; ++e)
 #pragma unroll
           for (int j = 0; j < dim; ++j)
-            ij[e][j] = p.inv_jac[((uint64_t)(e * dim + j) * nq + q) * p.ncp + cell];
-        jxw = p.jxw[(uint64_t)q * p.ncp + cell];
+            ij[e][j] = p.Q[qp.base + (uint64_t)(p.fJ + e * dim + j) * qp.fstride];
+        jxw = p.Q[qp.base + (uint64_t)p.fjxw * qp.fstride];
       }
   }
   template <int C>
@@ -283,17 +296,18 @@ __device__ __forceinline__ void symm_add(T (&gout)[dim + 1][dim], const T (&B)[d
 }
 
 template <int dim, typename T, int BR>
-__device__ __forceinline__ void qpoint_physics(const KParams<T> &p, uint64_t tq, uint32_t cell, uint64_t fs,
+__device__ __forceinline__ void qpoint_physics(const KParams<T> &p, const QPos<T> qp, uint32_t cell,
                                                const T (&val)[dim + 1], const T (&g)[dim + 1][dim],
                                                T (&vout)[dim + 1], T (&gout)[dim + 1][dim])
 {
-  const T d1 = p.cell_wise ? p.d1c[cell] : p.d1q[tq];
-  const T d2 = p.cell_wise ? p.d2c[cell] : p.d2q[tq];
+#define GLSB_QF(f) p.Q[qp.base + (uint64_t)(f)*qp.fstride]
+  const T d1 = p.cell_wise ? p.d1c[cell] : GLSB_QF(p.fd1q);
+  const T d2 = p.cell_wise ? p.d2c[cell] : GLSB_QF(p.fd2q);
   const T w  = p.weight;
   T       U[dim];
 #pragma unroll
   for (int j = 0; j < dim; ++j)
-    U[j] = p.U[j * fs + tq];
+    U[j] = GLSB_QF(p.fU + j);
 #pragma unroll
   for (int c = 0; c <= dim; ++c)
 #pragma unroll
@@ -306,10 +320,10 @@ __device__ __forceinline__ void qpoint_physics(const KParams<T> &p, uint64_t tq,
 #pragma unroll
       for (int c = 0; c < dim; ++c)
         {
-          P[c] = p.P[c * fs + tq];
+          P[c] = GLSB_QF(p.fP + c);
 #pragma unroll
           for (int j = 0; j < dim; ++j)
-            H[c][j] = p.H[(c * dim + j) * fs + tq];
+            H[c][j] = GLSB_QF(p.fH + c * dim + j);
         }
       T Gm[dim][dim];
       T div = 0;
@@ -340,7 +354,7 @@ __device__ __forceinline__ void qpoint_physics(const KParams<T> &p, uint64_t tq,
           if (p.ctd)
             {
               a = td + a;
-              b = (U[c] * w + p.O[c * fs + tq]) + b;
+              b = (U[c] * w + GLSB_QF(p.fO + c)) + b;
             }
           r0[c] = d1 * a;
           r1[c] = d1 * b;
@@ -379,17 +393,17 @@ __device__ __forceinline__ void qpoint_physics(const KParams<T> &p, uint64_t tq,
       if (res && p.has_o)
 #pragma unroll
         for (int c = 0; c < dim; ++c)
-          td[c] += p.O[c * fs + tq];
+          td[c] += GLSB_QF(p.fO + c);
       if (res && p.theta_ne_1)
         {
           const T omt = T(1) - th;
 #pragma unroll
           for (int c = 0; c < dim; ++c)
             {
-              pbar[c] += omt * p.gold_p[c * fs + tq];
+              pbar[c] += omt * GLSB_QF(p.fgoldp + c);
 #pragma unroll
               for (int j = 0; j < dim; ++j)
-                B[c][j] += omt * p.Gold[(c * dim + j) * fs + tq];
+                B[c][j] += omt * GLSB_QF(p.fGold + c * dim + j);
             }
         }
       T divb = 0;
@@ -426,6 +440,7 @@ __device__ __forceinline__ void qpoint_physics(const KParams<T> &p, uint64_t tq,
         gout[d][d] += d2 * divb;
       vout[dim] = divb;
     }
+#undef GLSB_QF
 }
 
 // ---------------------------------------------------------------------------------------
@@ -448,9 +463,7 @@ __device__ __forceinline__ void cell_apply(Ctx<dim, n, T> &ctx, const KParams<T>
   GeomQ<dim, n, T> geo;
   geo.load(p, sh, cell, ctx.l, ctx.ii);
   geo.template to_physical<C>(rg, g);
-  const uint64_t tq = (uint64_t)ctx.l * p.ncp + cell;
-  const uint64_t fs = (uint64_t)Geo<dim, n>::nq * p.ncp;
-  qpoint_physics<dim, T, BR>(p, tq, cell, fs, val, g, vout, gout);
+  qpoint_physics<dim, T, BR>(p, qpos(p, (uint32_t)ctx.l, cell), cell, val, g, vout, gout);
   geo.template to_reference<C>(gout, rgq);
 #pragma unroll
   for (int c = 0; c < C; ++c)
@@ -512,9 +525,8 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_linearization(const KP
   GeomQ<dim, n, T> geo;
   geo.load(p, sh, cell, ctx.l, ctx.ii);
   geo.template to_physical<C>(rg, g);
-  const uint64_t tq = (uint64_t)ctx.l * p.ncp + cell;
-  const uint64_t fs = (uint64_t)G::nq * p.ncp;
-  T              u2 = 0;
+  const QPos<T> qp = qpos(p, (uint32_t)ctx.l, cell);
+  T             u2 = 0;
 #pragma unroll
   for (int c = 0; c < dim; ++c)
     u2 += val[c] * val[c];
@@ -545,38 +557,24 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_linearization(const KP
   const T      d2q  = sqrt(um2) * hq * T(0.5);
   if (!active)
     return;
+#define GLSB_QF(f) p.Q[qp.base + (uint64_t)(f)*qp.fstride]
   if (ctx.l == 0)
     {
       p.d1c[cell] = T(d1c);
       p.d2c[cell] = T(d2c);
     }
-  p.d1q[tq] = d1q;
-  p.d2q[tq] = d2q;
+  GLSB_QF(p.fd1q) = d1q;
+  GLSB_QF(p.fd2q) = d2q;
 #pragma unroll
   for (int c = 0; c < dim; ++c)
     {
-      p.U[c * fs + tq] = val[c];
-      p.P[c * fs + tq] = g[dim][c];
+      GLSB_QF(p.fU + c) = val[c];
+      GLSB_QF(p.fP + c) = g[dim][c];
 #pragma unroll
       for (int j = 0; j < dim; ++j)
-        p.H[(c * dim + j) * fs + tq] = g[c][j];
+        GLSB_QF(p.fH + c * dim + j) = g[c][j];
     }
-  if (p.R1 != nullptr)
-    {
-      const T d1 = p.cell_wise ? T(d1c) : d1q;
-#pragma unroll
-      for (int c = 0; c < dim; ++c)
-        {
-          T sgs = 0;
-#pragma unroll
-          for (int j = 0; j < dim; ++j)
-            sgs += g[c][j] * val[j];
-          T b = g[dim][c] + sgs;
-          if (p.ctd)
-            b = (val[c] * p.weight + p.O[c * fs + tq]) + b;
-          p.R1[c * fs + tq] = d1 * b;
-        }
-    }
+#undef GLSB_QF
 }
 
 // set_previous_solution (operator_ns.cc:234-320).  GRAD = false: u_time_derivative_old from
@@ -606,13 +604,13 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_previous(const KParams
   ctx.evaluate(val, rg);
   if (!active)
     return;
-  const uint64_t tq = (uint64_t)ctx.l * p.ncp + cell;
-  const uint64_t fs = (uint64_t)G::nq * p.ncp;
+  const QPos<T> qp = qpos(p, (uint32_t)ctx.l, cell);
+#define GLSB_QF(f) p.Q[qp.base + (uint64_t)(f)*qp.fstride]
   if (!GRAD)
     {
 #pragma unroll
       for (int c = 0; c < dim; ++c)
-        p.O[c * fs + tq] = val[c];
+        GLSB_QF(p.fO + c) = val[c];
     }
   else
     {
@@ -622,12 +620,13 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_previous(const KParams
 #pragma unroll
       for (int c = 0; c < dim; ++c)
         {
-          p.gold_p[c * fs + tq] = g[dim][c];
+          GLSB_QF(p.fgoldp + c) = g[dim][c];
 #pragma unroll
           for (int j = 0; j < dim; ++j)
-            p.Gold[(c * dim + j) * fs + tq] = g[c][j];
+            GLSB_QF(p.fGold + c * dim + j) = g[c][j];
         }
     }
+#undef GLSB_QF
 }
 
 // get_max_u (operator_ns.cc:530-568)

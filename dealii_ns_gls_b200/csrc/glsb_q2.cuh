@@ -8,12 +8,14 @@
 //     traffic and no CTA barrier for evaluate / integrate; 1-D matrices come from the constant
 //     bank (kernel parameter) as immediate operands.
 //   * the quadrature-point physics couples the components: the 4 lanes of a cell exchange
-//     u, p, the needed entries of grad u / grad p and the SUPG residual with warp shuffles
-//     (4 broadcasts + a 2-step butterfly for div u + a 3-step rotation in which every source lane
-//     serves exactly one reader).
-//   * the q-point tables (U, grad U, grad P [, du/dt_old, delta_q, J^-T, JxW]) of a batch are
-//     streamed HBM -> shared memory one quadrature layer ahead with cp.async.bulk (TMA engine,
-//     mbarrier complete_tx) into an NST-deep ring; rows are 32 cells wide (256 B in FP64).
+//     u, p, grad u, grad p and the SUPG residual through a small per-warp shared-memory scratch
+//     (__syncwarp only, bank-conflict-free by a 33-element row stride); the transposed accesses
+//     (lane c needs d_c u_j from lane j) are plain address arithmetic there, where a shuffle
+//     version needs per-lane register selects that ptxas turns into divergent branches.
+//   * the q-point tables (U, grad U, grad P [, du/dt_old, delta_q, J^-T, JxW]) are stored
+//     [batch][layer][field][9][32 cells]; the block a CTA needs for one quadrature layer is
+//     contiguous and is streamed HBM -> shared memory with ONE cp.async.bulk (TMA engine,
+//     mbarrier complete_tx) per layer into an NST-deep ring, issued 1-2 layers ahead.
 //   * gather straight from global memory (the 4 components of a node are adjacent lanes, so a
 //     node-major numbering gives full 32 B sectors), scatter with RED.ADD.F64 atomics.
 #pragma once
@@ -67,11 +69,6 @@ __device__ __forceinline__ T sel3(int c, T a0, T a1, T a2)
 {
   return c == 0 ? a0 : (c == 1 ? a1 : a2);
 }
-template <typename T>
-__device__ __forceinline__ T sel4(int c, T a0, T a1, T a2, T a3)
-{
-  return c == 0 ? a0 : (c == 1 ? a1 : (c == 2 ? a2 : a3));
-}
 
 template <typename T>
 __host__ __device__ constexpr size_t stage_elems(int F)
@@ -79,49 +76,44 @@ __host__ __device__ constexpr size_t stage_elems(int F)
   return (size_t)F * 9 * CELLS;
 }
 
-// issue the bulk copies of stage j (batch bi of this CTA, quadrature layer j % 3) into ring slot
-// j % NST; executed by all lanes of warp 0
+constexpr int XROW  = 33;       // row stride of the exchange scratch (elements)
+constexpr int XSLOT = 5 * XROW; // rows: value, d_0, d_1, d_2, y
+
+// issue the bulk copy of stage j (quadrature layer j % 3 of this CTA's batch j / 3) into ring slot
+// j % NST; called by all lanes of warp 0, one elected lane issues
 template <typename T, int NST>
-__device__ __forceinline__ void issue_stage(const KParams<T> &p, const Q2Stage<T> &sd, T *tab, uint64_t *full,
-                                            uint64_t *empty, uint32_t j, uint32_t cell0, int layer, int lane)
+__device__ __forceinline__ void issue_stage(const KParams<T> &p, int F, T *tab, uint64_t *full, uint64_t *empty,
+                                            uint32_t j, uint32_t cell0, int layer, int lane)
 {
   const uint32_t b = j % NST, r = j / NST;
   if (r >= 1)
     mbar_wait(&empty[b], (r - 1) & 1);
-  T *dst = tab + (size_t)b * stage_elems<T>(sd.F);
   if (lane == 0)
-    mbar_expect_tx(&full[b], (uint32_t)(sd.F * 9 * CELLS * sizeof(T)));
-  __syncwarp();
-  int fo = 0;
-  for (int g = 0; g < sd.n_groups; ++g)
     {
-      const int rows = sd.nf[g] * 9;
-      for (int rr = lane; rr < rows; rr += 32)
-        {
-          const int f = rr / 9, q9 = rr - 9 * f;
-          bulk_g2s(dst + ((size_t)(fo + f) * 9 + q9) * CELLS,
-                   sd.base[g] + ((size_t)(f * 27 + layer * 9 + q9) * p.ncp + cell0),
-                   (uint32_t)(CELLS * sizeof(T)), &full[b]);
-        }
-      fo += sd.nf[g];
+      const uint32_t bytes = (uint32_t)(stage_elems<T>(F) * sizeof(T));
+      const T *src = p.Q + (((uint64_t)(cell0 >> 5) * 3 + layer) * p.FT) * (9 * CELLS);
+      mbar_expect_tx(&full[b], bytes);
+      bulk_g2s(tab + (size_t)b * stage_elems<T>(F), src, bytes, &full[b]);
     }
+  __syncwarp();
 }
 
-template <typename T, bool GENERAL, int NST>
-__global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, const Shape<T, 3> sh,
-                                                            const Q2Stage<T> sd)
+template <typename T, bool GENERAL, bool CTD, bool CELLWISE, int NST>
+__global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, const Shape<T, 3> sh, const int F)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T        *tab   = reinterpret_cast<T *>(smem_raw);
-  uint64_t *full  = reinterpret_cast<uint64_t *>(smem_raw + NST * stage_elems<T>(sd.F) * sizeof(T));
+  T        *xch   = tab + NST * stage_elems<T>(F);                    // [warp][2][XSLOT]
+  uint64_t *full  = reinterpret_cast<uint64_t *>(xch + (TPB / 32) * 2 * XSLOT);
   uint64_t *empty = full + NST;
 
   const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int      c = lane & 3, col = 8 * warp + (lane >> 2);
   const bool     is_p = (c == 3);
   const int      cv   = is_p ? 0 : c; // table row used by this lane (pressure lane: any valid row)
-  const unsigned bl   = lane & ~3u;
+  const int      bl   = lane & ~3;
   const T        m0 = (c == 0) ? T(1) : T(0), m1 = (c == 1) ? T(1) : T(0), m2 = (c == 2) ? T(1) : T(0);
+  T             *xw   = xch + warp * 2 * XSLOT;
 
   if (threadIdx.x == 0)
     {
@@ -144,10 +136,10 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
     for (uint32_t j = 0; j < (uint32_t)(NST - 1) && j < n_stages; ++j)
       {
         const uint32_t bj = blockIdx.x + (j / 3) * gridDim.x;
-        issue_stage<T, NST>(p, sd, tab, full, empty, j, p.cell_begin + bj * CELLS, j % 3, lane);
+        issue_stage<T, NST>(p, F, tab, full, empty, j, p.cell_begin + bj * CELLS, j % 3, lane);
       }
 
-  const T w = p.weight, nu = p.nu;
+  const T  w = p.weight, nu = p.nu;
   uint32_t it = 0;
   for (uint32_t bi = 0; bi < my_n; ++bi)
     {
@@ -156,6 +148,7 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
       const uint32_t cellr  = cell0 + col;
       const bool     active = cell_active(p, cellr);
       const uint32_t cell   = cellr < p.cell_end ? cellr : p.cell_end - 1;
+      const uint32_t *__restrict__ ixp = p.idx + (uint64_t)(c * 27) * p.ncp + cell;
 
       // ---- gather (read_dof_values) ------------------------------------------------------
       T t[27];
@@ -163,7 +156,7 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
         uint32_t iv[27];
 #pragma unroll
         for (int j = 0; j < 27; ++j)
-          iv[j] = p.idx[(uint64_t)(c * 27 + j) * p.ncp + cell];
+          iv[j] = ixp[(uint64_t)j * p.ncp];
 #pragma unroll
         for (int j = 0; j < 27; ++j)
           t[j] = gather_resolved(p, p.src, iv[j]);
@@ -177,7 +170,7 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
           cdet = p.jxw[cell];
         }
       T d1c = 0, d2c = 0;
-      if (p.cell_wise)
+      if (CELLWISE)
         {
           d1c = p.d1c[cell];
           d2c = p.d2c[cell];
@@ -227,7 +220,7 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
             }
           const uint32_t slot = it % NST;
           mbar_wait(&full[slot], (it / NST) & 1);
-          const T *tb = tab + (size_t)slot * stage_elems<T>(sd.F) + col;
+          const T *tb = tab + (size_t)slot * stage_elems<T>(F) + col;
 #define GLSB_TAB(f, a) tb[((f)*9 + (a)) * CELLS]
 
 #pragma unroll
@@ -243,10 +236,10 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
               T J00, J01, J02, J10, J11, J12, J20, J21, J22;
               if (GENERAL)
                 {
-                  J00 = GLSB_TAB(sd.oJ + 0, a), J01 = GLSB_TAB(sd.oJ + 1, a), J02 = GLSB_TAB(sd.oJ + 2, a);
-                  J10 = GLSB_TAB(sd.oJ + 3, a), J11 = GLSB_TAB(sd.oJ + 4, a), J12 = GLSB_TAB(sd.oJ + 5, a);
-                  J20 = GLSB_TAB(sd.oJ + 6, a), J21 = GLSB_TAB(sd.oJ + 7, a), J22 = GLSB_TAB(sd.oJ + 8, a);
-                  jq  = GLSB_TAB(sd.ojxw, a);
+                  J00 = GLSB_TAB(p.fJ + 0, a), J01 = GLSB_TAB(p.fJ + 1, a), J02 = GLSB_TAB(p.fJ + 2, a);
+                  J10 = GLSB_TAB(p.fJ + 3, a), J11 = GLSB_TAB(p.fJ + 4, a), J12 = GLSB_TAB(p.fJ + 5, a);
+                  J20 = GLSB_TAB(p.fJ + 6, a), J21 = GLSB_TAB(p.fJ + 7, a), J22 = GLSB_TAB(p.fJ + 8, a);
+                  jq  = GLSB_TAB(p.fjxw, a);
                   g0  = J00 * rx + J10 * ry + J20 * rz;
                   g1  = J01 * rx + J11 * ry + J21 * rz;
                   g2  = J02 * rx + J12 * ry + J22 * rz;
@@ -256,57 +249,52 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
                   g0 = rx * ij0, g1 = ry * ij1, g2 = rz * ij2;
                   jq = cdet * wz * (sh.w[qx] * sh.w[qy]);
                 }
-              // tables
-              const T U0 = GLSB_TAB(sd.oU, a), U1 = GLSB_TAB(sd.oU + 1, a), U2 = GLSB_TAB(sd.oU + 2, a);
-              const T H0 = GLSB_TAB(sd.oH + 3 * cv, a), H1 = GLSB_TAB(sd.oH + 3 * cv + 1, a),
-                      H2 = GLSB_TAB(sd.oH + 3 * cv + 2, a);
-              const T Pc = GLSB_TAB(sd.oP + cv, a);
-              const T d1 = p.cell_wise ? d1c : GLSB_TAB(sd.od1q, a);
-              const T d2 = p.cell_wise ? d2c : GLSB_TAB(sd.od2q, a);
-              // values of all four components of this cell
-              const T u0 = __shfl_sync(0xffffffffu, val, bl), u1 = __shfl_sync(0xffffffffu, val, bl + 1),
-                      u2 = __shfl_sync(0xffffffffu, val, bl + 2), pp = __shfl_sync(0xffffffffu, val, bl + 3);
-              // div u: butterfly over the three velocity lanes (pressure lane contributes 0)
-              const T gcc = sel4<T>(c, g0, g1, g2, T(0));
-              const T dh  = gcc + __shfl_xor_sync(0xffffffffu, gcc, 1);
-              const T div = dh + __shfl_xor_sync(0xffffffffu, dh, 2);
-              const T td  = val * w;
-              const T sgu = g0 * U0 + g1 * U1 + g2 * U2; // U . grad u_c
-              const T ugs = H0 * u0 + H1 * u1 + H2 * u2; // u . grad U_c
-              T       y   = sgu + ugs;
-              if (p.ctd)
+              // ---- exchange round 1: publish value and gradient of this component --------------
+              T *xs = xw + (a & 1) * XSLOT;
+              xs[lane]            = val;
+              xs[XROW + lane]     = g0;
+              xs[2 * XROW + lane] = g1;
+              xs[3 * XROW + lane] = g2;
+              // tables (field offsets of the prefix are fixed: U 0..2, grad U 3..11, grad P 12..14)
+              const T U0 = GLSB_TAB(0, a), U1 = GLSB_TAB(1, a), U2 = GLSB_TAB(2, a);
+              const T H0 = GLSB_TAB(3 + 3 * cv, a), H1 = GLSB_TAB(4 + 3 * cv, a), H2 = GLSB_TAB(5 + 3 * cv, a);
+              const T Pc = GLSB_TAB(12 + cv, a);
+              const T d1 = CELLWISE ? d1c : GLSB_TAB(p.fd1q, a);
+              const T d2 = CELLWISE ? d2c : GLSB_TAB(p.fd2q, a);
+              __syncwarp();
+              const T u0 = xs[bl], u1 = xs[bl + 1], u2 = xs[bl + 2], pp = xs[bl + 3];
+              const T div = xs[XROW + bl] + xs[2 * XROW + bl + 1] + xs[3 * XROW + bl + 2];
+              // column c of grad u and d_c p: entry (1 + c) of lanes bl .. bl + 3
+              const T *xc  = xs + (1 + cv) * XROW + bl;
+              const T  Gc0 = xc[0], Gc1 = xc[1], Gc2 = xc[2], gpc = xc[3];
+              const T  td  = val * w;
+              const T  sgu = g0 * U0 + g1 * U1 + g2 * U2; // U . grad u_c
+              const T  ugs = H0 * u0 + H1 * u1 + H2 * u2; // u . grad U_c
+              T        y   = sgu + ugs;
+              if (CTD)
                 y = td + y;
-              // rotation exchange: in step k lane j is read by lane (j - k) & 3 only
-              const T su1 = sel4<T>(c, y, g0, g1, g2);
-              const T su2 = sel4<T>(c, g2, y, g0, g1);
-              const T su3 = sel4<T>(c, g1, g2, y, g0);
-              const T r1  = __shfl_sync(0xffffffffu, su1, bl + ((c + 1) & 3));
-              const T r2  = __shfl_sync(0xffffffffu, su2, bl + ((c + 2) & 3));
-              const T r3  = __shfl_sync(0xffffffffu, su3, bl + ((c + 3) & 3));
-              const T Gc0 = sel3<T>(c, g0, r3, r2); // d_c u_0
-              const T Gc1 = sel3<T>(c, r1, g1, r3); // d_c u_1
-              const T Gc2 = sel3<T>(c, r2, r1, g2); // d_c u_2
-              const T gpc = sel3<T>(c, r3, r2, r1); // d_c p
+              // ---- exchange round 2: the pressure row needs y of the three velocity rows --------
+              xs[4 * XROW + lane] = y;
               // velocity row c
               const T r0  = d1 * (y + gpc);
               const T sgs = H0 * U0 + H1 * U1 + H2 * U2; // U . grad U_c
               T       rb  = Pc + sgs;
-              if (p.ctd)
-                rb = (GLSB_TAB(sd.oU + cv, a) * w + GLSB_TAB(sd.oO + cv, a)) + rb;
+              if (CTD)
+                rb = (GLSB_TAB(cv, a) * w + GLSB_TAB(p.fO + cv, a)) + rb;
               const T rr1  = d1 * rb;
               const T diag = d2 * div - pp;
               T       vo   = td + sgu + ugs;
               T       o0   = nu * (g0 + Gc0) + U0 * r0 + u0 * rr1 + m0 * diag;
               T       o1   = nu * (g1 + Gc1) + U1 * r0 + u1 * rr1 + m1 * diag;
               T       o2   = nu * (g2 + Gc2) + U2 * r0 + u2 * rr1 + m2 * diag;
-              // pressure row: (q, div u) and delta_1 (grad q, residual_0); r1..r3 = y_0..y_2 there
-              if (is_p)
-                {
-                  vo = div;
-                  o0 = d1 * (r1 + g0);
-                  o1 = d1 * (r2 + g1);
-                  o2 = d1 * (r3 + g2);
-                }
+              __syncwarp();
+              // pressure row: (q, div u) and delta_1 (grad q, residual_0)
+              const T y0 = xs[4 * XROW + bl], y1 = xs[4 * XROW + bl + 1], y2 = xs[4 * XROW + bl + 2];
+              const T q0 = d1 * (y0 + g0), q1 = d1 * (y1 + g1), q2 = d1 * (y2 + g2);
+              vo = is_p ? div : vo;
+              o0 = is_p ? q0 : o0;
+              o1 = is_p ? q1 : o1;
+              o2 = is_p ? q2 : o2;
               // submit_value / submit_gradient: times JxW, back to the reference cell
               vo *= jq;
               T ox, oy, oz;
@@ -343,7 +331,7 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
               if (j < n_stages)
                 {
                   const uint32_t bj = blockIdx.x + (j / 3) * gridDim.x;
-                  issue_stage<T, NST>(p, sd, tab, full, empty, j, p.cell_begin + bj * CELLS, j % 3, lane);
+                  issue_stage<T, NST>(p, F, tab, full, empty, j, p.cell_begin + bj * CELLS, j % 3, lane);
                 }
             }
 #pragma unroll
@@ -375,25 +363,32 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
             acc[3 * l + q] = sh.S[q] * a + sh.S[3 + q] * b + sh.S[6 + q] * d;
         }
 
-      // ---- scatter (distribute_local_to_global) --------------------------------------------
+      // ---- scatter (distribute_local_to_global): all index loads first, then the atomics ---
       if (active)
         {
+          uint32_t iv[27];
 #pragma unroll
           for (int j = 0; j < 27; ++j)
-            {
-              const uint32_t iv = p.idx[(uint64_t)(c * 27 + j) * p.ncp + cell];
-              scatter_resolved(p, p.dst, iv, acc[j]);
-            }
+            iv[j] = ixp[(uint64_t)j * p.ncp];
+#pragma unroll
+          for (int j = 0; j < 27; ++j)
+            scatter_resolved(p, p.dst, iv[j], acc[j]);
         }
     }
 }
 
-template <typename T, bool GENERAL, int NST>
-static int launch(const KParams<T> &p, const Shape<T, 3> &S, const Q2Stage<T> &sd, cudaStream_t s)
+template <typename T>
+size_t smem_bytes(int F, int nst)
 {
-  static int blocks_per_sm = -1, n_sm = 0;
-  const size_t smem = NST * stage_elems<T>(sd.F) * sizeof(T) + 2 * NST * sizeof(uint64_t);
-  auto         kern = k_vmult_q2_newton<T, GENERAL, NST>;
+  return (nst * stage_elems<T>(F) + (TPB / 32) * 2 * XSLOT) * sizeof(T) + 2 * nst * sizeof(uint64_t);
+}
+
+template <typename T, bool GENERAL, bool CTD, bool CELLWISE, int NST>
+static int launch(const KParams<T> &p, const Shape<T, 3> &S, int F, cudaStream_t s)
+{
+  static int   n_sm = 0;
+  const size_t smem = smem_bytes<T>(F, NST);
+  auto         kern = k_vmult_q2_newton<T, GENERAL, CTD, CELLWISE, NST>;
   if (smem > 227 * 1024)
     return -1;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -401,17 +396,24 @@ static int launch(const KParams<T> &p, const Shape<T, 3> &S, const Q2Stage<T> &s
   int bps = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TPB, smem) != cudaSuccess || bps < 1)
     return -1;
-  if (blocks_per_sm < 0)
+  if (n_sm == 0)
     {
       int dev = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     }
-  blocks_per_sm            = bps;
   const uint32_t n_batches = (p.cell_end - p.cell_begin + CELLS - 1) / CELLS;
   const uint32_t grid      = n_batches < (uint32_t)(n_sm * bps) ? n_batches : (uint32_t)(n_sm * bps);
-  kern<<<grid, TPB, smem, s>>>(p, S, sd);
+  kern<<<grid, TPB, smem, s>>>(p, S, F);
   return cudaGetLastError() != cudaSuccess;
+}
+
+template <typename T, bool GENERAL, int NST>
+static int launch_flags(const KParams<T> &p, const Shape<T, 3> &S, int F, cudaStream_t s)
+{
+  if (p.ctd)
+    return p.cell_wise ? launch<T, GENERAL, true, true, NST>(p, S, F, s) : launch<T, GENERAL, true, false, NST>(p, S, F, s);
+  return p.cell_wise ? launch<T, GENERAL, false, true, NST>(p, S, F, s) : launch<T, GENERAL, false, false, NST>(p, S, F, s);
 }
 
 } // namespace q2
