@@ -128,7 +128,7 @@ __global__ void k_invert_guarded(T *__restrict__ v, uint64_t n)
 template <typename T>
 __global__ void k_export_table(const T *__restrict__ Q, const uint32_t *__restrict__ perm, T *__restrict__ out,
                                uint32_t n_cells, uint32_t n_slots, uint32_t hole_begin, uint32_t hole_end,
-                               uint32_t nq, uint32_t nf, int FT, int NL, int QG, int f0, int per_cell)
+                               uint32_t nq, uint32_t nf, int FT, int NL, int QG, int f0, int per_cell, int rowdiv)
 {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (uint64_t)nf * nq * n_slots)
@@ -144,7 +144,8 @@ __global__ void k_export_table(const T *__restrict__ Q, const uint32_t *__restri
   else
     {
       const uint32_t layer = q / QG, ql = q - layer * QG;
-      o = ((((uint64_t)(i >> 5) * NL + layer) * FT + (f0 + f)) * QG + ql) * 32 + (i & 31);
+      const uint32_t row = rowdiv > 0 ? f / rowdiv : 0; // component row of the field (rotation, see qoff())
+      o = ((((uint64_t)(i >> 5) * NL + layer) * FT + (f0 + f)) * QG + ql) * 32 + (((i & 31) + 4 * row) & 31);
     }
   out[((uint64_t)f * n_cells + perm[i]) * nq + q] = Q[o];
 }
@@ -161,7 +162,7 @@ struct glsb_op
   uint64_t n_export = 0;
   size_t   tsize = 8;
 
-  DevBuf perm, idx, row_dof, row_ptr, ecol, eval, cidx, inv_jac, jxw, h_min, measure, export_idx;
+  DevBuf perm, idx, cell_flags, row_dof, row_ptr, ecol, eval, cidx, inv_jac, jxw, h_min, measure, export_idx;
   DevBuf Q, d1c, d2c, max_bits;
   int    FT = 0, NL = 1, QG = 1, F_stage = 0;
   int    fU = -1, fH = -1, fP = -1, fO = -1, fd1q = -1, fd2q = -1, fJ = -1, fjxw = -1, fGold = -1, fgoldp = -1;
@@ -203,6 +204,7 @@ KParams<T> base_params(const glsb_op *op)
   memset(&p, 0, sizeof p);
   p.ncp        = op->ncp;
   p.idx        = op->idx.as<uint32_t>();
+  p.cell_flags = op->cell_flags.as<uint8_t>();
   p.row_dof    = op->row_dof.as<uint32_t>();
   p.row_ptr    = op->row_ptr.as<uint32_t>();
   p.ecol       = op->ecol.as<uint32_t>();
@@ -480,7 +482,7 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
       if (d->row_dof[r] >= d->n_owned)
         row_ghost[r] = 1;
     }
-  std::vector<uint8_t> is_boundary(nc, 0), has_weighted(nc, 0);
+  std::vector<uint8_t> is_boundary(nc, 0), has_weighted(nc, 0), has_constrained(nc, 0);
   for (uint32_t k = 0; k < nc && ok; ++k)
     {
       const uint32_t *row = d->dof_indices + (uint64_t)k * ndof;
@@ -496,6 +498,7 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
                   why = "dof_indices refers to a constraint row that does not exist";
                   break;
                 }
+              has_constrained[k] = 1;
               is_boundary[k] |= row_ghost[r];
               has_weighted[k] |= row_weighted[r];
             }
@@ -538,6 +541,12 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
   auto slot_is_real = [&](uint64_t i) { return i < op->n_interior || (i >= op->n_int_pad && i < op->n_slots); };
 
   ok = ok && upload(op->perm, perm.data(), perm.size() * 4);
+  {
+    std::vector<uint8_t> fl(op->ncp);
+    for (uint64_t i = 0; i < op->ncp; ++i)
+      fl[i] = has_constrained[perm[i]];
+    ok = ok && upload(op->cell_flags, fl.data(), fl.size());
+  }
 
   // ---- dof indices: [cell][dof] -> [dof][ncp] in internal order -------------------------
   {
@@ -1025,17 +1034,17 @@ int glsb_get_table(glsb_op *op, const char *name, void *out, uint64_t out_count,
     return fail(op, "glsb_get_table: null argument");
   uint32_t      nf = 0, nq = op->nq;
   const int     d  = op->dim;
-  int           f0 = -1, per_cell = 0;
+  int           f0 = -1, per_cell = 0, rowdiv = 0;
   const void   *base = op->Q.p;
   const std::string s(name);
   if (s == "u_star_value")
-    f0 = op->fU, nf = d;
+    f0 = op->fU, nf = d, rowdiv = 1;
   else if (s == "u_star_gradient")
-    f0 = op->fH, nf = d * d;
+    f0 = op->fH, nf = d * d, rowdiv = d;
   else if (s == "p_star_gradient")
-    f0 = op->fP, nf = d;
+    f0 = op->fP, nf = d, rowdiv = 1;
   else if (s == "u_time_derivative_old")
-    f0 = op->fO, nf = d;
+    f0 = op->fO, nf = d, rowdiv = 1;
   else if (s == "u_old_gradient")
     f0 = op->fGold, nf = d * d;
   else if (s == "p_old_gradient")
@@ -1060,11 +1069,11 @@ int glsb_get_table(glsb_op *op, const char *name, void *out, uint64_t out_count,
   if (op->number_type == GLSB_F64)
     k_export_table<double><<<g, 256, 0, (cudaStream_t)stream>>>(
       (const double *)base, op->perm.as<uint32_t>(), (double *)out, (uint32_t)op->n_cells, op->n_slots,
-      op->n_interior, op->n_int_pad, nq, nf, op->FT, op->NL, op->QG, f0, per_cell);
+      op->n_interior, op->n_int_pad, nq, nf, op->FT, op->NL, op->QG, f0, per_cell, rowdiv);
   else
     k_export_table<float><<<g, 256, 0, (cudaStream_t)stream>>>(
       (const float *)base, op->perm.as<uint32_t>(), (float *)out, (uint32_t)op->n_cells, op->n_slots,
-      op->n_interior, op->n_int_pad, nq, nf, op->FT, op->NL, op->QG, f0, per_cell);
+      op->n_interior, op->n_int_pad, nq, nf, op->FT, op->NL, op->QG, f0, per_cell, rowdiv);
   if (cudaGetLastError() != cudaSuccess)
     return cuda_fail(op, "glsb_get_table");
   return 0;

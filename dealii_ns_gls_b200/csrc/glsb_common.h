@@ -46,6 +46,7 @@ struct KParams
   uint32_t hole_begin, hole_end; // padding slots between the interior and the boundary range
   uint64_t ncp;
   const uint32_t *idx; // [C*n_loc][ncp]
+  const uint8_t  *cell_flags; // [ncp] bit 0: the cell has constrained dofs
   // constraint rows
   const uint32_t *row_dof, *row_ptr, *ecol;
   const T        *eval;
@@ -88,21 +89,33 @@ __host__ __device__ inline bool cell_active(const KParams<T> &p, uint32_t cell)
   return cell < p.cell_end && !(cell >= p.hole_begin && cell < p.hole_end);
 }
 
-// position of (point q, cell) in the blocked q-point array; field f adds f * fstride
+// position of (point q, cell) in the blocked q-point array.  Field f of (q, cell) lives at
+//   base + f * fstride + ((lane32 + rot(f)) & 31),  lane32 = cell & 31,
+// where rot(f) = 4 * (component row of the field) for u_star_value[c], u_star_gradient[c][.],
+// p_star_gradient[c], u_time_derivative_old[c] and 0 otherwise: the Q2 kernel has the 4 component
+// lanes of a cell read rows c = 0..2 of these fields in one request, and the rotation puts them
+// in different shared-memory banks.
 template <typename T>
 struct QPos
 {
   uint64_t base;
-  uint32_t fstride;
+  uint32_t fstride, lane32;
 };
 template <typename T>
 __host__ __device__ inline QPos<T> qpos(const KParams<T> &p, uint32_t q, uint32_t cell)
 {
   QPos<T> r;
   const uint32_t layer = q / (uint32_t)p.QG, ql = q - layer * (uint32_t)p.QG;
-  r.base    = ((((uint64_t)(cell >> 5) * p.NL + layer) * p.FT) * p.QG + ql) * 32 + (cell & 31);
+  r.base    = ((((uint64_t)(cell >> 5) * p.NL + layer) * p.FT) * p.QG + ql) * 32;
   r.fstride = (uint32_t)p.QG * 32;
+  r.lane32  = cell & 31;
   return r;
+}
+// offset of field f with component row `row` (0 for fields without one)
+template <typename T>
+__host__ __device__ inline uint64_t qoff(const QPos<T> &qp, int f, int row)
+{
+  return qp.base + (uint64_t)f * qp.fstride + ((qp.lane32 + 4u * (uint32_t)row) & 31u);
 }
 
 // columns of C_cell for cells with weighted constraint rows (compute_diagonal)

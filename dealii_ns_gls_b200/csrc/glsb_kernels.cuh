@@ -227,8 +227,8 @@ struct GeomQ
         for (int e = 0; e < dim; ++e)
 #pragma unroll
           for (int j = 0; j < dim; ++j)
-            ij[e][j] = p.Q[qp.base + (uint64_t)(p.fJ + e * dim + j) * qp.fstride];
-        jxw = p.Q[qp.base + (uint64_t)p.fjxw * qp.fstride];
+            ij[e][j] = p.Q[qoff(qp, p.fJ + e * dim + j, 0)];
+        jxw = p.Q[qoff(qp, p.fjxw, 0)];
       }
   }
   template <int C>
@@ -300,14 +300,14 @@ __device__ __forceinline__ void qpoint_physics(const KParams<T> &p, const QPos<T
                                                const T (&val)[dim + 1], const T (&g)[dim + 1][dim],
                                                T (&vout)[dim + 1], T (&gout)[dim + 1][dim])
 {
-#define GLSB_QF(f) p.Q[qp.base + (uint64_t)(f)*qp.fstride]
-  const T d1 = p.cell_wise ? p.d1c[cell] : GLSB_QF(p.fd1q);
-  const T d2 = p.cell_wise ? p.d2c[cell] : GLSB_QF(p.fd2q);
+#define GLSB_QF(f, row) p.Q[qoff(qp, (f), (row))]
+  const T d1 = p.cell_wise ? p.d1c[cell] : GLSB_QF(p.fd1q, 0);
+  const T d2 = p.cell_wise ? p.d2c[cell] : GLSB_QF(p.fd2q, 0);
   const T w  = p.weight;
   T       U[dim];
 #pragma unroll
   for (int j = 0; j < dim; ++j)
-    U[j] = GLSB_QF(p.fU + j);
+    U[j] = GLSB_QF(p.fU + j, j);
 #pragma unroll
   for (int c = 0; c <= dim; ++c)
 #pragma unroll
@@ -320,10 +320,10 @@ __device__ __forceinline__ void qpoint_physics(const KParams<T> &p, const QPos<T
 #pragma unroll
       for (int c = 0; c < dim; ++c)
         {
-          P[c] = GLSB_QF(p.fP + c);
+          P[c] = GLSB_QF(p.fP + c, c);
 #pragma unroll
           for (int j = 0; j < dim; ++j)
-            H[c][j] = GLSB_QF(p.fH + c * dim + j);
+            H[c][j] = GLSB_QF(p.fH + c * dim + j, c);
         }
       T Gm[dim][dim];
       T div = 0;
@@ -354,7 +354,7 @@ __device__ __forceinline__ void qpoint_physics(const KParams<T> &p, const QPos<T
           if (p.ctd)
             {
               a = td + a;
-              b = (U[c] * w + GLSB_QF(p.fO + c)) + b;
+              b = (U[c] * w + GLSB_QF(p.fO + c, c)) + b;
             }
           r0[c] = d1 * a;
           r1[c] = d1 * b;
@@ -393,17 +393,17 @@ __device__ __forceinline__ void qpoint_physics(const KParams<T> &p, const QPos<T
       if (res && p.has_o)
 #pragma unroll
         for (int c = 0; c < dim; ++c)
-          td[c] += GLSB_QF(p.fO + c);
+          td[c] += GLSB_QF(p.fO + c, c);
       if (res && p.theta_ne_1)
         {
           const T omt = T(1) - th;
 #pragma unroll
           for (int c = 0; c < dim; ++c)
             {
-              pbar[c] += omt * GLSB_QF(p.fgoldp + c);
+              pbar[c] += omt * GLSB_QF(p.fgoldp + c, 0);
 #pragma unroll
               for (int j = 0; j < dim; ++j)
-                B[c][j] += omt * GLSB_QF(p.fGold + c * dim + j);
+                B[c][j] += omt * GLSB_QF(p.fGold + c * dim + j, 0);
             }
         }
       T divb = 0;
@@ -557,22 +557,22 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_linearization(const KP
   const T      d2q  = sqrt(um2) * hq * T(0.5);
   if (!active)
     return;
-#define GLSB_QF(f) p.Q[qp.base + (uint64_t)(f)*qp.fstride]
+#define GLSB_QF(f, row) p.Q[qoff(qp, (f), (row))]
   if (ctx.l == 0)
     {
       p.d1c[cell] = T(d1c);
       p.d2c[cell] = T(d2c);
     }
-  GLSB_QF(p.fd1q) = d1q;
-  GLSB_QF(p.fd2q) = d2q;
+  GLSB_QF(p.fd1q, 0) = d1q;
+  GLSB_QF(p.fd2q, 0) = d2q;
 #pragma unroll
   for (int c = 0; c < dim; ++c)
     {
-      GLSB_QF(p.fU + c) = val[c];
-      GLSB_QF(p.fP + c) = g[dim][c];
+      GLSB_QF(p.fU + c, c) = val[c];
+      GLSB_QF(p.fP + c, c) = g[dim][c];
 #pragma unroll
       for (int j = 0; j < dim; ++j)
-        GLSB_QF(p.fH + c * dim + j) = g[c][j];
+        GLSB_QF(p.fH + c * dim + j, c) = g[c][j];
     }
 #undef GLSB_QF
 }
@@ -605,12 +605,12 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_previous(const KParams
   if (!active)
     return;
   const QPos<T> qp = qpos(p, (uint32_t)ctx.l, cell);
-#define GLSB_QF(f) p.Q[qp.base + (uint64_t)(f)*qp.fstride]
+#define GLSB_QF(f, row) p.Q[qoff(qp, (f), (row))]
   if (!GRAD)
     {
 #pragma unroll
       for (int c = 0; c < dim; ++c)
-        GLSB_QF(p.fO + c) = val[c];
+        GLSB_QF(p.fO + c, c) = val[c];
     }
   else
     {
@@ -620,10 +620,10 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_previous(const KParams
 #pragma unroll
       for (int c = 0; c < dim; ++c)
         {
-          GLSB_QF(p.fgoldp + c) = g[dim][c];
+          GLSB_QF(p.fgoldp + c, 0) = g[dim][c];
 #pragma unroll
           for (int j = 0; j < dim; ++j)
-            GLSB_QF(p.fGold + c * dim + j) = g[c][j];
+            GLSB_QF(p.fGold + c * dim + j, 0) = g[c][j];
         }
     }
 #undef GLSB_QF

@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
   const int      bl   = lane & ~3;
   const T        m0 = (c == 0) ? T(1) : T(0), m1 = (c == 1) ? T(1) : T(0), m2 = (c == 2) ? T(1) : T(0);
   T             *xw   = xch + warp * 2 * XSLOT;
+  // column of this lane's cell in a 32-cell table row, for fields of component row 0, 1, 2 and cv
+  const int      colr[4] = {col, (col + 4) & 31, (col + 8) & 31, (col + 4 * cv) & 31};
 
   if (threadIdx.x == 0)
     {
@@ -150,6 +152,15 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
       const uint32_t cell   = cellr < p.cell_end ? cellr : p.cell_end - 1;
       const uint32_t *__restrict__ ixp = p.idx + (uint64_t)(c * 27) * p.ncp + cell;
 
+      // pull the dof-index rows of this CTA's next batch into L2 while this batch computes
+      if (bi + 1 < my_n && threadIdx.x < 108)
+        {
+          const uint32_t *nx = p.idx + (uint64_t)threadIdx.x * p.ncp + (cell0 + gridDim.x * CELLS);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+        }
+      // cells with constrained dofs are rare: one warp-uniform test instead of one per dof
+      const bool slow = __any_sync(0xffffffffu, p.cell_flags[cell] != 0);
+
       // ---- gather (read_dof_values) ------------------------------------------------------
       T t[27];
       {
@@ -157,9 +168,18 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
 #pragma unroll
         for (int j = 0; j < 27; ++j)
           iv[j] = ixp[(uint64_t)j * p.ncp];
+        if (!slow)
+          {
 #pragma unroll
-        for (int j = 0; j < 27; ++j)
-          t[j] = gather_resolved(p, p.src, iv[j]);
+            for (int j = 0; j < 27; ++j)
+              t[j] = p.src[iv[j]];
+          }
+        else
+          {
+#pragma unroll
+            for (int j = 0; j < 27; ++j)
+              t[j] = gather_resolved(p, p.src, iv[j]);
+          }
       }
       T ij0 = 0, ij1 = 0, ij2 = 0, cdet = 0;
       if (!GENERAL)
@@ -220,8 +240,9 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
             }
           const uint32_t slot = it % NST;
           mbar_wait(&full[slot], (it / NST) & 1);
-          const T *tb = tab + (size_t)slot * stage_elems<T>(F) + col;
-#define GLSB_TAB(f, a) tb[((f)*9 + (a)) * CELLS]
+          const T *tb = tab + (size_t)slot * stage_elems<T>(F);
+#define GLSB_TAB(f, a) tb[((f)*9 + (a)) * CELLS + col]          /* fields without a component row */
+#define GLSB_TABR(f, a, r) tb[((f)*9 + (a)) * CELLS + colr[r]] /* rotated by 4 * row, see qoff() */
 
 #pragma unroll
           for (int a = 0; a < 9; ++a)
@@ -256,9 +277,9 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
               xs[2 * XROW + lane] = g1;
               xs[3 * XROW + lane] = g2;
               // tables (field offsets of the prefix are fixed: U 0..2, grad U 3..11, grad P 12..14)
-              const T U0 = GLSB_TAB(0, a), U1 = GLSB_TAB(1, a), U2 = GLSB_TAB(2, a);
-              const T H0 = GLSB_TAB(3 + 3 * cv, a), H1 = GLSB_TAB(4 + 3 * cv, a), H2 = GLSB_TAB(5 + 3 * cv, a);
-              const T Pc = GLSB_TAB(12 + cv, a);
+              const T U0 = GLSB_TABR(0, a, 0), U1 = GLSB_TABR(1, a, 1), U2 = GLSB_TABR(2, a, 2);
+              const T H0 = GLSB_TABR(3 + 3 * cv, a, 3), H1 = GLSB_TABR(4 + 3 * cv, a, 3), H2 = GLSB_TABR(5 + 3 * cv, a, 3);
+              const T Pc = GLSB_TABR(12 + cv, a, 3);
               const T d1 = CELLWISE ? d1c : GLSB_TAB(p.fd1q, a);
               const T d2 = CELLWISE ? d2c : GLSB_TAB(p.fd2q, a);
               __syncwarp();
@@ -280,7 +301,7 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
               const T sgs = H0 * U0 + H1 * U1 + H2 * U2; // U . grad U_c
               T       rb  = Pc + sgs;
               if (CTD)
-                rb = (GLSB_TAB(cv, a) * w + GLSB_TAB(p.fO + cv, a)) + rb;
+                rb = (GLSB_TABR(cv, a, 3) * w + GLSB_TABR(p.fO + cv, a, 3)) + rb;
               const T rr1  = d1 * rb;
               const T diag = d2 * div - pp;
               T       vo   = td + sgu + ugs;
@@ -321,6 +342,7 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
               acc[a + 18] += gz2 * oz;
             }
 #undef GLSB_TAB
+#undef GLSB_TABR
           // release the ring slot, then let warp 0 refill the slot released one layer ago
           __syncwarp();
           if (lane == 0)
@@ -370,9 +392,18 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
 #pragma unroll
           for (int j = 0; j < 27; ++j)
             iv[j] = ixp[(uint64_t)j * p.ncp];
+          if (!slow)
+            {
 #pragma unroll
-          for (int j = 0; j < 27; ++j)
-            scatter_resolved(p, p.dst, iv[j], acc[j]);
+              for (int j = 0; j < 27; ++j)
+                atomic_add(p.dst + iv[j], acc[j]);
+            }
+          else
+            {
+#pragma unroll
+              for (int j = 0; j < 27; ++j)
+                scatter_resolved(p, p.dst, iv[j], acc[j]);
+            }
         }
     }
 }
