@@ -52,13 +52,14 @@ struct DevBuf
 };
 
 __global__ void k_transpose_idx(const uint32_t *__restrict__ raw, const uint32_t *__restrict__ perm,
-                                uint32_t *__restrict__ out, uint32_t n_cells, uint32_t ndof, uint64_t ncp)
+                                uint32_t *__restrict__ out, uint32_t n_cells, uint32_t ndof, uint32_t nloc, uint64_t ncp)
 {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (uint64_t)ndof * ncp)
     return;
   const uint32_t i = t % ncp, d = t / ncp;
-  out[t]           = raw[(uint64_t)perm[i] * ndof + d]; // perm is defined for every slot (padding repeats a cell)
+  // blocked [ncp/32][ndof][32]; perm is defined for every slot (padding repeats a cell)
+  out[((uint64_t)(i >> 5) * ndof + d) * 32 + (((i & 31) + 8 * (d / nloc)) & 31)] = raw[(uint64_t)perm[i] * ndof + d];
 }
 
 // general geometry raw[(cell*nq + q)*inner + f] (double, caller's cell order) -> blocked q-point
@@ -204,6 +205,8 @@ KParams<T> base_params(const glsb_op *op)
   memset(&p, 0, sizeof p);
   p.ncp        = op->ncp;
   p.idx        = op->idx.as<uint32_t>();
+  p.ndof       = (uint32_t)(op->C * op->n_loc);
+  p.nloc       = (uint32_t)op->n_loc;
   p.cell_flags = op->cell_flags.as<uint8_t>();
   p.row_dof    = op->row_dof.as<uint32_t>();
   p.row_ptr    = op->row_ptr.as<uint32_t>();
@@ -557,7 +560,7 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
       {
         const uint64_t tot = (uint64_t)ndof * op->ncp;
         k_transpose_idx<<<(unsigned)((tot + 255) / 256), 256>>>(raw.as<uint32_t>(), op->perm.as<uint32_t>(),
-                                                                 op->idx.as<uint32_t>(), nc, ndof, op->ncp);
+                                                                 op->idx.as<uint32_t>(), nc, ndof, (uint32_t)op->n_loc, op->ncp);
         ok = cudaDeviceSynchronize() == cudaSuccess;
       }
   }

@@ -45,7 +45,8 @@ struct KParams
   uint32_t cell_begin, cell_end;
   uint32_t hole_begin, hole_end; // padding slots between the interior and the boundary range
   uint64_t ncp;
-  const uint32_t *idx; // [C*n_loc][ncp]
+  const uint32_t *idx; // blocked [ncp/32][ndof = C*n_loc][32]: see idx_at()
+  uint32_t        ndof, nloc;
   const uint8_t  *cell_flags; // [ncp] bit 0: the cell has constrained dofs
   // constraint rows
   const uint32_t *row_dof, *row_ptr, *ecol;
@@ -82,6 +83,16 @@ struct KParams
   T       *dst;
   unsigned long long *max_bits; // get_max_u
 };
+
+// dof index of local dof `dof` of cell `cell`: rows of 32 consecutive cells are contiguous (coalesced
+// for every kernel) and the ndof rows of a 32-cell batch are one contiguous block (one bulk copy)
+template <typename T>
+__host__ __device__ inline uint64_t idx_at(const KParams<T> &p, uint32_t dof, uint32_t cell)
+{
+  // inside its row, component c's entry of a cell is rotated by 8c cells: the 4 component lanes of a
+  // cell in the Q2 kernel then hit 4 different shared-memory banks when the block is staged there
+  return ((uint64_t)(cell >> 5) * p.ndof + dof) * 32 + (((cell & 31) + 8 * (dof / p.nloc)) & 31);
+}
 
 template <typename T>
 __host__ __device__ inline bool cell_active(const KParams<T> &p, uint32_t cell)

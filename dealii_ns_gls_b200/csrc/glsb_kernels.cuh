@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_vmult_generic(const KP
 #pragma unroll
   for (int c = 0; c < G::C; ++c)
     {
-      iv[c] = p.idx[(uint64_t)(c * G::n_loc + ctx.l) * p.ncp + cell];
+      iv[c] = p.idx[idx_at(p, c * G::n_loc + ctx.l, cell)];
       ctx.v[ctx.at(c, ctx.l)] =
         (BR == BR_RESIDUAL) ? p.src[plain_index(p, iv[c])] : gather_resolved(p, p.src, iv[c]);
     }
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_linearization(const KP
   const uint32_t cell   = cell0 < p.cell_end ? cell0 : p.cell_end - 1;
 #pragma unroll
   for (int c = 0; c < C; ++c)
-    ctx.v[ctx.at(c, ctx.l)] = p.src[plain_index(p, p.idx[(uint64_t)(c * G::n_loc + ctx.l) * p.ncp + cell])];
+    ctx.v[ctx.at(c, ctx.l)] = p.src[plain_index(p, p.idx[idx_at(p, c * G::n_loc + ctx.l, cell)])];
   __syncthreads();
   T val[C], rg[C][dim], g[C][dim];
   ctx.evaluate(val, rg);
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_previous(const KParams
 #pragma unroll
   for (int c = 0; c < C; ++c)
     {
-      const uint32_t i = plain_index(p, p.idx[(uint64_t)(c * G::n_loc + ctx.l) * p.ncp + cell]);
+      const uint32_t i = plain_index(p, p.idx[idx_at(p, c * G::n_loc + ctx.l, cell)]);
       T              s = 0;
       for (int k = 0; k < p.hist_n; ++k)
         s += p.hist_w[k] * p.hist[k][i];
@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_max_u(const KParams<T>
   const uint32_t cell   = cell0 < p.cell_end ? cell0 : p.cell_end - 1;
 #pragma unroll
   for (int c = 0; c < C; ++c)
-    ctx.v[ctx.at(c, ctx.l)] = p.src[plain_index(p, p.idx[(uint64_t)(c * G::n_loc + ctx.l) * p.ncp + cell])];
+    ctx.v[ctx.at(c, ctx.l)] = p.src[plain_index(p, p.idx[idx_at(p, c * G::n_loc + ctx.l, cell)])];
   __syncthreads();
   T val[C], rg[C][dim];
   ctx.evaluate(val, rg);
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_diag_generic(const KPa
 #pragma unroll
   for (int c = 0; c < C; ++c)
     {
-      const uint32_t iv = p.idx[(uint64_t)(c * G::n_loc + ctx.l) * p.ncp + cell];
+      const uint32_t iv = p.idx[idx_at(p, c * G::n_loc + ctx.l, cell)];
       if (!(iv & GLSB_CONSTRAINED_BIT))
         atomic_add(p.dst + iv, mine[c]);
     }

@@ -76,6 +76,7 @@ __host__ __device__ constexpr size_t stage_elems(int F)
   return (size_t)F * 9 * CELLS;
 }
 
+constexpr int IDX_ELEMS = 108 * CELLS; // dof indices of one batch
 constexpr int XROW  = 33;       // row stride of the exchange scratch (elements)
 constexpr int XSLOT = 5 * XROW; // rows: value, d_0, d_1, d_2, y
 
@@ -104,8 +105,10 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T        *tab   = reinterpret_cast<T *>(smem_raw);
   T        *xch   = tab + NST * stage_elems<T>(F);                    // [warp][2][XSLOT]
-  uint64_t *full  = reinterpret_cast<uint64_t *>(xch + (TPB / 32) * 2 * XSLOT);
+  uint32_t *ibuf  = reinterpret_cast<uint32_t *>(xch + (TPB / 32) * 2 * XSLOT); // [2][108][32] dof indices
+  uint64_t *full  = reinterpret_cast<uint64_t *>(ibuf + 2 * IDX_ELEMS);
   uint64_t *empty = full + NST;
+  uint64_t *ifull = empty + NST, *iempty = ifull + 2;
 
   const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int      c = lane & 3, col = 8 * warp + (lane >> 2);
@@ -124,6 +127,11 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
           mbar_init(&full[s], 1);
           mbar_init(&empty[s], TPB / 32);
         }
+      for (int s = 0; s < 2; ++s)
+        {
+          mbar_init(&ifull[s], 1);
+          mbar_init(&iempty[s], TPB / 32);
+        }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -141,6 +149,22 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
         issue_stage<T, NST>(p, F, tab, full, empty, j, p.cell_begin + bj * CELLS, j % 3, lane);
       }
 
+  // dof indices of batch bi of this CTA -> index ring slot bi & 1 (one bulk copy of 13.5 KB)
+  auto issue_idx = [&](uint32_t bi) {
+    const uint32_t b = bi & 1, r = bi >> 1;
+    if (r >= 1)
+      mbar_wait(&iempty[b], (r - 1) & 1);
+    if (lane == 0)
+      {
+        const uint32_t cell0 = p.cell_begin + (blockIdx.x + bi * gridDim.x) * CELLS;
+        mbar_expect_tx(&ifull[b], IDX_ELEMS * 4);
+        bulk_g2s(ibuf + b * IDX_ELEMS, p.idx + (uint64_t)(cell0 >> 5) * IDX_ELEMS, IDX_ELEMS * 4, &ifull[b]);
+      }
+    __syncwarp();
+  };
+  if (warp == 0 && my_n > 0)
+    issue_idx(0);
+
   const T  w = p.weight, nu = p.nu;
   uint32_t it = 0;
   for (uint32_t bi = 0; bi < my_n; ++bi)
@@ -150,16 +174,11 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
       const uint32_t cellr  = cell0 + col;
       const bool     active = cell_active(p, cellr);
       const uint32_t cell   = cellr < p.cell_end ? cellr : p.cell_end - 1;
-      const uint32_t *__restrict__ ixp = p.idx + (uint64_t)(c * 27) * p.ncp + cell;
-
-      // pull the dof-index rows of this CTA's next batch into L2 while this batch computes
-      if (bi + 1 < my_n && threadIdx.x < 108)
-        {
-          const uint32_t *nx = p.idx + (uint64_t)threadIdx.x * p.ncp + (cell0 + gridDim.x * CELLS);
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
-        }
+      // this lane's 27 dof indices sit in shared memory (staged one batch ahead)
+      const uint32_t *ixs = ibuf + (bi & 1) * IDX_ELEMS + (c * 27) * CELLS + ((col + 8 * c) & 31);
       // cells with constrained dofs are rare: one warp-uniform test instead of one per dof
       const bool slow = __any_sync(0xffffffffu, p.cell_flags[cell] != 0);
+      mbar_wait(&ifull[bi & 1], (bi >> 1) & 1);
 
       // ---- gather (read_dof_values) ------------------------------------------------------
       T t[27];
@@ -167,7 +186,7 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
         uint32_t iv[27];
 #pragma unroll
         for (int j = 0; j < 27; ++j)
-          iv[j] = ixp[(uint64_t)j * p.ncp];
+          iv[j] = ixs[j * CELLS];
         if (!slow)
           {
 #pragma unroll
@@ -355,6 +374,8 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
                   const uint32_t bj = blockIdx.x + (j / 3) * gridDim.x;
                   issue_stage<T, NST>(p, F, tab, full, empty, j, p.cell_begin + bj * CELLS, j % 3, lane);
                 }
+              if (qz == 0 && bi + 1 < my_n)
+                issue_idx(bi + 1);
             }
 #pragma unroll
           for (int a = 0; a < 9; ++a)
@@ -391,7 +412,7 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
           uint32_t iv[27];
 #pragma unroll
           for (int j = 0; j < 27; ++j)
-            iv[j] = ixp[(uint64_t)j * p.ncp];
+            iv[j] = ixs[j * CELLS];
           if (!slow)
             {
 #pragma unroll
@@ -405,13 +426,17 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
                 scatter_resolved(p, p.dst, iv[j], acc[j]);
             }
         }
+      // release the index ring slot
+      __syncwarp();
+      if (lane == 0)
+        mbar_arrive(&iempty[bi & 1]);
     }
 }
 
 template <typename T>
 size_t smem_bytes(int F, int nst)
 {
-  return (nst * stage_elems<T>(F) + (TPB / 32) * 2 * XSLOT) * sizeof(T) + 2 * nst * sizeof(uint64_t);
+  return (nst * stage_elems<T>(F) + (TPB / 32) * 2 * XSLOT) * sizeof(T) + 2 * IDX_ELEMS * 4 + (2 * nst + 4) * sizeof(uint64_t);
 }
 
 template <typename T, bool GENERAL, bool CTD, bool CELLWISE, int NST>
