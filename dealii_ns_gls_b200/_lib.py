@@ -44,6 +44,8 @@ SYMBOLS = {
     "glsb_vmult_begin": (_I, [_P, _P, _P]),
     "glsb_vmult_cells": (_I, [_P, _P, _P, _D, _I, _P]),
     "glsb_vmult_finish": (_I, [_P, _P, _P, _P]),
+    "glsb_vmult_cells_part": (_I, [_P, _P, _P, _D, _I, _I, _I, _P]),
+    "glsb_set_sm_reserve": (_I, [_P, _I]),
     "glsb_evaluate_residual": (_I, [_P, _P, _P, _D, _P]),
     "glsb_evaluate_residual_cells": (_I, [_P, _P, _P, _D, _I, _P]),
     "glsb_set_linearization_point": (_I, [_P, _P, _D, _P]),

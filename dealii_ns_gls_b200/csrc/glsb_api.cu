@@ -173,7 +173,7 @@ struct glsb_op
   ShapeHost shape;
   bool      lin_valid = false, prev_valid = false;
   double    lin_dt = 0;
-  int       variant_forced = 0;
+  int       variant_forced = 0, sm_reserve = 0;
   uint64_t  launches = 0;
   std::string err;
   std::string variant = "generic";
@@ -244,6 +244,7 @@ KParams<T> base_params(const glsb_op *op)
   p.has_o      = op->prev_valid && op->fO >= 0;
   p.theta_ne_1 = (op->theta != 1.0);
   p.max_bits   = op->max_bits.as<unsigned long long>();
+  p.sm_reserve = op->sm_reserve;
   return p;
 }
 
@@ -287,10 +288,20 @@ void cell_range(const glsb_op *op, int which, KParams<T> &p)
   while (0)
 
 template <int dim, typename T>
-int do_cells(glsb_op *op, void *dst, const void *src, double weight, int which, int branch, cudaStream_t s)
+int do_cells(glsb_op *op, void *dst, const void *src, double weight, int which, int branch, cudaStream_t s,
+             int part = 0, int n_parts = 1)
 {
   KParams<T> p = base_params<T>(op);
   cell_range(op, which, p);
+  if (n_parts > 1)
+    {
+      // equal chunks of whole 32-cell batches
+      const uint32_t nb = (p.cell_end - p.cell_begin + 31) / 32;
+      const uint32_t b0 = (uint32_t)((uint64_t)nb * part / n_parts), b1 = (uint32_t)((uint64_t)nb * (part + 1) / n_parts);
+      const uint32_t base = p.cell_begin, end = p.cell_end;
+      p.cell_begin = base + b0 * 32;
+      p.cell_end   = (base + b1 * 32 < end) ? base + b1 * 32 : end;
+    }
   p.src           = static_cast<const T *>(src);
   p.dst           = static_cast<T *>(dst);
   p.weight        = (T)weight;
@@ -811,6 +822,35 @@ int glsb_vmult_cells(glsb_op *op, void *dst, const void *src, double weight, int
 #undef CALL
   if (rc)
     return cuda_fail(op, "glsb_vmult_cells: launch");
+  return 0;
+}
+
+int glsb_vmult_cells_part(glsb_op *op, void *dst, const void *src, double weight, int which, int part, int n_parts,
+                          void *stream)
+{
+  if (!op || !dst || !src)
+    return fail(op, "glsb_vmult_cells_part: null argument");
+  if (n_parts < 1 || part < 0 || part >= n_parts)
+    return fail(op, "glsb_vmult_cells_part: bad part");
+  if (!op->lin_valid)
+    return fail(op, "glsb_vmult: set_linearization_point has not been called");
+  if (op->increment_form && op->ctd && !op->prev_valid)
+    return fail(op, "glsb_vmult: set_previous_solution has not been called");
+  const int branch = op->increment_form ? BR_NEWTON : BR_FIXED_POINT;
+  int       rc     = 0;
+#define CALL(D, T) do_cells<D, T>(op, dst, src, weight, which, branch, (cudaStream_t)stream, part, n_parts)
+  GLSB_DISPATCH(op, CALL);
+#undef CALL
+  if (rc)
+    return cuda_fail(op, "glsb_vmult_cells_part: launch");
+  return 0;
+}
+
+int glsb_set_sm_reserve(glsb_op *op, int n_sms)
+{
+  if (!op || n_sms < 0)
+    return 1;
+  op->sm_reserve = n_sms;
   return 0;
 }
 

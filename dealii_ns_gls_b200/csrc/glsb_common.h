@@ -44,6 +44,7 @@ struct KParams
   // cells [cell_begin, cell_end) in internal order; ncp = padded cell stride of all SoA arrays
   uint32_t cell_begin, cell_end;
   uint32_t hole_begin, hole_end; // padding slots between the interior and the boundary range
+  int      sm_reserve;           // multiprocessors to leave free (persistent kernels)
   uint64_t ncp;
   const uint32_t *idx; // blocked [ncp/32][ndof = C*n_loc][32]: see idx_at()
   uint32_t        ndof, nloc;

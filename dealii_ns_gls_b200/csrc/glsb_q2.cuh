@@ -459,7 +459,8 @@ static int launch(const KParams<T> &p, const Shape<T, 3> &S, int F, cudaStream_t
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     }
   const uint32_t n_batches = (p.cell_end - p.cell_begin + CELLS - 1) / CELLS;
-  const uint32_t grid      = n_batches < (uint32_t)(n_sm * bps) ? n_batches : (uint32_t)(n_sm * bps);
+  const int      use_sm    = (p.sm_reserve > 0 && p.sm_reserve < n_sm) ? n_sm - p.sm_reserve : n_sm;
+  const uint32_t grid      = n_batches < (uint32_t)(use_sm * bps) ? n_batches : (uint32_t)(use_sm * bps);
   kern<<<grid, TPB, smem, s>>>(p, S, F);
   return cudaGetLastError() != cudaSuccess;
 }

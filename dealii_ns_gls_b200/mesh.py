@@ -86,6 +86,7 @@ class Mesh:
     node_compact: bool = True         # comp c of a node at index0 + c
     n_global_dofs: int = 0
     cell_is_boundary: np.ndarray | None = None  # touches ghost dofs
+    canonical_ids: np.ndarray | None = None     # slab meshes: partition-independent id of each local dof
 
     @property
     def C(self):
@@ -123,28 +124,15 @@ def _vertex_geometry(verts: np.ndarray, dim: int):
     return h, meas
 
 
-def structured_mesh(dim, shape, degree, *, deform=None, mapping_degree=1, periodic=None,
-                    order="morton", numbering="node", dirichlet=None,
-                    n_ranks=1, rank=0, extent=None, origin=None, index_dtype=np.uint32):
-    """Structured block of prod(shape) cells.
+def _number_nodes(dim, shape, p, periodic, order):
+    """Cells in traversal order and the first-touch node numbering on a structured block.
 
-    deform:    callable(points[..., dim]) -> points[..., dim]; None => Cartesian cells
-    periodic:  tuple of bools per direction (node identification, O-grid)
-    dirichlet: callable(ref_coords[n_nodes, dim], comp) -> bool mask of zero-constrained nodes
-    numbering: "node" (components of a node consecutive, deal.II-like) or
-               "component" (component-major blocks; exercises the general index path)
-    """
-    shape = tuple(int(s) for s in shape)
-    assert len(shape) == dim
-    periodic = tuple(periodic) if periodic is not None else (False,) * dim
-    extent = np.ones(dim) if extent is None else np.asarray(extent, dtype=np.float64)
-    origin = np.zeros(dim) if origin is None else np.asarray(origin, dtype=np.float64)
-    p = degree
+    Returns cc[ncell, dim] (cell coordinates in traversal order), loc[n_loc, dim] (local node
+    offsets, x fastest), cell_nodes[ncell, n_loc] (lexicographic grid node ids), node_rank[nnode]
+    (position of every grid node in the first-touch numbering), first_cell[nnode], npts."""
     n = p + 1
-    C = dim + 1
     n_loc = n ** dim
     ncell = int(np.prod(shape))
-
     # ---- cell traversal order -------------------------------------------------
     cc = np.stack(np.meshgrid(*[np.arange(s) for s in shape], indexing="ij"), axis=-1).reshape(-1, dim)
     if order == "morton":
@@ -185,6 +173,34 @@ def structured_mesh(dim, shape, degree, *, deform=None, mapping_degree=1, period
     node_rank = np.empty(nnode, dtype=np.int64)
     node_rank[np.argsort(first_key, kind="stable")] = np.arange(nnode)
     first_cell = first_key // n_loc
+
+    return cc, loc, cell_nodes, node_rank, first_cell, npts
+
+
+def structured_mesh(dim, shape, degree, *, deform=None, mapping_degree=1, periodic=None,
+                    order="morton", numbering="node", dirichlet=None,
+                    n_ranks=1, rank=0, extent=None, origin=None, index_dtype=np.uint32):
+    """Structured block of prod(shape) cells.
+
+    deform:    callable(points[..., dim]) -> points[..., dim]; None => Cartesian cells
+    periodic:  tuple of bools per direction (node identification, O-grid)
+    dirichlet: callable(ref_coords[n_nodes, dim], comp) -> bool mask of zero-constrained nodes
+    numbering: "node" (components of a node consecutive, deal.II-like) or
+               "component" (component-major blocks; exercises the general index path)
+    """
+    shape = tuple(int(s) for s in shape)
+    assert len(shape) == dim
+    periodic = tuple(periodic) if periodic is not None else (False,) * dim
+    extent = np.ones(dim) if extent is None else np.asarray(extent, dtype=np.float64)
+    origin = np.zeros(dim) if origin is None else np.asarray(origin, dtype=np.float64)
+    p = degree
+    n = p + 1
+    C = dim + 1
+    n_loc = n ** dim
+    ncell = int(np.prod(shape))
+
+    cc, loc, cell_nodes, node_rank, first_cell, npts = _number_nodes(dim, shape, p, periodic, order)
+    nnode = int(np.prod(npts))
 
     # ---- partition ------------------------------------------------------------
     bounds = [(ncell * r) // n_ranks for r in range(n_ranks + 1)]
@@ -292,6 +308,73 @@ def hypercube(dim, n_per_dir, degree, **kw):
     """performance.cc:29-31: GridGenerator::hyper_cube + uniform cells."""
     shape = (n_per_dir,) * dim if np.isscalar(n_per_dir) else tuple(n_per_dir)
     return structured_mesh(dim, shape, degree, **kw)
+
+
+def hypercube_slab(n_per_dir, degree, *, n_ranks=1, rank=0, dim=3, order="morton", with_points=True,
+                   index_dtype=np.uint32):
+    """Rank `rank`'s part of a hypercube of n x .. x (n * n_ranks) cells cut into n_ranks slabs
+    along the last direction (the weak-scaling workload of bench.py).
+
+    Only this rank's box is generated (O(local cells)).  Ownership follows deal.II: a node shared
+    by two ranks belongs to the lower rank, so rank r > 0 sees its bottom node plane as ghosts
+    owned by r - 1 and rank r < R - 1 exports its top plane.  Both sides order the exchanged
+    plane canonically (node lexicographic in the plane, then component), which is all the
+    Partitioner-style send / receive lists need."""
+    p, C, n = degree, dim + 1, degree + 1
+    n_loc = n ** dim
+    shape = (n_per_dir,) * dim
+    cc, loc, cell_nodes, node_rank, first_cell, npts = _number_nodes(dim, shape, p, (False,) * dim, order)
+    nnode = int(np.prod(npts))
+    ncell = cc.shape[0]
+    plane = int(np.prod(npts[:-1]))               # nodes per plane normal to the slab direction
+    node_ids = np.arange(nnode)
+    k_of = node_ids // plane                      # index along the slab direction
+    is_ghost_node = (k_of == 0) if rank > 0 else np.zeros(nnode, dtype=bool)
+    # owned nodes keep their first-touch order
+    owned_nodes = np.nonzero(~is_ghost_node)[0]
+    owned_sorted = owned_nodes[np.argsort(node_rank[owned_nodes], kind="stable")]
+    n_owned_nodes = len(owned_sorted)
+    local_of_node = np.empty(nnode, dtype=np.int64)
+    local_of_node[owned_sorted] = np.arange(n_owned_nodes)
+    ghost_nodes = np.nonzero(is_ghost_node)[0]    # lexicographic in the plane = canonical order
+    local_of_node[ghost_nodes] = n_owned_nodes + np.arange(len(ghost_nodes))
+    n_owned, n_ghost = n_owned_nodes * C, len(ghost_nodes) * C
+    ln = local_of_node[cell_nodes]
+    cell_dofs = np.concatenate([ln * C + c for c in range(C)], axis=1)
+
+    part = RankPartition(rank=rank, n_ranks=n_ranks, n_owned=n_owned, n_ghost=n_ghost, owned_offset=0,
+                         ghost_global=np.zeros(0, dtype=np.int64), ghost_owner=np.full(n_ghost, rank - 1))
+    if rank > 0:
+        part.recv.append((rank - 1, 0, n_ghost))
+    if rank < n_ranks - 1:
+        top = node_ids[k_of == npts[-1] - 1]
+        exp = (local_of_node[top][:, None] * C + np.arange(C)[None, :]).reshape(-1)
+        part.send.append((rank + 1, exp.astype(np.int64)))
+
+    ext = np.ones(dim)
+    ext[-1] = float(n_ranks)
+    hcell = 1.0 / n_per_dir
+    nodes_last = p * n_per_dir * n_ranks + 1
+    mesh = Mesh(dim=dim, degree=p, n_cells=ncell, n_dofs=n_owned + n_ghost, n_owned=n_owned,
+                cell_dofs=cell_dofs.astype(index_dtype), geometry_type=0, cell_points=None, mapping_degree=1,
+                constraints={}, cell_h_min=np.full(ncell, hcell), cell_measure=np.full(ncell, hcell ** dim),
+                partition=part, node_compact=True, n_global_dofs=plane * nodes_last * C)
+    mesh.cart_inv_jac = np.full((ncell, dim), 1.0 / hcell)
+    mesh.cart_det = np.full(ncell, hcell ** dim)
+    mesh.cell_is_boundary = (cell_dofs >= n_owned).any(axis=1)
+    # canonical global id of every local dof (tests use it to compare against a 1-rank run)
+    gz = k_of + rank * p * n_per_dir
+    gnode = (node_ids % plane) + plane * gz
+    canon = np.empty(n_owned + n_ghost, dtype=np.int64)
+    for c in range(C):
+        canon[local_of_node * C + c] = gnode * C + c
+    mesh.canonical_ids = canon
+    if with_points:
+        origin = np.zeros(dim)
+        origin[-1] = rank * 1.0
+        mloc = np.stack(np.meshgrid(*[np.arange(2)] * dim, indexing="ij"), axis=-1).reshape(-1, dim)[:, ::-1]
+        mesh.cell_points = origin[None, None, :] + (cc[:, None, :] + mloc[None, :, :].astype(np.float64)) * hcell
+    return mesh
 
 
 def cylinder_shell(shape, degree, *, r_inner=0.05, r_outer=0.5, length=0.41,

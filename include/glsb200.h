@@ -123,6 +123,13 @@ int glsb_vmult(glsb_op *op, void *dst, const void *src, double weight, void *str
 int glsb_vmult_begin(glsb_op *op, void *dst, void *stream);
 int glsb_vmult_cells(glsb_op *op, void *dst, const void *src, double weight, int which, void *stream);
 int glsb_vmult_finish(glsb_op *op, void *dst, const void *src, void *stream);
+/* chunk `part` of `n_parts` equal pieces of the cell class `which`: lets the host layer put the ghost
+ * import behind one half of the interior cells and compress(add) behind the other */
+int glsb_vmult_cells_part(glsb_op *op, void *dst, const void *src, double weight, int which, int part,
+                          int n_parts, void *stream);
+/* leave n_sms multiprocessors free when launching the (persistent) cell kernels, so that
+ * communication kernels (NCCL send/recv) can run next to them; 0 = use the whole GPU */
+int glsb_set_sm_reserve(glsb_op *op, int n_sms);
 
 /* evaluate_residual (operator_ns.cc:648-682): src must already carry the
  * inhomogeneous boundary values (constraints_inhomogeneous.distribute, :655-656)

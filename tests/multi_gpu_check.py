@@ -1,0 +1,80 @@
+"""Multi-GPU parity check, launched by hand on the GPU box (not collected by pytest):
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+      --master-port 29511 tests/multi_gpu_check.py
+
+Every rank builds its slab of a small hypercube, applies the CUDA operator with the NCCL ghost
+exchange (interior cells overlapped with the import, compress(add) afterwards) and the result is
+compared with the CPU oracle evaluated on the union of the slabs."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from dealii_ns_gls_b200 import mesh as gm  # noqa: E402
+from dealii_ns_gls_b200.distributed import GhostExchange  # noqa: E402
+from dealii_ns_gls_b200.operator import NavierStokesOperator  # noqa: E402
+from tests.util import TI, make_oracle  # noqa: E402
+
+
+def field(ids, seed):
+    x = (ids.astype(np.float64) * 0.6180339887498949 + seed * 0.137) % 1.0
+    return 2.0 * x - 1.0
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dev = torch.device("cuda", lr)
+    dist.init_process_group("nccl", device_id=dev)
+    n, degree, w = 7, 2, 10.0
+    m = gm.hypercube_slab(n, degree, n_ranks=world, rank=rank)
+    ex = GhostExchange(m.partition, dev)
+    ti = TI(2, [w, -w, 0.0], 0.1)
+    op = NavierStokesOperator(m, None, 0.1, 4.0, 2.0, ti, False, True, True, number="double", device=dev, exchange=ex)
+    lin = torch.tensor(field(m.canonical_ids, 1), device=dev)
+    src = torch.tensor(field(m.canonical_ids, 2), device=dev)
+    lin[m.n_owned:] = 0
+    src[m.n_owned:] = 0
+    op.set_linearization_point(lin)
+    dst = op.initialize_dof_vector()
+    op.vmult(dst, src)
+    diag = op.initialize_dof_vector()
+    op.compute_inverse_diagonal(diag)
+    umax = op.get_max_u(src)
+    torch.cuda.synchronize()
+    # reference on the union of the slabs (every rank computes it; sizes are tiny)
+    meshes = [gm.hypercube_slab(n, degree, n_ranks=world, rank=r) for r in range(world)]
+    ng = meshes[0].n_global_dofs
+    acc, dacc, um = np.zeros(ng), np.zeros(ng), 0.0
+    for mm in meshes:
+        o = make_oracle(mm, ti)
+        o.set_linearization_point(field(mm.canonical_ids, 1), 0.1)
+        np.add.at(acc, mm.canonical_ids, o._scatter(o._apply_cells(o._gather(field(mm.canonical_ids, 2)), w, False)))
+        A = o.cell_matrices(w)
+        dl = np.zeros(mm.n_dofs)
+        np.add.at(dl, mm.cell_dofs.reshape(-1).astype(np.int64), np.einsum("kii->ki", A).reshape(-1))
+        np.add.at(dacc, mm.canonical_ids, dl)
+        um = max(um, o.get_max_u(field(mm.canonical_ids, 2)))
+    ids = m.canonical_ids[: m.n_owned]
+    e1 = np.linalg.norm(dst[: m.n_owned].cpu().numpy() - acc[ids]) / np.linalg.norm(acc)
+    dref = np.where(np.abs(dacc) > 1e-10, 1.0 / dacc, 1.0)
+    e2 = np.linalg.norm(diag[: m.n_owned].cpu().numpy() - dref[ids]) / np.linalg.norm(dref)
+    e3 = abs(umax - um)
+    ok = e1 < 1e-12 and e2 < 1e-11 and e3 < 1e-12 and op.vmult_variant() == "q2_regtile_tma"
+    print(f"rank {rank}/{world}: vmult rel_l2 {e1:.2e}  inv_diag rel_l2 {e2:.2e}  max_u err {e3:.1e}  "
+          f"interior/boundary cells {m.n_cells - int(m.cell_is_boundary.sum())}/{int(m.cell_is_boundary.sum())} "
+          f"variant {op.vmult_variant()}  {'OK' if ok else 'FAIL'}", flush=True)
+    t = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(t)
+    dist.destroy_process_group()
+    sys.exit(int(t.item()) != 0)
+
+
+if __name__ == "__main__":
+    main()

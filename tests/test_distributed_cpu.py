@@ -1,0 +1,96 @@
+"""world_size-2 gloo tests of the N > 1 host path (partition lists + ghost exchange protocol),
+run on CPU with the oracle as each rank's local cell loop."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _slab_reference(n, degree, R, lin_fn, src_fn, weight):
+    from dealii_ns_gls_b200 import mesh as gm
+    from tests.util import TI, make_oracle
+    full = gm.hypercube_slab(n, degree, n_ranks=1, rank=0)
+    # one rank holding the whole R-slab domain: stack the slabs by canonical ids
+    meshes = [gm.hypercube_slab(n, degree, n_ranks=R, rank=r) for r in range(R)]
+    ng = meshes[0].n_global_dofs
+    ti = TI(2, [weight, -weight, 0.0], 0.1)
+    acc = np.zeros(ng)
+    for m in meshes:
+        o = make_oracle(m, ti)
+        o.set_linearization_point(lin_fn(m.canonical_ids), 0.1)
+        loc = o._scatter(o._apply_cells(o._gather(src_fn(m.canonical_ids)), weight, False))
+        np.add.at(acc, m.canonical_ids, loc)
+    del full
+    return acc
+
+
+def _field(ids, seed):
+    # deterministic pseudo-random value per canonical dof id, identical on every rank
+    x = (ids.astype(np.float64) * 0.6180339887498949 + seed * 0.137) % 1.0
+    return 2.0 * x - 1.0
+
+
+def _worker(rank, world, port, n, degree, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dealii_ns_gls_b200 import mesh as gm
+    from dealii_ns_gls_b200.distributed import GhostExchange
+    from tests.util import TI, make_oracle
+    m = gm.hypercube_slab(n, degree, n_ranks=world, rank=rank)
+    ex = GhostExchange(m.partition, "cpu")
+    ti = TI(2, [10.0, -10.0, 0.0], 0.1)
+    o = make_oracle(m, ti)
+    n_owned = m.n_owned
+    # vectors arrive without ghost values
+    lin = torch.tensor(_field(m.canonical_ids, 1))
+    src = torch.tensor(_field(m.canonical_ids, 2))
+    lin[n_owned:] = 0
+    src[n_owned:] = 0
+    ex.update_ghost_values(None, lin)
+    o.set_linearization_point(lin.numpy(), 0.1)
+    ex.update_ghost_values(None, src)
+    dst = torch.tensor(o._scatter(o._apply_cells(o._gather(src.numpy()), 10.0, False)))
+    ex.compress_add(None, dst)
+    mx = ex.allreduce_max(float(rank + 1))
+    torch.save({"ids": m.canonical_ids[:n_owned], "dst": dst[:n_owned].numpy(), "mx": mx,
+                "ghost_zero": bool((dst[n_owned:] == 0).all())}, out + f".{rank}")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_two_rank_ghost_exchange_matches_single_domain(tmp_path, degree):
+    n, world = 3, 2
+    port = 29500 + (os.getpid() % 2000) + degree
+    out = str(tmp_path / "res")
+    mp.spawn(_worker, args=(world, port, n, degree, out), nprocs=world, join=True)
+    ref = _slab_reference(n, degree, world, lambda ids: _field(ids, 1), lambda ids: _field(ids, 2), 10.0)
+    seen = np.zeros(len(ref), dtype=bool)
+    for r in range(world):
+        d = torch.load(out + f".{r}", weights_only=False)
+        assert d["ghost_zero"] and d["mx"] == float(world)
+        assert np.linalg.norm(d["dst"] - ref[d["ids"]]) <= 1e-13 * np.linalg.norm(ref)
+        assert not seen[d["ids"]].any()          # every dof owned exactly once
+        seen[d["ids"]] = True
+    assert seen.all()
+
+
+def test_slab_partition_lists_are_consistent():
+    from dealii_ns_gls_b200 import mesh as gm
+    R, n, p = 3, 2, 2
+    ms = [gm.hypercube_slab(n, p, n_ranks=R, rank=r) for r in range(R)]
+    assert sum(m.n_owned for m in ms) == ms[0].n_global_dofs
+    for r in range(R - 1):
+        (to, exp), = ms[r].partition.send
+        (frm, off, cnt), = ms[r + 1].partition.recv
+        assert to == r + 1 and frm == r and cnt == len(exp) and off == 0
+        # the sender's export order equals the receiver's ghost order (same canonical ids)
+        assert np.array_equal(ms[r].canonical_ids[exp], ms[r + 1].canonical_ids[ms[r + 1].n_owned:])
+    assert not ms[0].partition.recv and not ms[-1].partition.send
