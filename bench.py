@@ -164,7 +164,7 @@ def run_reference(args):
         "note": "CPU restatement of the reference algorithm (oracle/gls_oracle_c.c), not deal.II: the "
                 "reference cannot be built without deal.II/p4est/Trilinos/MPI",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, n_gpus):
@@ -320,12 +320,31 @@ def run_gpu(args):
         r = cpu_vmult_gdofs(args.cpu_cells, args.degree, 10, 2)
         line["cpu_baseline"] = {"value": r["value"], "unit": "GDoF/s", "cores": r["cores"], "kind": "port",
                                 "sample": r["sample"]}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """Libraries (NCCL prints its version banner) must not write into the one-JSON-line stdout:
+    point fd 1 at stderr for the whole run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

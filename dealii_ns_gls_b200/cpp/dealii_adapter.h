@@ -1,0 +1,312 @@
+// deal.II-side binding of libglsb200.so: NavierStokesOperatorB200<dim, Number>, a drop-in subclass of
+// the reference's OperatorBase<Number> (include/operator_base.h:13-73) with the constructor
+// signature of NavierStokesOperator<dim, Number> (include/operator_ns.h:24-41).  solver_l, solver_nl,
+// multigrid, time_integration and main.cc stay unchanged; main.cc:333-348 / :513-529 / :683-702 and
+// performance.cc:48-62 only swap the class name.
+//
+// NOT COMPILED IN THIS REPOSITORY: deal.II (>= 9.6, with p4est and Trilinos), MPI and the reference's
+// own headers are not available to this build.  The file is kept header-only and
+// is written against the public deal.II API; every accessor used is listed in INTEGRATION.md so a
+// maintainer with a deal.II tree can check it in one pass.  What it does is mechanical: flatten
+// MatrixFree / DoFHandler / AffineConstraints / Partitioner into the arrays of glsb_desc
+//  once, then forward each virtual to the matching C-ABI call.
+#pragma once
+
+#if __has_include(<deal.II/matrix_free/matrix_free.h>)
+
+#include <deal.II/base/mpi.h>
+#include <deal.II/base/partitioner.h>
+#include <deal.II/lac/affine_constraints.h>
+#include <deal.II/lac/la_parallel_vector.h>
+#include <deal.II/matrix_free/fe_evaluation.h>
+#include <deal.II/matrix_free/matrix_free.h>
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include "../../include/glsb200.h"
+#include "operator_base.h" // the reference's header
+#include "operator_ns.h"   // retained CPU operator for get_system_matrix() on the coarse level
+
+namespace glsb
+{
+using namespace dealii;
+
+/**
+ * Number = double for the Krylov operator, float for the multigrid level operators
+ * (include/config.h:6-7).  VectorType<Number> is the reference's alias (config.h:9-10).  With a
+ * Kokkos-CUDA deal.II and `MemorySpace::Default` vectors the device pointers are used directly;
+ * with host vectors (the reference's default alias) a pinned mirror is copied per call -- the
+ * "plumbing" mode that pays 16 B/DoF over PCIe and is only meant for bring-up.
+ */
+template <int dim, typename Number>
+class NavierStokesOperatorB200 : public OperatorBase<Number>
+{
+public:
+  using FECellIntegrator = FEEvaluation<dim, -1, 0, dim + 1, Number>;
+
+  NavierStokesOperatorB200(const Mapping<dim>              &mapping,
+                           const DoFHandler<dim>           &dof_handler,
+                           const AffineConstraints<Number> &constraints_homogeneous,
+                           const AffineConstraints<Number> &constraints,
+                           const AffineConstraints<Number> &constraints_inhomogeneous,
+                           const Quadrature<dim>           &quadrature,
+                           const Number                     nu,
+                           const Number                     c_1,
+                           const Number                     c_2,
+                           const std::set<unsigned int>    &all_outflow_bcs_cut,
+                           const std::map<unsigned int, std::shared_ptr<Function<dim, double>>> &all_outflow_bcs_nitsche,
+                           const TimeIntegratorData &time_integrator_data,
+                           const bool                consider_time_derivative,
+                           const bool                increment_form,
+                           const bool                cell_wise_stabilization,
+                           const unsigned int        mg_level = numbers::invalid_unsigned_int)
+    : constraints_inhomogeneous(constraints_inhomogeneous)
+    , time_integrator_data(time_integrator_data)
+    , cpu_operator(mapping, dof_handler, constraints_homogeneous, constraints, constraints_inhomogeneous, quadrature,
+                   nu, c_1, c_2, all_outflow_bcs_cut, all_outflow_bcs_nitsche, time_integrator_data,
+                   consider_time_derivative, increment_form, cell_wise_stabilization, mg_level)
+  {
+    // boundary-face outflow terms and GMG-LS edge operators are "next" rows of the scope table
+    AssertThrow(all_outflow_bcs_cut.empty() && all_outflow_bcs_nitsche.empty(), ExcNotImplemented());
+
+    typename MatrixFree<dim, Number>::AdditionalData ad;
+    ad.mapping_update_flags = update_values | update_gradients; // operator_ns.cc:112
+    ad.mg_level             = mg_level;
+    matrix_free.reinit(mapping, dof_handler, constraints_homogeneous, quadrature, ad);
+
+    const auto &part   = *matrix_free.get_vector_partitioner();
+    const auto &shape  = matrix_free.get_shape_info();
+    const auto &lex    = shape.lexicographic_numbering; // component-blocked lexicographic -> cell dof
+    const unsigned int degree = dof_handler.get_fe().tensor_degree();
+    const unsigned int n_q    = quadrature.size();
+    const unsigned int ndof   = dof_handler.get_fe().n_dofs_per_cell();
+
+    // ---- constraint rows (homogeneous part only, operator_ns.cc:107-108) -------------------
+    std::vector<uint32_t> row_dof, row_ptr(1, 0), entry_col;
+    std::vector<double>   entry_val;
+    std::map<types::global_dof_index, uint32_t> row_of;
+    auto row_for = [&](const types::global_dof_index g) -> uint32_t {
+      auto it = row_of.find(g);
+      if (it != row_of.end())
+        return it->second;
+      const uint32_t r = row_dof.size();
+      row_of[g]        = r;
+      row_dof.push_back(part.global_to_local(g));
+      if (const auto *entries = constraints_homogeneous.get_constraint_entries(g))
+        for (const auto &e : *entries)
+          {
+            entry_col.push_back(part.global_to_local(e.first));
+            entry_val.push_back(e.second);
+          }
+      row_ptr.push_back(entry_col.size());
+      return r;
+    };
+
+    // ---- cells: dof indices, geometry, h, measure ---------------------------------------------
+    std::vector<uint32_t> dof_indices;
+    std::vector<double>   inv_jac, jxw, h_min, measure;
+    bool                  all_cartesian = true;
+    for (unsigned int b = 0; b < matrix_free.n_cell_batches(); ++b)
+      if (matrix_free.get_mapping_info().get_cell_type(b) != internal::MatrixFreeFunctions::cartesian)
+        all_cartesian = false;
+    std::vector<types::global_dof_index> cell_dofs(ndof);
+    FECellIntegrator                     phi(matrix_free);
+    std::uint64_t                        n_cells = 0;
+    for (unsigned int b = 0; b < matrix_free.n_cell_batches(); ++b)
+      {
+        phi.reinit(b);
+        for (unsigned int v = 0; v < matrix_free.n_active_entries_per_cell_batch(b); ++v, ++n_cells)
+          {
+            const auto cell = matrix_free.get_cell_iterator(b, v);
+            if (mg_level == numbers::invalid_unsigned_int)
+              cell->get_dof_indices(cell_dofs);
+            else
+              cell->get_mg_dof_indices(cell_dofs);
+            for (unsigned int i = 0; i < ndof; ++i)
+              {
+                const auto g = cell_dofs[lex[i]];
+                dof_indices.push_back(constraints_homogeneous.is_constrained(g) ?
+                                        (GLSB_CONSTRAINED_BIT | row_for(g)) :
+                                        part.global_to_local(g));
+              }
+            h_min.push_back(cell->minimum_vertex_distance()); // operator_ns.cc:374
+            measure.push_back(cell->measure());               // operator_ns.cc:399
+            if (all_cartesian)
+              {
+                const auto J = phi.inverse_jacobian(0); // J^{-T}, diagonal for Cartesian cells
+                for (unsigned int d = 0; d < dim; ++d)
+                  inv_jac.push_back(J[d][d][v]);
+                // JxW(q) = det J * w_q  =>  det J = JxW(0) / w_0
+                jxw.push_back(phi.JxW(0)[v] / quadrature.weight(0));
+              }
+            else
+              for (unsigned int q = 0; q < n_q; ++q)
+                {
+                  const auto J = phi.inverse_jacobian(q); // J[j][e] = (J^{-1})_{e j}
+                  for (unsigned int e = 0; e < dim; ++e)
+                    for (unsigned int j = 0; j < dim; ++j)
+                      inv_jac.push_back(J[j][e][v]);
+                  jxw.push_back(phi.JxW(q)[v]);
+                }
+          }
+      }
+
+    std::vector<uint32_t> constrained_indices(matrix_free.get_constrained_dofs().begin(),
+                                              matrix_free.get_constrained_dofs().end()); // operator_ns.cc:123-124
+    // owned entries this rank exports, neighbour by neighbour (Partitioner::import_indices)
+    std::vector<uint32_t> export_indices;
+    for (const auto &range : part.import_indices())
+      for (unsigned int i = range.first; i < range.second; ++i)
+        export_indices.push_back(i);
+
+    glsb_desc d{};
+    d.abi_version = GLSB_ABI_VERSION;
+    cudaGetDevice(&d.device);
+    d.dim = dim, d.degree = degree, d.number_type = std::is_same<Number, double>::value ? GLSB_F64 : GLSB_F32;
+    d.increment_form = increment_form, d.consider_time_derivative = consider_time_derivative;
+    d.cell_wise_stabilization = cell_wise_stabilization, d.time_order = time_integrator_data.get_order();
+    d.nu = nu, d.c1 = c_1, d.c2 = c_2, d.theta = time_integrator_data.get_theta();
+    d.n_cells = n_cells, d.n_owned = part.locally_owned_size(), d.n_ghost = part.n_ghost_indices();
+    d.dof_indices = dof_indices.data();
+    d.n_constraint_rows = row_dof.size(), d.row_dof = row_dof.data(), d.row_ptr = row_ptr.data();
+    d.entry_col = entry_col.data(), d.entry_val = entry_val.data();
+    d.n_constrained_indices = constrained_indices.size(), d.constrained_indices = constrained_indices.data();
+    d.geometry_type = all_cartesian ? GLSB_GEOM_CARTESIAN : GLSB_GEOM_GENERAL;
+    d.inv_jac = inv_jac.data(), d.jxw = jxw.data(), d.cell_h_min = h_min.data(), d.cell_measure = measure.data();
+    d.n_export = export_indices.size(), d.export_indices = export_indices.data();
+    AssertThrow(glsb_create(&d, &op) == 0, ExcMessage(glsb_last_error(nullptr)));
+    n_local = d.n_owned + d.n_ghost;
+  }
+
+  ~NavierStokesOperatorB200() override { glsb_destroy(op); }
+
+  // ---- OperatorBase<Number> -------------------------------------------------------------------
+  types::global_dof_index m() const override { return cpu_operator.m(); }
+  const AffineConstraints<Number> &get_constraints() const override { return cpu_operator.get_constraints(); }
+  std::vector<std::vector<bool>>   extract_constant_modes() const override { return cpu_operator.extract_constant_modes(); }
+  // assembled matrix for the coarse-level AMG/direct solvers stays on the CPU operator (Trilinos)
+  const SparseMatrixType &get_system_matrix() const override { return cpu_operator.get_system_matrix(); }
+  void initialize_dof_vector(VectorType<Number> &vec) const override { matrix_free.initialize_dof_vector(vec); }
+  void invalidate_system() override
+  {
+    cpu_operator.invalidate_system();
+    check(glsb_invalidate_system(op));
+  }
+
+  void vmult(VectorType<Number> &dst, const VectorType<Number> &src) const override
+  {
+    MyScope scope(timer, "ns::vmult"); // same section names as the reference (operator_ns.cc:689)
+    const double w = time_integrator_data.get_primary_weight();
+    check(glsb_vmult_begin(op, dev(dst), stream));
+    update_ghost_values_start(src); // NCCL send/recv of the export block into the ghost block
+    check(glsb_vmult_cells_part(op, dev(dst), dev(src), w, GLSB_CELLS_INTERIOR, 0, 2, stream));
+    update_ghost_values_finish();
+    check(glsb_vmult_cells(op, dev(dst), dev(src), w, GLSB_CELLS_BOUNDARY, stream));
+    compress_start(dst);
+    check(glsb_vmult_cells_part(op, dev(dst), dev(src), w, GLSB_CELLS_INTERIOR, 1, 2, stream));
+    compress_finish(dst); // glsb_unpack_add
+    check(glsb_vmult_finish(op, dev(dst), dev(src), stream));
+    finish(dst);
+  }
+
+  void set_linearization_point(const VectorType<Number> &vec) override
+  {
+    MyScope scope(timer, "ns::set_linearization_point");
+    AssertThrow(vec.has_ghost_elements() == false, ExcInternalError()); // operator_ns.cc:589-591
+    update_ghost_values_start(vec);
+    update_ghost_values_finish();
+    check(glsb_set_linearization_point(op, dev(vec), time_integrator_data.get_current_dt(), stream));
+  }
+
+  void set_previous_solution(const SolutionHistory<Number> &history) override
+  {
+    MyScope scope(timer, "ns::set_previous_solution");
+    const unsigned int order = time_integrator_data.get_order();
+    if (order == 0)
+      return;
+    std::vector<const void *> ptr;
+    for (unsigned int i = 0; i <= order; ++i)
+      {
+        if (i > 0)
+          {
+            update_ghost_values_start(history.get_vectors()[i]);
+            update_ghost_values_finish();
+          }
+        ptr.push_back(dev(history.get_vectors()[i]));
+      }
+    check(glsb_set_previous_solution(op, ptr.data(), time_integrator_data.get_weights().data(), order, stream));
+  }
+
+  void evaluate_residual(VectorType<Number> &dst, const VectorType<Number> &src) const override
+  {
+    MyScope scope(timer, "ns::evaluate_residual");
+    VectorType<Number> tmp = src;
+    constraints_inhomogeneous.distribute(tmp); // operator_ns.cc:655-656
+    update_ghost_values_start(tmp);
+    update_ghost_values_finish();
+    check(glsb_evaluate_residual(op, dev(dst), dev(tmp), time_integrator_data.get_primary_weight(), stream));
+    compress_start(dst);
+    compress_finish(dst);
+    finish(dst);
+  }
+
+  void evaluate_rhs(VectorType<Number> &dst) const override
+  {
+    VectorType<Number> src;
+    src.reinit(dst);
+    evaluate_residual(dst, src);
+  }
+
+  void compute_inverse_diagonal(VectorType<Number> &diagonal) const override
+  {
+    MyScope scope(timer, "ns::compute_inverse_diagonal");
+    matrix_free.initialize_dof_vector(diagonal);
+    check(glsb_diagonal_cells(op, dev(diagonal), time_integrator_data.get_primary_weight(), stream));
+    compress_start(diagonal);
+    compress_finish(diagonal);
+    check(glsb_diagonal_finish(op, dev(diagonal), stream));
+    finish(diagonal);
+  }
+
+  double get_max_u(const VectorType<Number> &vec) const override
+  {
+    update_ghost_values_start(vec);
+    update_ghost_values_finish();
+    double v = 0;
+    check(glsb_get_max_u(op, dev(vec), &v, stream));
+    return Utilities::MPI::max(v, MPI_COMM_WORLD); // operator_ns.cc:567
+  }
+
+private:
+  void check(const int rc) const { AssertThrow(rc == 0, ExcMessage(glsb_last_error(op))); }
+
+  // Device pointer of a vector.  MemorySpace::Default vectors: get_values() is already device memory.
+  // Host vectors: copy into a cached device mirror (and back in finish()).
+  void       *dev(VectorType<Number> &v) const;
+  const void *dev(const VectorType<Number> &v) const;
+  void        finish(VectorType<Number> &v) const;
+
+  // ghost exchange over NCCL: ncclGroupStart; ncclSend(export buffer slice -> import_targets);
+  // ncclRecv(ghost block slice <- ghost_targets); ncclGroupEnd on comm_stream, packed / unpacked by
+  // glsb_pack_export / glsb_unpack_add.  Rank = GPU mapping and the communicator come from the
+  // driver (one MPI rank per GPU, ncclCommInitRank with an id broadcast over MPI).
+  void update_ghost_values_start(const VectorType<Number> &v) const;
+  void update_ghost_values_finish() const;
+  void compress_start(VectorType<Number> &v) const;
+  void compress_finish(VectorType<Number> &v) const;
+
+  const AffineConstraints<Number>  &constraints_inhomogeneous;
+  const TimeIntegratorData         &time_integrator_data;
+  NavierStokesOperator<dim, Number> cpu_operator; // system matrix / constant modes / constraints only
+  MatrixFree<dim, Number>           matrix_free;
+  glsb_op                          *op      = nullptr;
+  std::uint64_t                     n_local = 0;
+  cudaStream_t                      stream = nullptr, comm_stream = nullptr;
+  ncclComm_t                        nccl   = nullptr;
+  mutable MyTimerOutput             timer;
+};
+
+} // namespace glsb
+
+#endif // deal.II available

@@ -11,16 +11,25 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_PATH = os.path.join(_HERE, "libgls_oracle_c.so")
 _lib = None
+
+
+def _isa_level():
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        return "v3"
+    need = ("avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl")
+    return "v4" if all(f in flags for f in need) else "v3"
 
 
 def load():
     global _lib
     if _lib is None:
-        if not os.path.exists(_PATH):
+        path = os.path.join(_HERE, f"libgls_oracle_c_{_isa_level()}.so")
+        if not os.path.exists(path):
             subprocess.check_call(["make", "-C", _HERE])
-        lib = C.CDLL(_PATH)
+        lib = C.CDLL(path)
         P, D, I, L = C.c_void_p, C.c_double, C.c_int, C.c_int64
         lib.glso_create.restype = P
         lib.glso_create.argtypes = [I, I, L, L, P, P, P, P, I, P, P, D, D, I, I, I]
@@ -41,7 +50,12 @@ def _p(a):
 
 
 def max_threads():
-    return load().glso_max_threads()
+    """All host threads this process may use (torchrun sets OMP_NUM_THREADS=1; the affinity mask is
+    what the box really offers)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return load().glso_max_threads()
 
 
 class COracle:
