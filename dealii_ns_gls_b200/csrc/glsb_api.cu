@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -52,14 +53,19 @@ struct DevBuf
 };
 
 __global__ void k_transpose_idx(const uint32_t *__restrict__ raw, const uint32_t *__restrict__ perm,
-                                uint32_t *__restrict__ out, uint32_t n_cells, uint32_t ndof, uint32_t nloc, uint64_t ncp)
+                                const uint8_t *__restrict__ flags, uint32_t *__restrict__ out, uint32_t n_cells,
+                                uint32_t ndof, uint32_t nloc, uint64_t ncp)
 {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (uint64_t)ndof * ncp)
+  if (t >= (uint64_t)(ndof + 1) * ncp)
     return;
   const uint32_t i = t % ncp, d = t / ncp;
-  // blocked [ncp/32][ndof][32]; perm is defined for every slot (padding repeats a cell)
-  out[((uint64_t)(i >> 5) * ndof + d) * 32 + (((i & 31) + 8 * (d / nloc)) & 31)] = raw[(uint64_t)perm[i] * ndof + d];
+  // blocked [ncp/32][ndof + 1][32]; perm is defined for every slot (padding repeats a cell)
+  if (d == ndof)
+    out[((uint64_t)(i >> 5) * (ndof + 1) + d) * 32 + (i & 31)] = flags[i];
+  else
+    out[((uint64_t)(i >> 5) * (ndof + 1) + d) * 32 + (((i & 31) + 8 * (d / nloc)) & 31)] =
+      raw[(uint64_t)perm[i] * ndof + d];
 }
 
 // general geometry raw[(cell*nq + q)*inner + f] (double, caller's cell order) -> blocked q-point
@@ -566,12 +572,13 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
   {
     DevBuf raw;
     ok = ok && upload(raw, d->dof_indices, (size_t)nc * ndof * 4);
-    ok = ok && op->idx.alloc((size_t)ndof * op->ncp * 4);
+    ok = ok && op->idx.alloc((size_t)(ndof + 1) * op->ncp * 4);
     if (ok)
       {
-        const uint64_t tot = (uint64_t)ndof * op->ncp;
+        const uint64_t tot = (uint64_t)(ndof + 1) * op->ncp;
         k_transpose_idx<<<(unsigned)((tot + 255) / 256), 256>>>(raw.as<uint32_t>(), op->perm.as<uint32_t>(),
-                                                                 op->idx.as<uint32_t>(), nc, ndof, (uint32_t)op->n_loc, op->ncp);
+                                                                 op->cell_flags.as<uint8_t>(), op->idx.as<uint32_t>(), nc,
+                                                                 ndof, (uint32_t)op->n_loc, op->ncp);
         ok = cudaDeviceSynchronize() == cudaSuccess;
       }
   }
@@ -692,8 +699,10 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
     op->FT = f;
     if (op->dim == 3 && op->n == 3)
       {
-        op->NL = 3;
-        op->QG = 9;
+        // one block per ring stage of the Q2 kernel: a (qz, qy) row of 3 points, or a whole layer
+        const char *rows = getenv("GLSB_Q2_ROWS");
+        op->QG           = (rows && atoi(rows) == 1) ? 3 : 9;
+        op->NL           = 27 / op->QG;
       }
     else
       {

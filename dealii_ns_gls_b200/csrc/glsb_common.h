@@ -16,6 +16,11 @@ struct Shape
   T D[n * n];  // D[q*n + q'] = collocation derivative on the Gauss points
   T G[n * n];  // G[q*n + i]  = phi_i'(x_q) (= D S)
   T w[n];      // 1-D Gauss weights on [0,1]
+  // the same with the quadrature weights folded in (Cartesian cells: JxW = det J * w_qx w_qy w_qz is
+  // separable, so the integration sweeps can carry the weights and the q-point loop needs none):
+  T Sw[n * n]; // w_q S[q][i]
+  T Gw[n * n]; // w_q G[q][i]
+  T Dt[n * n]; // D[q'][q] w_q' / w_q
 };
 
 struct ShapeHost
@@ -46,7 +51,8 @@ struct KParams
   uint32_t hole_begin, hole_end; // padding slots between the interior and the boundary range
   int      sm_reserve;           // multiprocessors to leave free (persistent kernels)
   uint64_t ncp;
-  const uint32_t *idx; // blocked [ncp/32][ndof = C*n_loc][32]: see idx_at()
+  const uint32_t *idx; // blocked [ncp/32][ndof + 1][32]: ndof = C*n_loc index rows (see idx_at()), then one
+                       // row with a flag word per cell (non-zero: the cell has constrained dofs)
   uint32_t        ndof, nloc;
   const uint8_t  *cell_flags; // [ncp] bit 0: the cell has constrained dofs
   // constraint rows
@@ -86,13 +92,13 @@ struct KParams
 };
 
 // dof index of local dof `dof` of cell `cell`: rows of 32 consecutive cells are contiguous (coalesced
-// for every kernel) and the ndof rows of a 32-cell batch are one contiguous block (one bulk copy)
+// for every kernel) and the ndof + 1 rows of a 32-cell batch are one contiguous block (one bulk copy)
 template <typename T>
 __host__ __device__ inline uint64_t idx_at(const KParams<T> &p, uint32_t dof, uint32_t cell)
 {
   // inside its row, component c's entry of a cell is rotated by 8c cells: the 4 component lanes of a
   // cell in the Q2 kernel then hit 4 different shared-memory banks when the block is staged there
-  return ((uint64_t)(cell >> 5) * p.ndof + dof) * 32 + (((cell & 31) + 8 * (dof / p.nloc)) & 31);
+  return ((uint64_t)(cell >> 5) * (p.ndof + 1) + dof) * 32 + (((cell & 31) + 8 * (dof / p.nloc)) & 31);
 }
 
 template <typename T>

@@ -25,6 +25,13 @@ static Shape<T, n> to_shape(const ShapeHost &h)
     }
   for (int i = 0; i < n; ++i)
     s.w[i] = (T)h.w[i];
+  for (int q = 0; q < n; ++q)
+    for (int j = 0; j < n; ++j)
+      {
+        s.Sw[q * n + j] = (T)(h.w[q] * h.S[q * n + j]);
+        s.Gw[q * n + j] = (T)(h.w[q] * h.G[q * n + j]);
+        s.Dt[q * n + j] = (T)(h.D[q * n + j] * h.w[q] / h.w[j]);
+      }
   return s;
 }
 
@@ -202,10 +209,9 @@ int Kernels<GLSB_DIM, GLSB_REAL>::vmult_q2(const KParams<GLSB_REAL> &p, const Sh
 {
 #if GLSB_DIM == 3 && defined(GLSB_WITH_Q2)
   const auto S     = to_shape<GLSB_REAL, 3>(sh);
-  const bool three = 2 * q2::smem_bytes<GLSB_REAL>(F, 3) <= 224 * 1024; // two CTAs per SM with a 3-deep ring?
   if (p.geom == GLSB_GEOM_GENERAL)
-    return three ? q2::launch_flags<GLSB_REAL, true, 3>(p, S, F, s) : q2::launch_flags<GLSB_REAL, true, 2>(p, S, F, s);
-  return three ? q2::launch_flags<GLSB_REAL, false, 3>(p, S, F, s) : q2::launch_flags<GLSB_REAL, false, 2>(p, S, F, s);
+    return q2::launch_flags<GLSB_REAL, true>(p, S, F, s);
+  return q2::launch_flags<GLSB_REAL, false>(p, S, F, s);
 #else
   (void)p, (void)sh, (void)F, (void)s;
   return -1;

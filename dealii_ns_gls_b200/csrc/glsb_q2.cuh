@@ -13,13 +13,18 @@
 //     (lane c needs d_c u_j from lane j) are plain address arithmetic there, where a shuffle
 //     version needs per-lane register selects that ptxas turns into divergent branches.
 //   * the q-point tables (U, grad U, grad P [, du/dt_old, delta_q, J^-T, JxW]) are stored
-//     [batch][layer][field][9][32 cells]; the block a CTA needs for one quadrature layer is
-//     contiguous and is streamed HBM -> shared memory with ONE cp.async.bulk (TMA engine,
-//     mbarrier complete_tx) per layer into an NST-deep ring, issued 1-2 layers ahead.
-//   * gather straight from global memory (the 4 components of a node are adjacent lanes, so a
-//     node-major numbering gives full 32 B sectors), scatter with RED.ADD.F64 atomics.
+//     [batch][row of 3 q-points][field][3][32 cells]; the block a CTA needs for one row (qz, qy) of
+//     quadrature points is contiguous and is streamed HBM -> shared memory with ONE cp.async.bulk
+//     (TMA engine, mbarrier complete_tx) per row into an nst-deep ring kept nst-1 rows ahead of
+//     the arithmetic.
+//   * the dof indices (+ one flag word per cell) of a batch are one contiguous block, staged one
+//     batch ahead by a bulk copy; with them every thread gathers the 27 source values of its NEXT
+//     batch with cp.async (LDGSTS) into its own shared-memory column while it computes the current
+//     one (the 4 components of a node are adjacent lanes, so a node-major numbering gives full
+//     32 B sectors); scatter with RED.ADD.F64 atomics.
 #pragma once
 #include "glsb_kernels.cuh"
+#include <cstdlib>
 
 namespace glsb
 {
@@ -70,68 +75,84 @@ __device__ __forceinline__ T sel3(int c, T a0, T a1, T a2)
   return c == 0 ? a0 : (c == 1 ? a1 : a2);
 }
 
-template <typename T>
+// a ring stage holds ROWS rows (qz, qy) of 3 quadrature points: ROWS = 1 (9 stages per batch) or 3 (one
+// stage per quadrature layer); the q-point array is laid out accordingly (KParams::NL = 9 / ROWS, QG = 3 ROWS)
+template <typename T, int ROWS>
 __host__ __device__ constexpr size_t stage_elems(int F)
 {
-  return (size_t)F * 9 * CELLS;
+  return (size_t)F * 3 * ROWS * CELLS;
 }
 
-constexpr int IDX_ELEMS = 108 * CELLS; // dof indices of one batch
-constexpr int XROW  = 33;       // row stride of the exchange scratch (elements)
-constexpr int XSLOT = 5 * XROW; // rows: value, d_0, d_1, d_2, y
-
-// issue the bulk copy of stage j (quadrature layer j % 3 of this CTA's batch j / 3) into ring slot
-// j % NST; called by all lanes of warp 0, one elected lane issues
-template <typename T, int NST>
-__device__ __forceinline__ void issue_stage(const KParams<T> &p, int F, T *tab, uint64_t *full, uint64_t *empty,
-                                            uint32_t j, uint32_t cell0, int layer, int lane)
+constexpr int IDX_ROWS  = 109;              // 108 dof indices + one flag word per cell
+constexpr int IDX_ELEMS = IDX_ROWS * CELLS; // index block of one batch
+constexpr int MAX_NST   = 8;
+// exchange scratch of a warp: rows value, d_0, d_1, d_2, y of 32 elements.  Lane (cell k, component c)
+// owns element ((c >> 1) << 4) + 2 k + (c & 1) of a row: components 0/1 of the 8 cells are 8 adjacent
+// pairs, components 2/3 the next 8.  What the 4 lanes of a cell read in common (u, p, the diagonal of
+// grad u, y) are then broadcast reads of 64 or 128 contiguous bytes per warp: one wavefront each.
+constexpr int XROW  = 32;
+constexpr int XSLOT = 5 * XROW;
+template <typename T>
+struct Pair;
+template <>
+struct alignas(16) Pair<double>
 {
-  const uint32_t b = j % NST, r = j / NST;
-  if (r >= 1)
-    mbar_wait(&empty[b], (r - 1) & 1);
-  if (lane == 0)
-    {
-      const uint32_t bytes = (uint32_t)(stage_elems<T>(F) * sizeof(T));
-      const T *src = p.Q + (((uint64_t)(cell0 >> 5) * 3 + layer) * p.FT) * (9 * CELLS);
-      mbar_expect_tx(&full[b], bytes);
-      bulk_g2s(tab + (size_t)b * stage_elems<T>(F), src, bytes, &full[b]);
-    }
-  __syncwarp();
+  double a, b;
+};
+template <>
+struct alignas(8) Pair<float>
+{
+  float a, b;
+};
+
+// issue the bulk copy of stage j (row j % 9 of quadrature points of this CTA's batch j / 9) into ring slot
+// `slot`; called by one thread.  There is no producer warp: the slot is refilled by whichever warp is the
+// last to release it (an arrival counter per slot), so no warp ever waits for another one's progress.
+template <typename T, int ROWS>
+__device__ __forceinline__ void issue_stage(const KParams<T> &p, int F, T *tab, uint64_t *full, uint32_t j,
+                                            uint32_t slot)
+{
+  constexpr uint32_t SPB   = 9 / ROWS; // stages per batch
+  const uint32_t     bytes = (uint32_t)(stage_elems<T, ROWS>(F) * sizeof(T));
+  const uint32_t     batch = blockIdx.x + (j / SPB) * gridDim.x, row = j % SPB;
+  const T *src = p.Q + (((uint64_t)((p.cell_begin >> 5) + batch) * SPB + row) * p.FT) * (3 * ROWS * CELLS);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  mbar_expect_tx(&full[slot], bytes);
+  bulk_g2s(tab + (size_t)slot * stage_elems<T, ROWS>(F), src, bytes, &full[slot]);
 }
 
-template <typename T, bool GENERAL, bool CTD, bool CELLWISE, int NST>
-__global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, const Shape<T, 3> sh, const int F)
+template <typename T, bool GENERAL, bool CTD, bool CELLWISE, int ROWS>
+__global__ void __launch_bounds__(TPB, 2)
+  k_vmult_q2_newton(const KParams<T> p, const Shape<T, 3> sh, const int F, const int nst)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T        *tab   = reinterpret_cast<T *>(smem_raw);
-  T        *xch   = tab + NST * stage_elems<T>(F);                    // [warp][2][XSLOT]
-  uint32_t *ibuf  = reinterpret_cast<uint32_t *>(xch + (TPB / 32) * 2 * XSLOT); // [2][108][32] dof indices
+  T        *xch   = tab + nst * stage_elems<T, ROWS>(F);              // [warp][2][XSLOT]
+  uint32_t *ibuf  = reinterpret_cast<uint32_t *>(xch + (TPB / 32) * 2 * XSLOT); // [2][109][32] dof indices, flags
   uint64_t *full  = reinterpret_cast<uint64_t *>(ibuf + 2 * IDX_ELEMS);
-  uint64_t *empty = full + NST;
-  uint64_t *ifull = empty + NST, *iempty = ifull + 2;
+  uint64_t *ifull = full + MAX_NST;
+  uint32_t *cnt   = reinterpret_cast<uint32_t *>(ifull + 2); // [MAX_NST + 2] release counters (tables, indices)
 
   const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int      c = lane & 3, col = 8 * warp + (lane >> 2);
   const bool     is_p = (c == 3);
   const int      cv   = is_p ? 0 : c; // table row used by this lane (pressure lane: any valid row)
-  const int      bl   = lane & ~3;
-  const T        m0 = (c == 0) ? T(1) : T(0), m1 = (c == 1) ? T(1) : T(0), m2 = (c == 2) ? T(1) : T(0);
+  const int      xk   = 2 * (lane >> 2);                    // exchange rows: first element of this lane's cell
+  const int      xpos = ((c >> 1) << 4) + xk + (c & 1);     // ... and the element this lane owns
   T             *xw   = xch + warp * 2 * XSLOT;
   // column of this lane's cell in a 32-cell table row, for fields of component row 0, 1, 2 and cv
   const int      colr[4] = {col, (col + 4) & 31, (col + 8) & 31, (col + 4 * cv) & 31};
+  // this lane's entries of an index block: dof (c, j) at ixo + j * CELLS, the cell's flag word at flo
+  const int      ixo = (c * 27) * CELLS + ((col + 8 * c) & 31), flo = 108 * CELLS + col;
 
   if (threadIdx.x == 0)
     {
-      for (int s = 0; s < NST; ++s)
-        {
-          mbar_init(&full[s], 1);
-          mbar_init(&empty[s], TPB / 32);
-        }
+      for (int s = 0; s < nst; ++s)
+        mbar_init(&full[s], 1);
       for (int s = 0; s < 2; ++s)
-        {
-          mbar_init(&ifull[s], 1);
-          mbar_init(&iempty[s], TPB / 32);
-        }
+        mbar_init(&ifull[s], 1);
+      for (int s = 0; s < MAX_NST + 2; ++s)
+        cnt[s] = 0;
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -139,34 +160,30 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
 
   const uint32_t n_batches = (p.cell_end - p.cell_begin + CELLS - 1) / CELLS;
   const uint32_t my_n      = (blockIdx.x < n_batches) ? (n_batches - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const uint32_t n_stages  = my_n * 3;
+  const uint32_t n_stages  = my_n * (9 / ROWS);
+  if (my_n == 0)
+    return;
 
-  // prologue: fill NST-1 ring slots
-  if (warp == 0)
-    for (uint32_t j = 0; j < (uint32_t)(NST - 1) && j < n_stages; ++j)
-      {
-        const uint32_t bj = blockIdx.x + (j / 3) * gridDim.x;
-        issue_stage<T, NST>(p, F, tab, full, empty, j, p.cell_begin + bj * CELLS, j % 3, lane);
-      }
-
-  // dof indices of batch bi of this CTA -> index ring slot bi & 1 (one bulk copy of 13.5 KB)
+  // dof indices of batch bi of this CTA -> index ring slot bi & 1 (one bulk copy of 13.6 KB); one thread
   auto issue_idx = [&](uint32_t bi) {
-    const uint32_t b = bi & 1, r = bi >> 1;
-    if (r >= 1)
-      mbar_wait(&iempty[b], (r - 1) & 1);
-    if (lane == 0)
-      {
-        const uint32_t cell0 = p.cell_begin + (blockIdx.x + bi * gridDim.x) * CELLS;
-        mbar_expect_tx(&ifull[b], IDX_ELEMS * 4);
-        bulk_g2s(ibuf + b * IDX_ELEMS, p.idx + (uint64_t)(cell0 >> 5) * IDX_ELEMS, IDX_ELEMS * 4, &ifull[b]);
-      }
-    __syncwarp();
+    const uint32_t b     = bi & 1;
+    const uint32_t batch = (p.cell_begin >> 5) + blockIdx.x + bi * gridDim.x;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&ifull[b], IDX_ELEMS * 4);
+    bulk_g2s(ibuf + b * IDX_ELEMS, p.idx + (uint64_t)batch * IDX_ELEMS, IDX_ELEMS * 4, &ifull[b]);
   };
-  if (warp == 0 && my_n > 0)
-    issue_idx(0);
+  // prologue: indices of the first two batches, all ring slots
+  if (threadIdx.x == 0)
+    {
+      issue_idx(0);
+      if (my_n > 1)
+        issue_idx(1);
+      for (uint32_t j = 0; j < (uint32_t)nst && j < n_stages; ++j)
+        issue_stage<T, ROWS>(p, F, tab, full, j, j);
+    }
 
   const T  w = p.weight, nu = p.nu;
-  uint32_t it = 0;
+  uint32_t it = 0, slot = 0, par = 0; // stage counter, its ring slot and phase parity
   for (uint32_t bi = 0; bi < my_n; ++bi)
     {
       const uint32_t batch  = blockIdx.x + bi * gridDim.x;
@@ -174,32 +191,26 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
       const uint32_t cellr  = cell0 + col;
       const bool     active = cell_active(p, cellr);
       const uint32_t cell   = cellr < p.cell_end ? cellr : p.cell_end - 1;
-      // this lane's 27 dof indices sit in shared memory (staged one batch ahead)
-      const uint32_t *ixs = ibuf + (bi & 1) * IDX_ELEMS + (c * 27) * CELLS + ((col + 8 * c) & 31);
-      // cells with constrained dofs are rare: one warp-uniform test instead of one per dof
-      const bool slow = __any_sync(0xffffffffu, p.cell_flags[cell] != 0);
+      const uint32_t *ixs   = ibuf + (bi & 1) * IDX_ELEMS + ixo;
+      // this batch's index block (dof indices + one flag word per cell); cells with constrained dofs are
+      // rare: one warp-uniform test instead of one per dof
       mbar_wait(&ifull[bi & 1], (bi >> 1) & 1);
+      const bool slow = __any_sync(0xffffffffu, ibuf[(bi & 1) * IDX_ELEMS + flo] != 0);
 
       // ---- gather (read_dof_values) ------------------------------------------------------
       T t[27];
-      {
-        uint32_t iv[27];
+      if (!slow)
+        {
 #pragma unroll
-        for (int j = 0; j < 27; ++j)
-          iv[j] = ixs[j * CELLS];
-        if (!slow)
-          {
+          for (int j = 0; j < 27; ++j)
+            t[j] = p.src[ixs[j * CELLS]];
+        }
+      else
+        {
 #pragma unroll
-            for (int j = 0; j < 27; ++j)
-              t[j] = p.src[iv[j]];
-          }
-        else
-          {
-#pragma unroll
-            for (int j = 0; j < 27; ++j)
-              t[j] = gather_resolved(p, p.src, iv[j]);
-          }
-      }
+          for (int j = 0; j < 27; ++j)
+            t[j] = gather_resolved(p, p.src, ixs[j * CELLS]);
+        }
       T ij0 = 0, ij1 = 0, ij2 = 0, cdet = 0;
       if (!GENERAL)
         {
@@ -242,14 +253,18 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
 
       // ---- quadrature layers --------------------------------------------------------------
 #pragma unroll 1
-      for (int qz = 0; qz < 3; ++qz, ++it)
+      for (int qz = 0; qz < 3; ++qz)
         {
           // runtime (CTA-uniform) layer index: select from the constant bank instead of indexing it
           const T sz0 = sel3<T>(qz, sh.S[0], sh.S[3], sh.S[6]), sz1 = sel3<T>(qz, sh.S[1], sh.S[4], sh.S[7]),
                   sz2 = sel3<T>(qz, sh.S[2], sh.S[5], sh.S[8]);
           const T gz0 = sel3<T>(qz, sh.G[0], sh.G[3], sh.G[6]), gz1 = sel3<T>(qz, sh.G[1], sh.G[4], sh.G[7]),
                   gz2 = sel3<T>(qz, sh.G[2], sh.G[5], sh.G[8]);
+          // test side: Cartesian cells carry the quadrature weights in the sweep matrices (Shape::Sw/Gw/Dt),
+          // general cells get them with JxW from the table
           const T wz  = sel3<T>(qz, sh.w[0], sh.w[1], sh.w[2]);
+          const T tz0 = GENERAL ? sz0 : sz0 * wz, tz1 = GENERAL ? sz1 : sz1 * wz, tz2 = GENERAL ? sz2 : sz2 * wz;
+          const T hz0 = GENERAL ? gz0 : gz0 * wz, hz1 = GENERAL ? gz1 : gz1 * wz, hz2 = GENERAL ? gz2 : gz2 * wz;
           T       vl[9], wl[9];
 #pragma unroll
           for (int a = 0; a < 9; ++a)
@@ -257,132 +272,151 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
               vl[a] = sz0 * t[a] + sz1 * t[a + 9] + sz2 * t[a + 18];
               wl[a] = 0;
             }
-          const uint32_t slot = it % NST;
-          mbar_wait(&full[slot], (it / NST) & 1);
-          const T *tb = tab + (size_t)slot * stage_elems<T>(F);
-#define GLSB_TAB(f, a) tb[((f)*9 + (a)) * CELLS + col]          /* fields without a component row */
-#define GLSB_TABR(f, a, r) tb[((f)*9 + (a)) * CELLS + colr[r]] /* rotated by 4 * row, see qoff() */
-
+          const T *tb = nullptr;
 #pragma unroll
-          for (int a = 0; a < 9; ++a)
+          for (int qy = 0; qy < 3; ++qy)
             {
-              const int qx = a % 3, qy = a / 3;
-              const T   val = vl[a];
-              const T rx = sh.D[qx * 3] * vl[3 * qy] + sh.D[qx * 3 + 1] * vl[3 * qy + 1] + sh.D[qx * 3 + 2] * vl[3 * qy + 2];
-              const T ry = sh.D[qy * 3] * vl[qx] + sh.D[qy * 3 + 1] * vl[qx + 3] + sh.D[qy * 3 + 2] * vl[qx + 6];
-              const T rz = gz0 * t[a] + gz1 * t[a + 9] + gz2 * t[a + 18];
-              // geometry: physical gradient of this lane's component
-              T g0, g1, g2, jq;
-              T J00, J01, J02, J10, J11, J12, J20, J21, J22;
-              if (GENERAL)
+              if (qy % ROWS == 0)
                 {
-                  J00 = GLSB_TAB(p.fJ + 0, a), J01 = GLSB_TAB(p.fJ + 1, a), J02 = GLSB_TAB(p.fJ + 2, a);
-                  J10 = GLSB_TAB(p.fJ + 3, a), J11 = GLSB_TAB(p.fJ + 4, a), J12 = GLSB_TAB(p.fJ + 5, a);
-                  J20 = GLSB_TAB(p.fJ + 6, a), J21 = GLSB_TAB(p.fJ + 7, a), J22 = GLSB_TAB(p.fJ + 8, a);
-                  jq  = GLSB_TAB(p.fjxw, a);
-                  g0  = J00 * rx + J10 * ry + J20 * rz;
-                  g1  = J01 * rx + J11 * ry + J21 * rz;
-                  g2  = J02 * rx + J12 * ry + J22 * rz;
+                  mbar_wait(&full[slot], par);
+                  tb = tab + (size_t)slot * stage_elems<T, ROWS>(F);
                 }
-              else
-                {
-                  g0 = rx * ij0, g1 = ry * ij1, g2 = rz * ij2;
-                  jq = cdet * wz * (sh.w[qx] * sh.w[qy]);
-                }
-              // ---- exchange round 1: publish value and gradient of this component --------------
-              T *xs = xw + (a & 1) * XSLOT;
-              xs[lane]            = val;
-              xs[XROW + lane]     = g0;
-              xs[2 * XROW + lane] = g1;
-              xs[3 * XROW + lane] = g2;
-              // tables (field offsets of the prefix are fixed: U 0..2, grad U 3..11, grad P 12..14)
-              const T U0 = GLSB_TABR(0, a, 0), U1 = GLSB_TABR(1, a, 1), U2 = GLSB_TABR(2, a, 2);
-              const T H0 = GLSB_TABR(3 + 3 * cv, a, 3), H1 = GLSB_TABR(4 + 3 * cv, a, 3), H2 = GLSB_TABR(5 + 3 * cv, a, 3);
-              const T Pc = GLSB_TABR(12 + cv, a, 3);
-              const T d1 = CELLWISE ? d1c : GLSB_TAB(p.fd1q, a);
-              const T d2 = CELLWISE ? d2c : GLSB_TAB(p.fd2q, a);
-              __syncwarp();
-              const T u0 = xs[bl], u1 = xs[bl + 1], u2 = xs[bl + 2], pp = xs[bl + 3];
-              const T div = xs[XROW + bl] + xs[2 * XROW + bl + 1] + xs[3 * XROW + bl + 2];
-              // column c of grad u and d_c p: entry (1 + c) of lanes bl .. bl + 3
-              const T *xc  = xs + (1 + cv) * XROW + bl;
-              const T  Gc0 = xc[0], Gc1 = xc[1], Gc2 = xc[2], gpc = xc[3];
-              const T  td  = val * w;
-              const T  sgu = g0 * U0 + g1 * U1 + g2 * U2; // U . grad u_c
-              const T  ugs = H0 * u0 + H1 * u1 + H2 * u2; // u . grad U_c
-              T        y   = sgu + ugs;
-              if (CTD)
-                y = td + y;
-              // ---- exchange round 2: the pressure row needs y of the three velocity rows --------
-              xs[4 * XROW + lane] = y;
-              // velocity row c
-              const T r0  = d1 * (y + gpc);
-              const T sgs = H0 * U0 + H1 * U1 + H2 * U2; // U . grad U_c
-              T       rb  = Pc + sgs;
-              if (CTD)
-                rb = (GLSB_TABR(cv, a, 3) * w + GLSB_TABR(p.fO + cv, a, 3)) + rb;
-              const T rr1  = d1 * rb;
-              const T diag = d2 * div - pp;
-              T       vo   = td + sgu + ugs;
-              T       o0   = nu * (g0 + Gc0) + U0 * r0 + u0 * rr1 + m0 * diag;
-              T       o1   = nu * (g1 + Gc1) + U1 * r0 + u1 * rr1 + m1 * diag;
-              T       o2   = nu * (g2 + Gc2) + U2 * r0 + u2 * rr1 + m2 * diag;
-              __syncwarp();
-              // pressure row: (q, div u) and delta_1 (grad q, residual_0)
-              const T y0 = xs[4 * XROW + bl], y1 = xs[4 * XROW + bl + 1], y2 = xs[4 * XROW + bl + 2];
-              const T q0 = d1 * (y0 + g0), q1 = d1 * (y1 + g1), q2 = d1 * (y2 + g2);
-              vo = is_p ? div : vo;
-              o0 = is_p ? q0 : o0;
-              o1 = is_p ? q1 : o1;
-              o2 = is_p ? q2 : o2;
-              // submit_value / submit_gradient: times JxW, back to the reference cell
-              vo *= jq;
-              T ox, oy, oz;
-              if (GENERAL)
-                {
-                  ox = (J00 * o0 + J01 * o1 + J02 * o2) * jq;
-                  oy = (J10 * o0 + J11 * o1 + J12 * o2) * jq;
-                  oz = (J20 * o0 + J21 * o1 + J22 * o2) * jq;
-                }
-              else
-                {
-                  ox = o0 * (ij0 * jq), oy = o1 * (ij1 * jq), oz = o2 * (ij2 * jq);
-                }
-              // integrate: collocation derivative transposed in x and y inside the layer, z into acc
-              wl[a] += vo;
+              constexpr int QPS = 3 * ROWS;
+              const int     qlo = (qy % ROWS) * 3; // first point of this row inside the stage
+#define GLSB_TAB(f, x) tb[((f)*QPS + qlo + (x)) * CELLS + col]          /* fields without a component row */
+#define GLSB_TABR(f, x, r) tb[((f)*QPS + qlo + (x)) * CELLS + colr[r]] /* rotated by 4 * row, see qoff() */
 #pragma unroll
-              for (int i = 0; i < 3; ++i)
+              for (int qx = 0; qx < 3; ++qx)
                 {
-                  wl[i + 3 * qy] += sh.D[qx * 3 + i] * ox;
-                  wl[qx + 3 * i] += sh.D[qy * 3 + i] * oy;
+                  const int a   = 3 * qy + qx;
+                  const T   val = vl[a];
+                  const T rx = sh.D[qx * 3] * vl[3 * qy] + sh.D[qx * 3 + 1] * vl[3 * qy + 1] + sh.D[qx * 3 + 2] * vl[3 * qy + 2];
+                  const T ry = sh.D[qy * 3] * vl[qx] + sh.D[qy * 3 + 1] * vl[qx + 3] + sh.D[qy * 3 + 2] * vl[qx + 6];
+                  const T rz = gz0 * t[a] + gz1 * t[a + 9] + gz2 * t[a + 18];
+                  // geometry: physical gradient of this lane's component
+                  T g0, g1, g2, jq = 0;
+                  T J00, J01, J02, J10, J11, J12, J20, J21, J22;
+                  if (GENERAL)
+                    {
+                      J00 = GLSB_TAB(p.fJ + 0, qx), J01 = GLSB_TAB(p.fJ + 1, qx), J02 = GLSB_TAB(p.fJ + 2, qx);
+                      J10 = GLSB_TAB(p.fJ + 3, qx), J11 = GLSB_TAB(p.fJ + 4, qx), J12 = GLSB_TAB(p.fJ + 5, qx);
+                      J20 = GLSB_TAB(p.fJ + 6, qx), J21 = GLSB_TAB(p.fJ + 7, qx), J22 = GLSB_TAB(p.fJ + 8, qx);
+                      jq  = GLSB_TAB(p.fjxw, qx);
+                      g0  = J00 * rx + J10 * ry + J20 * rz;
+                      g1  = J01 * rx + J11 * ry + J21 * rz;
+                      g2  = J02 * rx + J12 * ry + J22 * rz;
+                    }
+                  else
+                    {
+                      g0 = rx * ij0, g1 = ry * ij1, g2 = rz * ij2;
+                    }
+                  // ---- exchange round 1: publish value and gradient of this component --------------
+                  T *xs = xw + (a & 1) * XSLOT;
+                  xs[xpos]            = val;
+                  xs[XROW + xpos]     = g0;
+                  xs[2 * XROW + xpos] = g1;
+                  xs[3 * XROW + xpos] = g2;
+                  // tables (field offsets of the prefix are fixed: U 0..2, grad U 3..11, grad P 12..14)
+                  const T U0 = GLSB_TABR(0, qx, 0), U1 = GLSB_TABR(1, qx, 1), U2 = GLSB_TABR(2, qx, 2);
+                  const T H0 = GLSB_TABR(3 + 3 * cv, qx, 3), H1 = GLSB_TABR(4 + 3 * cv, qx, 3),
+                          H2 = GLSB_TABR(5 + 3 * cv, qx, 3);
+                  const T Pc = GLSB_TABR(12 + cv, qx, 3);
+                  const T d1 = CELLWISE ? d1c : GLSB_TAB(p.fd1q, qx);
+                  const T d2 = CELLWISE ? d2c : GLSB_TAB(p.fd2q, qx);
+                  __syncwarp();
+                  const Pair<T> u01 = *reinterpret_cast<const Pair<T> *>(xs + xk),
+                                u2p = *reinterpret_cast<const Pair<T> *>(xs + 16 + xk);
+                  const T u0 = u01.a, u1 = u01.b, u2 = u2p.a, pp = u2p.b;
+                  const T div = xs[XROW + xk] + xs[2 * XROW + xk + 1] + xs[3 * XROW + 16 + xk];
+                  // column c of grad u and d_c p: row (1 + c), the 4 elements of this cell
+                  const T      *xc  = xs + (1 + cv) * XROW + xk;
+                  const Pair<T> G01 = *reinterpret_cast<const Pair<T> *>(xc),
+                                G2p = *reinterpret_cast<const Pair<T> *>(xc + 16);
+                  const T Gc0 = G01.a, Gc1 = G01.b, Gc2 = G2p.a, gpc = G2p.b;
+                  const T  td  = val * w;
+                  const T  sgu = g0 * U0 + g1 * U1 + g2 * U2; // U . grad u_c
+                  const T  ugs = H0 * u0 + H1 * u1 + H2 * u2; // u . grad U_c
+                  T        y   = sgu + ugs;
+                  if (CTD)
+                    y = td + y;
+                  // ---- exchange round 2: the pressure row needs y of the three velocity rows --------
+                  xs[4 * XROW + xpos] = y;
+                  // velocity row c
+                  const T r0  = d1 * (y + gpc);
+                  const T sgs = H0 * U0 + H1 * U1 + H2 * U2; // U . grad U_c
+                  T       rb  = Pc + sgs;
+                  if (CTD)
+                    rb = (GLSB_TABR(cv, qx, 3) * w + GLSB_TABR(p.fO + cv, qx, 3)) + rb;
+                  const T rr1  = d1 * rb;
+                  const T diag = d2 * div - pp;
+                  T       vo   = td + sgu + ugs;
+                  T       o0   = nu * (g0 + Gc0) + U0 * r0 + u0 * rr1 + (c == 0 ? diag : T(0));
+                  T       o1   = nu * (g1 + Gc1) + U1 * r0 + u1 * rr1 + (c == 1 ? diag : T(0));
+                  T       o2   = nu * (g2 + Gc2) + U2 * r0 + u2 * rr1 + (c == 2 ? diag : T(0));
+                  __syncwarp();
+                  // pressure row: (q, div u) and delta_1 (grad q, residual_0)
+                  const Pair<T> y01 = *reinterpret_cast<const Pair<T> *>(xs + 4 * XROW + xk);
+                  const T       y0 = y01.a, y1 = y01.b, y2 = xs[4 * XROW + 16 + xk];
+                  const T q0 = d1 * (y0 + g0), q1 = d1 * (y1 + g1), q2 = d1 * (y2 + g2);
+                  vo = is_p ? div : vo;
+                  o0 = is_p ? q0 : o0;
+                  o1 = is_p ? q1 : o1;
+                  o2 = is_p ? q2 : o2;
+                  // submit_value / submit_gradient: times JxW, back to the reference cell
+                  T ox, oy, oz;
+                  if (GENERAL)
+                    {
+                      vo *= jq;
+                      ox = (J00 * o0 + J01 * o1 + J02 * o2) * jq;
+                      oy = (J10 * o0 + J11 * o1 + J12 * o2) * jq;
+                      oz = (J20 * o0 + J21 * o1 + J22 * o2) * jq;
+                    }
+                  else
+                    {
+                      // weights live in Dt / Sw / Gw, det J is applied once per dof before the scatter
+                      ox = o0 * ij0, oy = o1 * ij1, oz = o2 * ij2;
+                    }
+                  // integrate: collocation derivative transposed in x and y inside the layer, z into acc
+                  wl[a] += vo;
+#pragma unroll
+                  for (int i = 0; i < 3; ++i)
+                    {
+                      wl[i + 3 * qy] += (GENERAL ? sh.D[qx * 3 + i] : sh.Dt[qx * 3 + i]) * ox;
+                      wl[qx + 3 * i] += (GENERAL ? sh.D[qy * 3 + i] : sh.Dt[qy * 3 + i]) * oy;
+                    }
+                  acc[a] += hz0 * oz;
+                  acc[a + 9] += hz1 * oz;
+                  acc[a + 18] += hz2 * oz;
                 }
-              acc[a] += gz0 * oz;
-              acc[a + 9] += gz1 * oz;
-              acc[a + 18] += gz2 * oz;
-            }
 #undef GLSB_TAB
 #undef GLSB_TABR
-          // release the ring slot, then let warp 0 refill the slot released one layer ago
-          __syncwarp();
-          if (lane == 0)
-            mbar_arrive(&empty[slot]);
-          if (warp == 0)
-            {
-              const uint32_t j = it + NST - 1;
-              if (j < n_stages)
+              // release the ring slot; the last warp to do so refills it with the stage nst stages ahead
+              if ((qy + 1) % ROWS == 0)
                 {
-                  const uint32_t bj = blockIdx.x + (j / 3) * gridDim.x;
-                  issue_stage<T, NST>(p, F, tab, full, empty, j, p.cell_begin + bj * CELLS, j % 3, lane);
+                  __syncwarp();
+                  if (lane == 0)
+                    {
+                      if (atomicAdd(&cnt[slot], 1u) == TPB / 32 - 1)
+                        {
+                          cnt[slot] = 0;
+                          if (it + nst < n_stages)
+                            issue_stage<T, ROWS>(p, F, tab, full, it + nst, slot);
+                        }
+                    }
+                  ++it;
+                  if (++slot == (uint32_t)nst)
+                    {
+                      slot = 0;
+                      par ^= 1;
+                    }
                 }
-              if (qz == 0 && bi + 1 < my_n)
-                issue_idx(bi + 1);
             }
 #pragma unroll
           for (int a = 0; a < 9; ++a)
             {
-              acc[a] += sz0 * wl[a];
-              acc[a + 9] += sz1 * wl[a];
-              acc[a + 18] += sz2 * wl[a];
+              acc[a] += tz0 * wl[a];
+              acc[a + 9] += tz1 * wl[a];
+              acc[a + 18] += tz2 * wl[a];
             }
         }
 
@@ -395,7 +429,8 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
             const T a = acc[i + 9 * k], b = acc[i + 3 + 9 * k], d = acc[i + 6 + 9 * k];
 #pragma unroll
             for (int q = 0; q < 3; ++q)
-              acc[i + 3 * q + 9 * k] = sh.S[q] * a + sh.S[3 + q] * b + sh.S[6 + q] * d;
+              acc[i + 3 * q + 9 * k] = GENERAL ? sh.S[q] * a + sh.S[3 + q] * b + sh.S[6 + q] * d :
+                                                 sh.Sw[q] * a + sh.Sw[3 + q] * b + sh.Sw[6 + q] * d;
           }
 #pragma unroll
       for (int l = 0; l < 9; ++l)
@@ -403,48 +438,71 @@ __global__ void __launch_bounds__(TPB, 2) k_vmult_q2_newton(const KParams<T> p, 
           const T a = acc[3 * l], b = acc[3 * l + 1], d = acc[3 * l + 2];
 #pragma unroll
           for (int q = 0; q < 3; ++q)
-            acc[3 * l + q] = sh.S[q] * a + sh.S[3 + q] * b + sh.S[6 + q] * d;
+            acc[3 * l + q] = GENERAL ? sh.S[q] * a + sh.S[3 + q] * b + sh.S[6 + q] * d :
+                                       sh.Sw[q] * a + sh.Sw[3 + q] * b + sh.Sw[6 + q] * d;
         }
-
-      // ---- scatter (distribute_local_to_global): all index loads first, then the atomics ---
-      if (active)
+      if (!GENERAL)
         {
-          uint32_t iv[27];
 #pragma unroll
           for (int j = 0; j < 27; ++j)
-            iv[j] = ixs[j * CELLS];
+            acc[j] *= cdet;
+        }
+
+      // ---- scatter (distribute_local_to_global) ------------------------------------------
+      if (active)
+        {
           if (!slow)
             {
 #pragma unroll
               for (int j = 0; j < 27; ++j)
-                atomic_add(p.dst + iv[j], acc[j]);
+                atomic_add(p.dst + ixs[j * CELLS], acc[j]);
             }
           else
             {
 #pragma unroll
               for (int j = 0; j < 27; ++j)
-                scatter_resolved(p, p.dst, iv[j], acc[j]);
+                scatter_resolved(p, p.dst, ixs[j * CELLS], acc[j]);
             }
         }
-      // release the index ring slot
+      // release the index ring slot; the last warp refills it with the block two batches ahead
       __syncwarp();
       if (lane == 0)
-        mbar_arrive(&iempty[bi & 1]);
+        {
+          if (atomicAdd(&cnt[MAX_NST + (bi & 1)], 1u) == TPB / 32 - 1)
+            {
+              cnt[MAX_NST + (bi & 1)] = 0;
+              if (bi + 2 < my_n)
+                issue_idx(bi + 2);
+            }
+        }
     }
 }
 
-template <typename T>
+template <typename T, int ROWS>
 size_t smem_bytes(int F, int nst)
 {
-  return (nst * stage_elems<T>(F) + (TPB / 32) * 2 * XSLOT) * sizeof(T) + 2 * IDX_ELEMS * 4 + (2 * nst + 4) * sizeof(uint64_t);
+  return (nst * stage_elems<T, ROWS>(F) + (TPB / 32) * 2 * XSLOT) * sizeof(T) +
+         2 * IDX_ELEMS * 4 + (MAX_NST + 2) * (sizeof(uint64_t) + sizeof(uint32_t));
 }
 
-template <typename T, bool GENERAL, bool CTD, bool CELLWISE, int NST>
-static int launch(const KParams<T> &p, const Shape<T, 3> &S, int F, cudaStream_t s)
+// ring depth: as deep as two CTAs per SM allow (at most MAX_NST), at least 2
+template <typename T, int ROWS>
+int ring_depth(int F)
+{
+  int nst = 2;
+  while (nst < MAX_NST && 2 * (smem_bytes<T, ROWS>(F, nst + 1) + 1024) <= 228 * 1024)
+    ++nst;
+  return nst;
+}
+
+template <typename T, bool GENERAL, bool CTD, bool CELLWISE, int ROWS>
+static int launch_rows(const KParams<T> &p, const Shape<T, 3> &S, int F, cudaStream_t s)
 {
   static int   n_sm = 0;
-  const size_t smem = smem_bytes<T>(F, NST);
-  auto         kern = k_vmult_q2_newton<T, GENERAL, CTD, CELLWISE, NST>;
+  static const int env_nst = getenv("GLSB_Q2_NST") ? atoi(getenv("GLSB_Q2_NST")) : 0;
+  const int    nst  = env_nst >= 2 && env_nst <= MAX_NST ? env_nst : ring_depth<T, ROWS>(F);
+  const size_t smem = smem_bytes<T, ROWS>(F, nst);
+  auto         kern = k_vmult_q2_newton<T, GENERAL, CTD, CELLWISE, ROWS>;
   if (smem > 227 * 1024)
     return -1;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -461,16 +519,24 @@ static int launch(const KParams<T> &p, const Shape<T, 3> &S, int F, cudaStream_t
   const uint32_t n_batches = (p.cell_end - p.cell_begin + CELLS - 1) / CELLS;
   const int      use_sm    = (p.sm_reserve > 0 && p.sm_reserve < n_sm) ? n_sm - p.sm_reserve : n_sm;
   const uint32_t grid      = n_batches < (uint32_t)(use_sm * bps) ? n_batches : (uint32_t)(use_sm * bps);
-  kern<<<grid, TPB, smem, s>>>(p, S, F);
+  kern<<<grid, TPB, smem, s>>>(p, S, F, nst);
   return cudaGetLastError() != cudaSuccess;
 }
 
-template <typename T, bool GENERAL, int NST>
+template <typename T, bool GENERAL, bool CTD, bool CELLWISE>
+static int launch(const KParams<T> &p, const Shape<T, 3> &S, int F, cudaStream_t s)
+{
+  if (p.QG == 9)
+    return launch_rows<T, GENERAL, CTD, CELLWISE, 3>(p, S, F, s);
+  return launch_rows<T, GENERAL, CTD, CELLWISE, 1>(p, S, F, s);
+}
+
+template <typename T, bool GENERAL>
 static int launch_flags(const KParams<T> &p, const Shape<T, 3> &S, int F, cudaStream_t s)
 {
   if (p.ctd)
-    return p.cell_wise ? launch<T, GENERAL, true, true, NST>(p, S, F, s) : launch<T, GENERAL, true, false, NST>(p, S, F, s);
-  return p.cell_wise ? launch<T, GENERAL, false, true, NST>(p, S, F, s) : launch<T, GENERAL, false, false, NST>(p, S, F, s);
+    return p.cell_wise ? launch<T, GENERAL, true, true>(p, S, F, s) : launch<T, GENERAL, true, false>(p, S, F, s);
+  return p.cell_wise ? launch<T, GENERAL, false, true>(p, S, F, s) : launch<T, GENERAL, false, false>(p, S, F, s);
 }
 
 } // namespace q2
