@@ -86,11 +86,15 @@ __host__ __device__ constexpr size_t stage_elems(int F)
 constexpr int IDX_ROWS  = 109;              // 108 dof indices + one flag word per cell
 constexpr int IDX_ELEMS = IDX_ROWS * CELLS; // index block of one batch
 constexpr int MAX_NST   = 8;
-// exchange scratch of a warp: rows value, d_0, d_1, d_2, y of 32 elements.  Lane (cell k, component c)
-// owns element ((c >> 1) << 4) + 2 k + (c & 1) of a row: components 0/1 of the 8 cells are 8 adjacent
-// pairs, components 2/3 the next 8.  What the 4 lanes of a cell read in common (u, p, the diagonal of
-// grad u, y) are then broadcast reads of 64 or 128 contiguous bytes per warp: one wavefront each.
-constexpr int XROW  = 32;
+// exchange scratch of a warp: rows value, d_0, d_1, d_2, y.  A row holds 16 pairs (components 0/1 or 2/3
+// of a cell, 16 bytes); lane (cell k, component c), h = c >> 1, owns element c & 1 of pair
+// ((k + 4 h) & 7) + 8 h.  With that (measured with ncu, shared-memory wavefronts per warp instruction):
+//   * the 64-bit stores of a half-warp hit 16 different bank pairs (2 wavefronts, the minimum);
+//   * what the 4 lanes of a cell read in common (u, p, diagonal of grad u, y) are broadcast reads of
+//     contiguous or 16-byte-strided words: 1 wavefront per 64-bit, 2 per 128-bit load;
+//   * the column reads (lane c reads row 1 + c) touch 3 rows per quarter-warp: rows are 36 elements apart,
+//     i.e. staggered by two 16-byte bank groups, so these 128-bit loads take 4 wavefronts, not 12.
+constexpr int XROW  = 36;
 constexpr int XSLOT = 5 * XROW;
 template <typename T>
 struct Pair;
@@ -137,8 +141,9 @@ __global__ void __launch_bounds__(TPB, 2)
   const int      c = lane & 3, col = 8 * warp + (lane >> 2);
   const bool     is_p = (c == 3);
   const int      cv   = is_p ? 0 : c; // table row used by this lane (pressure lane: any valid row)
-  const int      xk   = 2 * (lane >> 2);                    // exchange rows: first element of this lane's cell
-  const int      xpos = ((c >> 1) << 4) + xk + (c & 1);     // ... and the element this lane owns
+  // exchange rows: the pairs (components 0/1 and 2/3) of this lane's cell, and the element this lane owns
+  const int      xp0 = 2 * (lane >> 2), xp1 = 2 * (8 + (((lane >> 2) + 4) & 7));
+  const int      xpos = ((c >> 1) ? xp1 : xp0) + (c & 1);
   T             *xw   = xch + warp * 2 * XSLOT;
   // column of this lane's cell in a 32-cell table row, for fields of component row 0, 1, 2 and cv
   const int      colr[4] = {col, (col + 4) & 31, (col + 8) & 31, (col + 4 * cv) & 31};
@@ -324,14 +329,14 @@ __global__ void __launch_bounds__(TPB, 2)
                   const T d1 = CELLWISE ? d1c : GLSB_TAB(p.fd1q, qx);
                   const T d2 = CELLWISE ? d2c : GLSB_TAB(p.fd2q, qx);
                   __syncwarp();
-                  const Pair<T> u01 = *reinterpret_cast<const Pair<T> *>(xs + xk),
-                                u2p = *reinterpret_cast<const Pair<T> *>(xs + 16 + xk);
+                  const Pair<T> u01 = *reinterpret_cast<const Pair<T> *>(xs + xp0),
+                                u2p = *reinterpret_cast<const Pair<T> *>(xs + xp1);
                   const T u0 = u01.a, u1 = u01.b, u2 = u2p.a, pp = u2p.b;
-                  const T div = xs[XROW + xk] + xs[2 * XROW + xk + 1] + xs[3 * XROW + 16 + xk];
+                  const T div = xs[XROW + xp0] + xs[2 * XROW + xp0 + 1] + xs[3 * XROW + xp1];
                   // column c of grad u and d_c p: row (1 + c), the 4 elements of this cell
-                  const T      *xc  = xs + (1 + cv) * XROW + xk;
-                  const Pair<T> G01 = *reinterpret_cast<const Pair<T> *>(xc),
-                                G2p = *reinterpret_cast<const Pair<T> *>(xc + 16);
+                  const T      *xc  = xs + (1 + cv) * XROW;
+                  const Pair<T> G01 = *reinterpret_cast<const Pair<T> *>(xc + xp0),
+                                G2p = *reinterpret_cast<const Pair<T> *>(xc + xp1);
                   const T Gc0 = G01.a, Gc1 = G01.b, Gc2 = G2p.a, gpc = G2p.b;
                   const T  td  = val * w;
                   const T  sgu = g0 * U0 + g1 * U1 + g2 * U2; // U . grad u_c
@@ -355,8 +360,8 @@ __global__ void __launch_bounds__(TPB, 2)
                   T       o2   = nu * (g2 + Gc2) + U2 * r0 + u2 * rr1 + (c == 2 ? diag : T(0));
                   __syncwarp();
                   // pressure row: (q, div u) and delta_1 (grad q, residual_0)
-                  const Pair<T> y01 = *reinterpret_cast<const Pair<T> *>(xs + 4 * XROW + xk);
-                  const T       y0 = y01.a, y1 = y01.b, y2 = xs[4 * XROW + 16 + xk];
+                  const Pair<T> y01 = *reinterpret_cast<const Pair<T> *>(xs + 4 * XROW + xp0);
+                  const T       y0 = y01.a, y1 = y01.b, y2 = xs[4 * XROW + xp1];
                   const T q0 = d1 * (y0 + g0), q1 = d1 * (y1 + g1), q2 = d1 * (y2 + g2);
                   vo = is_p ? div : vo;
                   o0 = is_p ? q0 : o0;
