@@ -41,6 +41,9 @@ SYMBOLS = {
     "glsb_last_error": (C.c_char_p, [_P]),
     "glsb_invalidate_system": (_I, [_P]),
     "glsb_vmult": (_I, [_P, _P, _P, _D, _P]),
+    "glsb_vmult_host": (_I, [_P, _P, _P, _D, _P]),
+    "glsb_host_register": (_I, [_P, _U64]),
+    "glsb_host_unregister": (_I, [_P]),
     "glsb_vmult_begin": (_I, [_P, _P, _P]),
     "glsb_vmult_cells": (_I, [_P, _P, _P, _D, _I, _P]),
     "glsb_vmult_finish": (_I, [_P, _P, _P, _P]),

@@ -111,6 +111,53 @@ __global__ void k_unpack_add(T *__restrict__ vec, const T *__restrict__ buf, con
     atomicAdd(vec + idx[t], buf[t]);
 }
 
+// glsb_vmult_host: last[d] = last chunk of cells that touches vector entry d
+__global__ void k_last_touch(const uint32_t *__restrict__ idx, const uint8_t *__restrict__ chunk_of_batch,
+                             const uint32_t *__restrict__ row_dof, const uint32_t *__restrict__ row_ptr,
+                             const uint32_t *__restrict__ ecol, uint32_t *__restrict__ last, uint32_t n_slots,
+                             uint32_t hole_begin, uint32_t hole_end, uint32_t ndof)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)ndof * n_slots)
+    return;
+  const uint32_t i = t % n_slots, j = t / n_slots;
+  if (i >= hole_begin && i < hole_end)
+    return;
+  // the rotation inside a 32-cell row does not matter here: every entry of the row belongs to the batch
+  const uint32_t iv = idx[((uint64_t)(i >> 5) * (ndof + 1) + j) * 32 + (i & 31)];
+  const uint32_t c  = chunk_of_batch[i >> 5];
+  if (iv & GLSB_CONSTRAINED_BIT)
+    {
+      const uint32_t r = iv & ~GLSB_CONSTRAINED_BIT;
+      atomicMax(last + row_dof[r], c);
+      for (uint32_t e = row_ptr[r]; e < row_ptr[r + 1]; ++e)
+        atomicMax(last + ecol[e], c);
+    }
+  else
+    atomicMax(last + iv, c);
+}
+// flag[d] = entry d is touched again after the chunk whose completion triggers its download
+__global__ void k_late_flags(const uint32_t *__restrict__ last, const uint64_t *__restrict__ in_end, uint32_t nch,
+                             uint8_t *__restrict__ flag, uint64_t n)
+{
+  const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n)
+    return;
+  uint32_t c = 0;
+  while (c + 1 < nch && in_end[c] <= d)
+    ++c;
+  flag[d] = last[d] > c;
+}
+// re-send the flagged entries with stores to the (mapped, page-locked) host vector
+template <typename T>
+__global__ void k_flush_flagged(T *__restrict__ host_dst, const T *__restrict__ dev_dst,
+                                const uint8_t *__restrict__ flag, uint64_t n)
+{
+  const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < n && flag[d])
+    host_dst[d] = dev_dst[d];
+}
+
 // diag finish: constrained rows -> 1, then x -> |x| > 1e-10 ? 1/x : 1 (operator_ns.cc:220-224)
 template <typename T>
 __global__ void k_set_indexed(T *__restrict__ v, const uint32_t *__restrict__ idx, uint32_t n, T val)
@@ -176,10 +223,29 @@ struct glsb_op
   DevBuf diag_skip, dc_cell, dc_col_ptr, dc_col_dof, dc_ent_ptr, dc_ent_loc, dc_ent_val;
   uint32_t dc_n_list = 0;
 
+  // vmult on host vectors (glsb_vmult_host): cell chunks with the dof ranges they need / complete
+  struct HostPipe
+  {
+    bool                     ready = false;
+    cudaStream_t             s_in = nullptr, s_out = nullptr;
+    cudaEvent_t              e_start = nullptr, e_done = nullptr;
+    std::vector<cudaEvent_t> e_in, e_cells;
+    std::vector<uint32_t>    cell_begin; // [n_chunks + 1] slots (multiples of 32)
+    std::vector<uint64_t>    in_end;     // [n_chunks] src[0, in_end[c]) is needed by chunks 0..c
+    std::vector<uint64_t>    out_end;    // [n_chunks] dst[0, out_end[c]) is final after chunks 0..c
+    std::vector<uint32_t>    cidx_end;   // [n_chunks] constrained indices (sorted) below out_end[c]
+    std::vector<uint32_t>    cidx_end_spec; // ... below in_end[c] (speculative download)
+    DevBuf                   src, dst, late_flag; // late_flag[d]: entry d changes after its speculative download
+    uint64_t                 n_late = 0;
+  } hp;
+  std::vector<uint32_t> cidx_sorted;
+  std::vector<uint32_t> slot_lo, slot_hi; // per 32-slot batch: smallest / largest vector index touched
+
   ShapeHost shape;
   bool      lin_valid = false, prev_valid = false;
   double    lin_dt = 0;
   int       variant_forced = 0, sm_reserve = 0;
+  uint32_t  range_override[2] = {0, 0}; // glsb_vmult_host: explicit slot range for the next cell launch
   uint64_t  launches = 0;
   std::string err;
   std::string variant = "generic";
@@ -270,6 +336,11 @@ void cell_range(const glsb_op *op, int which, KParams<T> &p)
     {
       p.cell_begin = op->n_int_pad;
       p.hole_begin = p.hole_end = 0;
+    }
+  if (op->range_override[1] > op->range_override[0])
+    {
+      p.cell_begin = op->range_override[0];
+      p.cell_end   = op->range_override[1];
     }
 }
 
@@ -502,10 +573,12 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
       if (d->row_dof[r] >= d->n_owned)
         row_ghost[r] = 1;
     }
-  std::vector<uint8_t> is_boundary(nc, 0), has_weighted(nc, 0), has_constrained(nc, 0);
+  std::vector<uint8_t>  is_boundary(nc, 0), has_weighted(nc, 0), has_constrained(nc, 0);
+  std::vector<uint32_t> cell_lo(nc, 0xffffffffu), cell_hi(nc, 0);
   for (uint32_t k = 0; k < nc && ok; ++k)
     {
       const uint32_t *row = d->dof_indices + (uint64_t)k * ndof;
+      uint32_t        lo = 0xffffffffu, hi = 0;
       for (uint32_t j = 0; j < ndof; ++j)
         {
           const uint32_t iv = row[j];
@@ -521,6 +594,13 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
               has_constrained[k] = 1;
               is_boundary[k] |= row_ghost[r];
               has_weighted[k] |= row_weighted[r];
+              lo = std::min(lo, d->row_dof[r]);
+              hi = std::max(hi, d->row_dof[r]);
+              for (uint32_t e = d->row_ptr[r]; e < d->row_ptr[r + 1]; ++e)
+                {
+                  lo = std::min(lo, d->entry_col[e]);
+                  hi = std::max(hi, d->entry_col[e]);
+                }
             }
           else
             {
@@ -532,8 +612,12 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
                 }
               if (iv >= d->n_owned)
                 is_boundary[k] = 1;
+              lo = std::min(lo, iv);
+              hi = std::max(hi, iv);
             }
         }
+      cell_lo[k] = lo;
+      cell_hi[k] = hi;
     }
   if (!ok)
     {
@@ -559,6 +643,14 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
   while (perm.size() < op->ncp)
     perm.push_back(perm.back());
   auto slot_is_real = [&](uint64_t i) { return i < op->n_interior || (i >= op->n_int_pad && i < op->n_slots); };
+  op->slot_lo.assign((op->n_slots + 31) / 32, 0xffffffffu);
+  op->slot_hi.assign((op->n_slots + 31) / 32, 0);
+  for (uint32_t i = 0; i < op->n_slots; ++i)
+    if (slot_is_real(i))
+      {
+        op->slot_lo[i >> 5] = std::min(op->slot_lo[i >> 5], cell_lo[perm[i]]);
+        op->slot_hi[i >> 5] = std::max(op->slot_hi[i >> 5], cell_hi[perm[i]]);
+      }
 
   ok = ok && upload(op->perm, perm.data(), perm.size() * 4);
   {
@@ -596,7 +688,10 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
       ok = ok && upload(op->eval, ne ? d->entry_val : &zd, (ne ? ne : 1) * 8);
     else
       ok = ok && upload_converted<float>(op->eval, ne ? d->entry_val : &zd, ne ? ne : 1);
-    ok = ok && upload(op->cidx, d->n_constrained_indices ? d->constrained_indices : zero2,
+    // sorted: glsb_vmult_host applies the identity on constrained rows range by range
+    op->cidx_sorted.assign(d->constrained_indices, d->constrained_indices + d->n_constrained_indices);
+    std::sort(op->cidx_sorted.begin(), op->cidx_sorted.end());
+    ok = ok && upload(op->cidx, d->n_constrained_indices ? op->cidx_sorted.data() : zero2,
                       (size_t)(d->n_constrained_indices ? d->n_constrained_indices : 1) * 4);
     ok = ok && upload(op->export_idx, d->n_export ? d->export_indices : zero2,
                       (size_t)(d->n_export ? d->n_export : 1) * 4);
@@ -794,6 +889,18 @@ void glsb_destroy(glsb_op *op)
   if (op)
     {
       cudaSetDevice(op->device);
+      for (cudaEvent_t e : op->hp.e_in)
+        cudaEventDestroy(e);
+      for (cudaEvent_t e : op->hp.e_cells)
+        cudaEventDestroy(e);
+      if (op->hp.e_start)
+        cudaEventDestroy(op->hp.e_start);
+      if (op->hp.e_done)
+        cudaEventDestroy(op->hp.e_done);
+      if (op->hp.s_in)
+        cudaStreamDestroy(op->hp.s_in);
+      if (op->hp.s_out)
+        cudaStreamDestroy(op->hp.s_out);
       delete op;
     }
 }
@@ -891,6 +998,219 @@ int glsb_vmult(glsb_op *op, void *dst, const void *src, double weight, void *str
     rc = glsb_vmult_finish(op, dst, src, stream);
   return rc;
 }
+
+// vmult with HOST vectors.  The cells are cut into chunks (internal order); chunk c needs src[0, in_end[c]), so
+// the upload of src and the cell kernels are pipelined on two streams.  The download of dst is pipelined too:
+//   * speculative mode (dst_host is page-locked and device-accessible): dst[in_end[c-1], in_end[c]) is sent as
+//     soon as chunk c is done; the few entries of that range that a LATER chunk still adds to (chunk-surface
+//     nodes, found once on the device: k_last_touch / k_late_flags) are re-sent at the end by a kernel that
+//     stores straight into the host vector.  Works for any numbering, e.g. deal.II's first-touch numbering along
+//     the Morton curve, where low-numbered surface nodes are touched by cells far down the cell order;
+//   * conservative mode (pageable dst_host): dst[0, out_end[c]) is sent once no later chunk touches it.
+// PCIe is full duplex, so the total is ~ max(upload, download) instead of upload + kernels + download.
+static int host_pipe_setup(glsb_op *op)
+{
+  glsb_op::HostPipe &hp = op->hp;
+  if (hp.ready)
+    return 0;
+  const uint64_t n_local = op->n_owned + op->n_ghost;
+  const uint32_t nb      = (op->n_slots + 31) / 32;
+  const char    *env     = getenv("GLSB_HOST_CHUNKS");
+  uint32_t       nch     = env ? (uint32_t)atoi(env) : 16;
+  if (nch < 1)
+    nch = 1;
+  if (nch > 64)
+    nch = 64;
+  if (nb < 8 * nch)
+    nch = 1;
+  hp.cell_begin.resize(nch + 1);
+  for (uint32_t c = 0; c <= nch; ++c)
+    hp.cell_begin[c] = (uint32_t)((uint64_t)nb * c / nch) * 32;
+  hp.cell_begin[nch] = op->n_slots;
+  std::vector<uint64_t> lo(nch, n_local), hi(nch, 0);
+  std::vector<uint8_t>  chunk_of_batch(nb, 0);
+  for (uint32_t c = 0; c < nch; ++c)
+    for (uint32_t b = hp.cell_begin[c] / 32; b < (hp.cell_begin[c + 1] + 31) / 32 && b < nb; ++b)
+      {
+        chunk_of_batch[b] = (uint8_t)c;
+        if (op->slot_lo[b] != 0xffffffffu)
+          {
+            lo[c] = std::min<uint64_t>(lo[c], op->slot_lo[b]);
+            hi[c] = std::max<uint64_t>(hi[c], (uint64_t)op->slot_hi[b] + 1);
+          }
+      }
+  hp.in_end.resize(nch);
+  hp.out_end.resize(nch);
+  hp.cidx_end.resize(nch);
+  hp.cidx_end_spec.resize(nch);
+  uint64_t run = 0;
+  for (uint32_t c = 0; c < nch; ++c)
+    {
+      run          = std::max(run, hi[c]);
+      hp.in_end[c] = (c + 1 == nch) ? n_local : run;
+    }
+  run = n_local;
+  for (uint32_t c = nch; c-- > 0;)
+    {
+      hp.out_end[c] = (c + 1 == nch) ? n_local : run; // nothing of chunks > c starts below `run`
+      run           = std::min(run, lo[c]);
+    }
+  auto below = [&](uint64_t x) {
+    return (uint32_t)(std::lower_bound(op->cidx_sorted.begin(), op->cidx_sorted.end(),
+                                       (uint32_t)std::min<uint64_t>(x, 0xffffffffull)) -
+                      op->cidx_sorted.begin());
+  };
+  for (uint32_t c = 0; c < nch; ++c)
+    {
+      hp.cidx_end[c]      = below(hp.out_end[c]);
+      hp.cidx_end_spec[c] = below(hp.in_end[c]);
+    }
+  hp.cidx_end[nch - 1] = hp.cidx_end_spec[nch - 1] = (uint32_t)op->cidx_sorted.size();
+  if (!hp.src.alloc(n_local * op->tsize) || !hp.dst.alloc(n_local * op->tsize))
+    return 1;
+  // entries that change after their speculative download
+  {
+    DevBuf last, cob, d_in_end;
+    if (!last.alloc(n_local * 4) || !hp.late_flag.alloc(n_local) || !upload(cob, chunk_of_batch.data(), nb) ||
+        !upload(d_in_end, hp.in_end.data(), nch * 8))
+      return 1;
+    cudaMemset(last.p, 0, n_local * 4);
+    const uint32_t ndof = (uint32_t)(op->C * op->n_loc);
+    const uint64_t tot  = (uint64_t)ndof * op->n_slots;
+    k_last_touch<<<(unsigned)((tot + 255) / 256), 256>>>(op->idx.as<uint32_t>(), cob.as<uint8_t>(),
+                                                         op->row_dof.as<uint32_t>(), op->row_ptr.as<uint32_t>(),
+                                                         op->ecol.as<uint32_t>(), last.as<uint32_t>(), op->n_slots,
+                                                         op->n_interior, op->n_int_pad, ndof);
+    k_late_flags<<<(unsigned)((n_local + 255) / 256), 256>>>(last.as<uint32_t>(), d_in_end.as<uint64_t>(), nch,
+                                                             hp.late_flag.as<uint8_t>(), n_local);
+    if (cudaDeviceSynchronize() != cudaSuccess)
+      return 1;
+  }
+  if (cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking) != cudaSuccess)
+    return 1;
+  hp.e_in.resize(nch);
+  hp.e_cells.resize(nch);
+  for (uint32_t c = 0; c < nch; ++c)
+    if (cudaEventCreateWithFlags(&hp.e_in[c], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&hp.e_cells[c], cudaEventDisableTiming) != cudaSuccess)
+      return 1;
+  if (cudaEventCreateWithFlags(&hp.e_start, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&hp.e_done, cudaEventDisableTiming) != cudaSuccess)
+    return 1;
+  hp.ready = true;
+  return 0;
+}
+
+int glsb_vmult_host(glsb_op *op, void *dst_host, const void *src_host, double weight, void *stream)
+{
+  if (!op || !dst_host || !src_host)
+    return fail(op, "glsb_vmult_host: null argument");
+  if (op->n_ghost != 0)
+    return fail(op, "glsb_vmult_host: operators with ghost entries exchange on the device; use glsb_vmult");
+  if (!op->lin_valid)
+    return fail(op, "glsb_vmult: set_linearization_point has not been called");
+  if (op->increment_form && op->ctd && !op->prev_valid)
+    return fail(op, "glsb_vmult: set_previous_solution has not been called");
+  if (host_pipe_setup(op))
+    return cuda_fail(op, "glsb_vmult_host: setup");
+  glsb_op::HostPipe &hp     = op->hp;
+  cudaStream_t       s      = (cudaStream_t)stream;
+  const uint32_t     nch    = (uint32_t)hp.in_end.size();
+  const size_t       ts     = op->tsize;
+  const uint64_t     n      = op->n_owned + op->n_ghost;
+  const int          branch = op->increment_form ? BR_NEWTON : BR_FIXED_POINT;
+  char              *d_src = hp.src.as<char>(), *d_dst = hp.dst.as<char>();
+  // speculative download needs a device-visible (page-locked, mapped) destination
+  void *dst_mapped = nullptr;
+  {
+    cudaPointerAttributes at;
+    static const bool     off = getenv("GLSB_HOST_NO_SPEC") != nullptr;
+    if (!off && nch > 1 && cudaPointerGetAttributes(&at, dst_host) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+        at.devicePointer != nullptr)
+      dst_mapped = at.devicePointer;
+    cudaGetLastError();
+  }
+  const std::vector<uint64_t> &out_end  = dst_mapped ? hp.in_end : hp.out_end;
+  const std::vector<uint32_t> &cidx_end = dst_mapped ? hp.cidx_end_spec : hp.cidx_end;
+  // everything below is ordered after the work already enqueued on the caller's stream
+  cudaEventRecord(hp.e_start, s);
+  cudaStreamWaitEvent(hp.s_in, hp.e_start, 0);
+  cudaStreamWaitEvent(hp.s_out, hp.e_start, 0);
+  if (cudaMemsetAsync(d_dst, 0, (size_t)n * ts, s) != cudaSuccess)
+    return cuda_fail(op, "glsb_vmult_host: memset");
+  uint64_t in_done = 0, out_done = 0;
+  uint32_t c_done = 0;
+  for (uint32_t c = 0; c < nch; ++c)
+    {
+      if (hp.in_end[c] > in_done)
+        {
+          if (cudaMemcpyAsync(d_src + in_done * ts, (const char *)src_host + in_done * ts, (hp.in_end[c] - in_done) * ts,
+                              cudaMemcpyHostToDevice, hp.s_in) != cudaSuccess)
+            return cuda_fail(op, "glsb_vmult_host: upload");
+          in_done = hp.in_end[c];
+        }
+      cudaEventRecord(hp.e_in[c], hp.s_in);
+      cudaStreamWaitEvent(s, hp.e_in[c], 0);
+      int rc = 0;
+      {
+        // cells [cell_begin[c], cell_begin[c + 1]) of the internal order (the padding hole is skipped)
+        op->range_override[0] = hp.cell_begin[c];
+        op->range_override[1] = hp.cell_begin[c + 1];
+#define CALL(D, T) do_cells<D, T>(op, d_dst, d_src, weight, GLSB_CELLS_ALL, branch, s)
+        GLSB_DISPATCH(op, CALL);
+#undef CALL
+        op->range_override[0] = op->range_override[1] = 0;
+      }
+      if (rc)
+        return cuda_fail(op, "glsb_vmult_host: launch");
+      // identity on the constrained rows inside the range sent after this chunk (operator_ns.cc:719-721)
+      if (cidx_end[c] > c_done)
+        {
+          const uint32_t m = cidx_end[c] - c_done;
+          if (op->number_type == GLSB_F64)
+            k_copy_indexed<double><<<(m + 255) / 256, 256, 0, s>>>((double *)d_dst, (const double *)d_src,
+                                                                 op->cidx.as<uint32_t>() + c_done, m);
+          else
+            k_copy_indexed<float><<<(m + 255) / 256, 256, 0, s>>>((float *)d_dst, (const float *)d_src,
+                                                                op->cidx.as<uint32_t>() + c_done, m);
+          op->launches++;
+          c_done = cidx_end[c];
+        }
+      cudaEventRecord(hp.e_cells[c], s);
+      if (out_end[c] > out_done)
+        {
+          cudaStreamWaitEvent(hp.s_out, hp.e_cells[c], 0);
+          if (cudaMemcpyAsync((char *)dst_host + out_done * ts, d_dst + out_done * ts, (out_end[c] - out_done) * ts,
+                              cudaMemcpyDeviceToHost, hp.s_out) != cudaSuccess)
+            return cuda_fail(op, "glsb_vmult_host: download");
+          out_done = out_end[c];
+        }
+    }
+  cudaEventRecord(hp.e_done, hp.s_out);
+  cudaStreamWaitEvent(s, hp.e_done, 0);
+  if (dst_mapped)
+    {
+      // after the last range has landed: re-send what later chunks changed
+      if (op->number_type == GLSB_F64)
+        k_flush_flagged<double><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((double *)dst_mapped, (const double *)d_dst,
+                                                                          hp.late_flag.as<uint8_t>(), n);
+      else
+        k_flush_flagged<float><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((float *)dst_mapped, (const float *)d_dst,
+                                                                         hp.late_flag.as<uint8_t>(), n);
+      op->launches++;
+    }
+  if (cudaGetLastError() != cudaSuccess)
+    return cuda_fail(op, "glsb_vmult_host");
+  return 0;
+}
+
+/* page-lock a host vector so that glsb_vmult_host's copies are asynchronous DMA transfers */
+int glsb_host_register(void *ptr, uint64_t bytes)
+{
+  return cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault) == cudaSuccess ? 0 : 1;
+}
+int glsb_host_unregister(void *ptr) { return cudaHostUnregister(ptr) == cudaSuccess ? 0 : 1; }
 
 int glsb_evaluate_residual_cells(glsb_op *op, void *dst, const void *src, double weight, int which, void *stream)
 {

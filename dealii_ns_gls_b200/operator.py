@@ -335,7 +335,17 @@ class NavierStokesOperator:
 
     # ---- end-to-end entry with HOST vectors (what a host-vector deal.II caller pays) ----
     def vmult_host(self, dst_host: torch.Tensor, src_host: torch.Tensor):
-        """vmult on pinned host tensors: H2D copy, device vmult, D2H copy."""
+        """vmult on host tensors (the reference's VectorType lives in host memory, config.h:9-10): forwards
+        to glsb_vmult_host, which pipelines upload, cell kernels and download in chunks.  Pinned tensors
+        make the copies asynchronous.  With a ghost exchange attached the vectors go to the device whole."""
+        for t, name in ((dst_host, "dst_host"), (src_host, "src_host")):
+            if t.is_cuda or t.dtype != self.dtype or not t.is_contiguous() or t.numel() != self.n_local:
+                raise ValueError(f"{name}: expected a contiguous host {self.dtype} vector of length {self.n_local}")
+        if self.exchange is None:
+            w = self.time_integrator_data.get_primary_weight()
+            self._chk(self._lib.glsb_vmult_host(self._op, C.c_void_p(dst_host.data_ptr()),
+                                                C.c_void_p(src_host.data_ptr()), w, self._stream()), "vmult_host")
+            return
         key = "vh"
         if key not in self._pinned:
             self._pinned[key] = (self.initialize_dof_vector(), self.initialize_dof_vector())

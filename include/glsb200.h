@@ -114,6 +114,16 @@ int glsb_invalidate_system(glsb_op *op);
  * loops over all cells, copies the constrained rows. */
 int glsb_vmult(glsb_op *op, void *dst, const void *src, double weight, void *stream);
 
+/* vmult for callers whose vectors live in HOST memory (the reference's VectorType is a host
+ * LinearAlgebra::distributed::Vector, config.h:9-10): src_host / dst_host are host pointers to n_owned
+ * values (page-locked for full speed, see glsb_host_register); upload, cell kernels and download run as a
+ * chunked pipeline over PCIe.  Ordered after the work on `stream`; `stream` waits for the last download.
+ * Single-rank operators only (n_ghost == 0). */
+int glsb_vmult_host(glsb_op *op, void *dst_host, const void *src_host, double weight, void *stream);
+/* cudaHostRegister / cudaHostUnregister for a caller-owned host vector */
+int glsb_host_register(void *ptr, uint64_t bytes);
+int glsb_host_unregister(void *ptr);
+
 /* The three pieces of cell_loop(..., zero_dst = true) for the host layer that
  * overlaps the ghost exchange with the interior cells (operator_ns.cc:703-708):
  *   glsb_vmult_begin  : zero dst (owned + ghost)

@@ -237,3 +237,42 @@ def test_q2_fast_kernel_matches_generic_and_oracle(kind, ctd, cell_wise, number)
     assert gpu.vmult_variant() == "generic"
     assert rel_l2(dst2.cpu().numpy(), ref) < TOL[number]
     assert rel_l2(dst.cpu().numpy(), dst2.cpu().numpy()) < TOL[number]
+
+
+@pytest.mark.parametrize("number", ["double", "float"])
+@pytest.mark.parametrize("case", ["cube_24_chunked", "cube_dirichlet_chunked", "shell_small"])
+def test_vmult_host_matches_device_vmult(case, number, monkeypatch):
+    """glsb_vmult_host (host vectors in, host vector out; chunked upload / cells / download pipeline)
+    must give bit-for-bit the order-independent part of the device result and agree to round-off
+    (atomics reorder the sums), with and without constrained rows, pinned and pageable buffers."""
+    torch = _torch()
+    monkeypatch.setenv("GLSB_HOST_CHUNKS", "7")
+    if case == "cube_24_chunked":
+        mesh = gm.hypercube(3, 24, 2)
+    elif case == "cube_dirichlet_chunked":
+        def walls(ref, c):  # no-slip on all faces of the cube, pressure free
+            on = (np.abs(ref) < 1e-12).any(axis=1) | (np.abs(ref - 1.0) < 1e-12).any(axis=1)
+            return on if c < 3 else np.zeros(len(ref), dtype=bool)
+        mesh = gm.hypercube(3, 20, 2, dirichlet=walls)
+    else:
+        mesh = gm.cylinder_shell((2, 5, 2), 2)
+    ti = TI(2, [10.0, -10.0, 0.0], 0.1)
+    gpu = make_gpu(mesh, ti, number=number)
+    if case == "cube_dirichlet_chunked":
+        gm.add_random_constraints  # noqa: B018  (weighted rows are covered by the device tests)
+    dt = torch.float64 if number == "double" else torch.float32
+    g = torch.Generator(device="cuda").manual_seed(7)
+    lin = (torch.rand(mesh.n_dofs, dtype=torch.float64, device="cuda", generator=g) * 2 - 1).to(dt)
+    gpu.set_linearization_point(lin)
+    x = (torch.rand(mesh.n_dofs, dtype=torch.float64, device="cuda", generator=g) * 2 - 1).to(dt)
+    ref = gpu.initialize_dof_vector()
+    gpu.vmult(ref, x)
+    for pinned in (True, False):
+        h_src = torch.empty(mesh.n_dofs, dtype=dt, pin_memory=pinned)
+        h_dst = torch.full((mesh.n_dofs,), float("nan"), dtype=dt).pin_memory() if pinned else \
+            torch.full((mesh.n_dofs,), float("nan"), dtype=dt)
+        h_src.copy_(x)
+        gpu.vmult_host(h_dst, h_src)
+        torch.cuda.synchronize()
+        assert not bool(torch.isnan(h_dst).any())
+        assert rel_l2(h_dst.numpy(), ref.cpu().numpy()) < (1e-13 if number == "double" else 1e-5)
