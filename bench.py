@@ -168,12 +168,26 @@ def run_reference(args):
 
 
 def workload_config(args, n_gpus):
+    if args.workload == "C":
+        nr, nt, nz = shell_shape(args)
+        return {"workload": f"config C (input_turek_3D_Re100.json flags): 3D O-grid around a cylinder, Q{args.degree}, "
+                            f"{nr}x{nt}x{nz} curved cells, Q{args.degree} mapping (general geometry), no-slip rows, "
+                            "Newton form, q-point-wise delta, BDF2 with time-derivative terms, random U/src/history "
+                            f"seed 1234, Number = {args.number}",
+                "cells_per_gpu": nr * nt * nz, "degree": args.degree, "dim": 3, "parallelism": "single GPU",
+                "l2_policy": "inputs larger than L2 (tables + vectors >> 126 MB), no flush"}
     return {"workload": f"performance.cc: 3D hypercube, Q{args.degree}, {args.cells}^3 cells per GPU, "
                         "Cartesian, no constraints, Newton form, cell-wise delta, BDF2 weight 10, "
-                        "random U/src seed 1234",
+                        "random U/src seed 1234" + ("" if args.number == "double" else ", Number = float"),
             "cells_per_gpu": args.cells ** 3, "degree": args.degree, "dim": 3,
             "parallelism": f"domain decomposition, {n_gpus} z-slab(s)",
             "l2_policy": "inputs larger than L2 (tables + vectors >> 126 MB), no flush"}
+
+
+def shell_shape(args):
+    """O-grid of about args.cells^3 cells: radial x circumferential x axial."""
+    c = args.cells
+    return max(2, c // 2), 4 * c, max(2, c // 2)
 
 
 # --------------------------------------------------------------------------------------
@@ -201,26 +215,40 @@ def run_gpu(args):
         from dealii_ns_gls_b200.distributed import GhostExchange
         mesh = gm.hypercube_slab(args.cells, args.degree, n_ranks=world, rank=rank)
         exchange = GhostExchange(mesh.partition, dev)
+    elif args.workload == "C":
+        mesh = gm.cylinder_shell(shell_shape(args), args.degree)
     else:
         mesh = gm.hypercube(3, args.cells, args.degree)
 
+    tdt = torch.float64 if args.number == "double" else torch.float32
     ti = TimeIntegratorDataBDF(2)
     ti.update_dt(DT)  # performance.cc:44-46: weights (10, -10, 0)
-    op = NavierStokesOperator(mesh, None, NU, C1, C2, ti, False, True, True, number="double", device=dev,
-                              exchange=exchange)
+    if args.workload == "C":
+        ti.update_dt(DT)  # second step: full BDF2 weights (15, -20, 5)
+        op = NavierStokesOperator(mesh, None, 0.001, C1, C2, ti, True, True, False, number=args.number, device=dev,
+                                  exchange=exchange)
+    else:
+        op = NavierStokesOperator(mesh, None, NU, C1, C2, ti, False, True, True, number=args.number, device=dev,
+                                  exchange=exchange)
     n_local, n_owned = mesh.n_dofs, mesh.n_owned
     n_global = mesh.n_global_dofs
     n_cells = mesh.n_cells
     del mesh
 
     g = torch.Generator(device=dev).manual_seed(SEED + rank)
-    hist = [torch.zeros(n_local, dtype=torch.float64, device=dev) for _ in range(3)]
-    op.set_previous_solution(hist)  # performance.cc:66-69
+    def rand_vec():
+        return (torch.rand(n_local, dtype=torch.float64, device=dev, generator=g) * 2 - 1).to(tdt)
+
+    if args.workload == "C":
+        hist = [rand_vec() for _ in range(3)]
+    else:
+        hist = [torch.zeros(n_local, dtype=tdt, device=dev) for _ in range(3)]  # performance.cc:66-69
+    op.set_previous_solution(hist)
     del hist
-    lin = torch.rand(n_local, dtype=torch.float64, device=dev, generator=g) * 2 - 1
+    lin = rand_vec()
     op.set_linearization_point(lin)
     del lin
-    src = torch.rand(n_local, dtype=torch.float64, device=dev, generator=g) * 2 - 1
+    src = rand_vec()
     if n_local > n_owned:
         src[n_owned:] = 0
     dst = op.initialize_dof_vector()
@@ -253,8 +281,8 @@ def run_gpu(args):
     checksum = float(dst[:n_owned].double().abs().sum())
 
     # ---- end to end: host vectors in, host vector out, every step ----------------------
-    h_src = torch.empty(n_local, dtype=torch.float64, pin_memory=True)
-    h_dst = torch.empty(n_local, dtype=torch.float64, pin_memory=True)
+    h_src = torch.empty(n_local, dtype=tdt, pin_memory=True)
+    h_dst = torch.empty(n_local, dtype=tdt, pin_memory=True)
     h_src.copy_(src)
     e2e_steps = max(2, min(args.steps, 10))
     for _ in range(2):
@@ -288,7 +316,11 @@ def run_gpu(args):
         peaks_src = "measured"
     except Exception:
         peaks = {"hbm_gbs": 6650.0}
-    bpc = algorithmic_bytes_per_cell(3, args.degree, 8)
+    nb = 8 if args.number == "double" else 4
+    if args.workload == "C":
+        bpc = algorithmic_bytes_per_cell(3, args.degree, nb, ctd=True, q_wise=True, general=True)
+    else:
+        bpc = algorithmic_bytes_per_cell(3, args.degree, nb)
     achieved = n_cells * bpc / (k_ms * 1e-3) / 1e9
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
@@ -304,11 +336,11 @@ def run_gpu(args):
     line = {
         "metric": "GLS NS operator vmult throughput", "value": value, "unit": "GDoF/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": t_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.number == "double" else "f32", "data": "synthetic",
         "config": dict(workload_config(args, world), n_dofs_global=n_global, kernel_variant=op.vmult_variant(),
                        checksum_abs_sum=checksum),
         "e2e": {"value": n_global * e2e_steps / (e2e_ms * 1e-3) / 1e9, "unit": "GDoF/s",
-                "h2d_bytes_per_step": n_local * 8, "d2h_bytes_per_step": n_local * 8, "steps": e2e_steps},
+                "h2d_bytes_per_step": n_local * nb, "d2h_bytes_per_step": n_local * nb, "steps": e2e_steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                      "frac": achieved / peaks.get("hbm_gbs"), "traffic": traffic,
@@ -316,7 +348,7 @@ def run_gpu(args):
                      "algorithmic_bytes_per_cell": bpc, "cells_per_launch": n_cells},
         "clocks": sampler.summary(),
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "P":
         r = cpu_vmult_gdofs(args.cpu_cells, args.degree, 10, 2)
         line["cpu_baseline"] = {"value": r["value"], "unit": "GDoF/s", "cores": r["cores"], "kind": "port",
                                 "sample": r["sample"]}
@@ -354,6 +386,10 @@ def main():
     ap.add_argument("--degree", type=int, default=2)
     ap.add_argument("--cpu-cells", type=int, default=64, help="cells per direction of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="P", choices=["P", "C"],
+                    help="P = performance.cc hypercube (the headline); C = curved O-grid with the Turek-3D flags")
+    ap.add_argument("--number", default="double", choices=["double", "float"],
+                    help="double = Krylov operator (headline); float = multigrid level operator (config.h:7)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

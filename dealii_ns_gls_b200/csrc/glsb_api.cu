@@ -794,9 +794,14 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
     op->FT = f;
     if (op->dim == 3 && op->n == 3)
       {
-        // one block per ring stage of the Q2 kernel: a (qz, qy) row of 3 points, or a whole layer
-        const char *rows = getenv("GLSB_Q2_ROWS");
-        op->QG           = (rows && atoi(rows) == 1) ? 3 : 9;
+        // one block per ring stage of the Q2 kernel: a whole quadrature layer (9 points) if two CTAs with a
+        // 2-deep ring of such stages fit into an SM's shared memory, else one (qz, qy) row of 3 points
+        // (measured, config C in FP64: 73 % instead of 55 % of the HBM roofline with row stages)
+        const char  *rows  = getenv("GLSB_Q2_ROWS");
+        const size_t layer = (size_t)op->F_stage * 9 * 32 * op->tsize;
+        const size_t fixed = (size_t)4 * 2 * 180 * op->tsize + 2 * 109 * 32 * 4 + 256;
+        const bool   fits  = 2 * (2 * layer + fixed + 1024) <= 228 * 1024;
+        op->QG             = rows ? (atoi(rows) == 1 ? 3 : 9) : (fits ? 9 : 3);
         op->NL           = 27 / op->QG;
       }
     else

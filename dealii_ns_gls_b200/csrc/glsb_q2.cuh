@@ -30,6 +30,9 @@ namespace glsb
 {
 namespace q2
 {
+#ifndef GLSB_Q2_F32_CTAS
+#define GLSB_Q2_F32_CTAS 3 // resident CTAs per SM the float instantiation is compiled for
+#endif
 constexpr int CELLS = 32; // cells per CTA batch
 constexpr int TPB   = 128;
 
@@ -126,7 +129,7 @@ __device__ __forceinline__ void issue_stage(const KParams<T> &p, int F, T *tab, 
 }
 
 template <typename T, bool GENERAL, bool CTD, bool CELLWISE, int ROWS>
-__global__ void __launch_bounds__(TPB, 2)
+__global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : 2))
   k_vmult_q2_newton(const KParams<T> p, const Shape<T, 3> sh, const int F, const int nst)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -490,12 +493,13 @@ size_t smem_bytes(int F, int nst)
          2 * IDX_ELEMS * 4 + (MAX_NST + 2) * (sizeof(uint64_t) + sizeof(uint32_t));
 }
 
-// ring depth: as deep as two CTAs per SM allow (at most MAX_NST), at least 2
+// ring depth: 2 stages of a whole layer; with row stages as deep as the target occupancy allows (<= 4)
 template <typename T, int ROWS>
 int ring_depth(int F)
 {
-  int nst = 2;
-  while (nst < MAX_NST && 2 * (smem_bytes<T, ROWS>(F, nst + 1) + 1024) <= 228 * 1024)
+  const int ctas = sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : 2;
+  int       nst  = 2;
+  while (ROWS == 1 && nst < 4 && ctas * (smem_bytes<T, ROWS>(F, nst + 1) + 1024) <= 228 * 1024)
     ++nst;
   return nst;
 }
