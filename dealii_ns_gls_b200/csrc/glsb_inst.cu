@@ -1,5 +1,6 @@
 // One translation unit per (dim, Number): compile with -DGLSB_DIM=2|3 -DGLSB_REAL=double|float.
 #include "glsb_kernels.cuh"
+#include <cstdlib>
 #ifdef GLSB_WITH_Q2
 #include "glsb_q2.cuh"
 #endif
@@ -131,9 +132,20 @@ static int launch_diag_br(const KParams<T> &p, const ShapeHost &sh, const uint8_
   const auto   S  = to_shape<T, n>(sh);
   if (p.cell_end > p.cell_begin)
     {
-      if (ensure_smem(k_diag_generic<dim, n, T, BR>, sm))
-        return 1;
-      k_diag_generic<dim, n, T, BR><<<GLSB_GRID(G, p), G::THREADS, sm, s>>>(p, S, skip);
+      // sum-factorised diagonal; GLSB_DIAG_UNIT_VECTORS=1 selects the unit-vector kernel (cross-check)
+      static const bool unit = getenv("GLSB_DIAG_UNIT_VECTORS") != nullptr;
+      if (unit)
+        {
+          if (ensure_smem(k_diag_generic<dim, n, T, BR>, sm))
+            return 1;
+          k_diag_generic<dim, n, T, BR><<<GLSB_GRID(G, p), G::THREADS, sm, s>>>(p, S, skip);
+        }
+      else
+        {
+          if (ensure_smem(k_diag_sumfac<dim, n, T, BR>, sm))
+            return 1;
+          k_diag_sumfac<dim, n, T, BR><<<GLSB_GRID(G, p), G::THREADS, sm, s>>>(p, S, skip);
+        }
     }
   if (dc.n_list > 0)
     {

@@ -295,19 +295,64 @@ __device__ __forceinline__ void symm_add(T (&gout)[dim + 1][dim], const T (&B)[d
       }
 }
 
+// the table entries of one quadrature point that a cell application reads (operator_ns.h:117-132);
+// loaded once, BEFORE the sum-factorisation sweeps, so that the global loads complete behind them
+// (and once per cell, not once per unit vector, in the diagonal kernels)
+template <int dim, typename T>
+struct QTables
+{
+  T d1, d2;
+  T U[dim], H[dim][dim], P[dim], O[dim], Gold[dim][dim], gold_p[dim];
+};
+
 template <int dim, typename T, int BR>
-__device__ __forceinline__ void qpoint_physics(const KParams<T> &p, const QPos<T> qp, uint32_t cell,
+__device__ __forceinline__ void load_tables(const KParams<T> &p, const QPos<T> qp, uint32_t cell, QTables<dim, T> &t)
+{
+#define GLSB_QF(f, row) p.Q[qoff(qp, (f), (row))]
+  t.d1 = p.cell_wise ? p.d1c[cell] : GLSB_QF(p.fd1q, 0);
+  t.d2 = p.cell_wise ? p.d2c[cell] : GLSB_QF(p.fd2q, 0);
+#pragma unroll
+  for (int j = 0; j < dim; ++j)
+    t.U[j] = GLSB_QF(p.fU + j, j);
+  if (BR == BR_NEWTON)
+    {
+#pragma unroll
+      for (int c = 0; c < dim; ++c)
+        {
+          t.P[c] = GLSB_QF(p.fP + c, c);
+          t.O[c] = p.ctd ? GLSB_QF(p.fO + c, c) : T(0);
+#pragma unroll
+          for (int j = 0; j < dim; ++j)
+            t.H[c][j] = GLSB_QF(p.fH + c * dim + j, c);
+        }
+    }
+  else
+    {
+      constexpr bool res = (BR == BR_RESIDUAL);
+#pragma unroll
+      for (int c = 0; c < dim; ++c)
+        {
+          t.O[c]      = (res && p.has_o) ? GLSB_QF(p.fO + c, c) : T(0);
+          t.gold_p[c] = (res && p.theta_ne_1) ? GLSB_QF(p.fgoldp + c, 0) : T(0);
+#pragma unroll
+          for (int j = 0; j < dim; ++j)
+            t.Gold[c][j] = (res && p.theta_ne_1) ? GLSB_QF(p.fGold + c * dim + j, 0) : T(0);
+        }
+    }
+#undef GLSB_QF
+}
+
+template <int dim, typename T, int BR>
+__device__ __forceinline__ void qpoint_physics(const KParams<T> &p, const QTables<dim, T> &tb,
                                                const T (&val)[dim + 1], const T (&g)[dim + 1][dim],
                                                T (&vout)[dim + 1], T (&gout)[dim + 1][dim])
 {
-#define GLSB_QF(f, row) p.Q[qoff(qp, (f), (row))]
-  const T d1 = p.cell_wise ? p.d1c[cell] : GLSB_QF(p.fd1q, 0);
-  const T d2 = p.cell_wise ? p.d2c[cell] : GLSB_QF(p.fd2q, 0);
+  const T d1 = tb.d1, d2 = tb.d2;
   const T w  = p.weight;
   T       U[dim];
 #pragma unroll
   for (int j = 0; j < dim; ++j)
-    U[j] = GLSB_QF(p.fU + j, j);
+    U[j] = tb.U[j];
 #pragma unroll
   for (int c = 0; c <= dim; ++c)
 #pragma unroll
@@ -320,10 +365,10 @@ __device__ __forceinline__ void qpoint_physics(const KParams<T> &p, const QPos<T
 #pragma unroll
       for (int c = 0; c < dim; ++c)
         {
-          P[c] = GLSB_QF(p.fP + c, c);
+          P[c] = tb.P[c];
 #pragma unroll
           for (int j = 0; j < dim; ++j)
-            H[c][j] = GLSB_QF(p.fH + c * dim + j, c);
+            H[c][j] = tb.H[c][j];
         }
       T Gm[dim][dim];
       T div = 0;
@@ -354,7 +399,7 @@ __device__ __forceinline__ void qpoint_physics(const KParams<T> &p, const QPos<T
           if (p.ctd)
             {
               a = td + a;
-              b = (U[c] * w + GLSB_QF(p.fO + c, c)) + b;
+              b = (U[c] * w + tb.O[c]) + b;
             }
           r0[c] = d1 * a;
           r1[c] = d1 * b;
@@ -393,17 +438,17 @@ __device__ __forceinline__ void qpoint_physics(const KParams<T> &p, const QPos<T
       if (res && p.has_o)
 #pragma unroll
         for (int c = 0; c < dim; ++c)
-          td[c] += GLSB_QF(p.fO + c, c);
+          td[c] += tb.O[c];
       if (res && p.theta_ne_1)
         {
           const T omt = T(1) - th;
 #pragma unroll
           for (int c = 0; c < dim; ++c)
             {
-              pbar[c] += omt * GLSB_QF(p.fgoldp + c, 0);
+              pbar[c] += omt * tb.gold_p[c];
 #pragma unroll
               for (int j = 0; j < dim; ++j)
-                B[c][j] += omt * GLSB_QF(p.fGold + c * dim + j, 0);
+                B[c][j] += omt * tb.Gold[c][j];
             }
         }
       T divb = 0;
@@ -440,7 +485,6 @@ __device__ __forceinline__ void qpoint_physics(const KParams<T> &p, const QPos<T
         gout[d][d] += d2 * divb;
       vout[dim] = divb;
     }
-#undef GLSB_QF
 }
 
 // ---------------------------------------------------------------------------------------
@@ -453,17 +497,17 @@ constexpr size_t generic_smem_bytes()
   return sizeof(T) * ((size_t)(G::C + G::C * dim) * G::n_loc * G::CPB + 2 * n * n);
 }
 
-// full cell operator on the local vector in ctx.v (dof values in, tested result out)
+// full cell operator on the local vector in ctx.v (dof values in, tested result out); geo and tb are this
+// thread's quadrature-point geometry and table entries, loaded by the caller before the dof values
 template <int dim, int n, typename T, int BR>
-__device__ __forceinline__ void cell_apply(Ctx<dim, n, T> &ctx, const KParams<T> &p, const Shape<T, n> &sh, uint32_t cell)
+__device__ __forceinline__ void cell_apply(Ctx<dim, n, T> &ctx, const KParams<T> &p, const GeomQ<dim, n, T> &geo,
+                                           const QTables<dim, T> &tb)
 {
   constexpr int C = dim + 1;
   T             val[C], rg[C][dim], g[C][dim], vout[C], gout[C][dim], rgq[C][dim];
   ctx.evaluate(val, rg);
-  GeomQ<dim, n, T> geo;
-  geo.load(p, sh, cell, ctx.l, ctx.ii);
   geo.template to_physical<C>(rg, g);
-  qpoint_physics<dim, T, BR>(p, qpos(p, (uint32_t)ctx.l, cell), cell, val, g, vout, gout);
+  qpoint_physics<dim, T, BR>(p, tb, val, g, vout, gout);
   geo.template to_reference<C>(gout, rgq);
 #pragma unroll
   for (int c = 0; c < C; ++c)
@@ -484,13 +528,18 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_vmult_generic(const KP
   uint32_t       iv[G::C];
 #pragma unroll
   for (int c = 0; c < G::C; ++c)
-    {
-      iv[c] = p.idx[idx_at(p, c * G::n_loc + ctx.l, cell)];
-      ctx.v[ctx.at(c, ctx.l)] =
-        (BR == BR_RESIDUAL) ? p.src[plain_index(p, iv[c])] : gather_resolved(p, p.src, iv[c]);
-    }
+    iv[c] = p.idx[idx_at(p, c * G::n_loc + ctx.l, cell)];
+  // this point's geometry and table entries: issued now, consumed after the evaluate sweeps
+  GeomQ<dim, n, T> geo;
+  geo.load(p, sh, cell, ctx.l, ctx.ii);
+  QTables<dim, T> tb;
+  load_tables<dim, T, BR>(p, qpos(p, (uint32_t)ctx.l, cell), cell, tb);
+#pragma unroll
+  for (int c = 0; c < G::C; ++c)
+    ctx.v[ctx.at(c, ctx.l)] =
+      (BR == BR_RESIDUAL) ? p.src[plain_index(p, iv[c])] : gather_resolved(p, p.src, iv[c]);
   __syncthreads();
-  cell_apply<dim, n, T, BR>(ctx, p, sh, cell);
+  cell_apply<dim, n, T, BR>(ctx, p, geo, tb);
   if (active)
     {
 #pragma unroll
@@ -678,6 +727,10 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_diag_generic(const KPa
   const bool     active = cell_active(p, cell0);
   const uint32_t cell   = cell0 < p.cell_end ? cell0 : p.cell_end - 1;
   T              mine[C];
+  GeomQ<dim, n, T> geo;
+  geo.load(p, sh, cell, ctx.l, ctx.ii);
+  QTables<dim, T> tb;
+  load_tables<dim, T, BR>(p, qpos(p, (uint32_t)ctx.l, cell), cell, tb);
   for (int j = 0; j < C * G::n_loc; ++j)
     {
       __syncthreads();
@@ -685,7 +738,7 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_diag_generic(const KPa
       for (int c = 0; c < C; ++c)
         ctx.v[ctx.at(c, ctx.l)] = (c * G::n_loc + ctx.l == j) ? T(1) : T(0);
       __syncthreads();
-      cell_apply<dim, n, T, BR>(ctx, p, sh, cell);
+      cell_apply<dim, n, T, BR>(ctx, p, geo, tb);
 #pragma unroll
       for (int c = 0; c < C; ++c)
         if (c * G::n_loc + ctx.l == j)
@@ -699,6 +752,200 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_diag_generic(const KPa
       const uint32_t iv = p.idx[idx_at(p, c * G::n_loc + ctx.l, cell)];
       if (!(iv & GLSB_CONSTRAINED_BIT))
         atomic_add(p.dst + iv, mine[c]);
+    }
+}
+
+// diag(A_cell) without unit vectors.  For a trial/test function pair of the SAME component c the
+// quadrature-point operator (operator_ns.cc:1067-1182 resp. :955-1066) restricted to that component is
+//   value_out = alpha v + beta . g,     grad_out_j = gamma_j v + sum_m K_jm g_m       (v = phi, g = grad phi)
+// Newton branch, velocity c:  alpha = w + H_cc, beta = U, gamma_j = U_j delta_1 (t w + H_cc) + [j = c] r1_c,
+//                             K = nu I + (nu + delta_2) e_c e_c^T + delta_1 U U^T,
+//                             r1_c = delta_1 (t (w U_c + o_c) + P_c + H_c. U)
+// fixed-point, velocity c:    alpha = w, beta = theta U, gamma_j = U_j delta_1 t w,
+//                             K = nu theta I + theta (nu + delta_2) e_c e_c^T + delta_1 theta U U^T
+// pressure (both):            alpha = beta = gamma = 0, K = delta_1 I
+// so that  A_ii = sum_q JxW [ alpha phi_i^2 + (beta + gamma) . grad phi_i phi_i + grad phi_i . K grad phi_i ].
+// With phi_i a tensor product this is a sum-factorised contraction of 1 + dim + dim (dim + 1) / 2 coefficient
+// fields with the 1-D matrices S^2, S G, G^2: O(10 n^4) flops per component and cell instead of the
+// (dim + 1) n^dim full cell applications of MatrixFreeTools::compute_diagonal (operator_ns.cc:210-218), same
+// result up to round-off.  Cells with weighted constraint rows go through k_diag_columns.
+template <int dim, int n, typename T, int BR>
+__global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_diag_sumfac(const KParams<T> p, const Shape<T, n> sh,
+                                                                     const uint8_t *__restrict__ skip_cell)
+{
+  using G             = Geo<dim, n>;
+  constexpr int C     = G::C;
+  constexpr int NTERM = 1 + dim + dim * (dim + 1) / 2;
+  extern __shared__ __align__(16) unsigned char smem[];
+  Ctx<dim, n, T> ctx;
+  ctx.init(smem, sh);
+  // 1-D products of the basis with itself, [q * n + i]; they live behind v in the (unused) gradient scratch
+  T *mSS = ctx.sg, *mSG = mSS + n * n, *mGG = mSG + n * n;
+  for (int k = threadIdx.x; k < n * n; k += blockDim.x)
+    {
+      mSS[k] = sh.S[k] * sh.S[k];
+      mSG[k] = sh.S[k] * sh.G[k];
+      mGG[k] = sh.G[k] * sh.G[k];
+    }
+  const uint32_t cell0  = p.cell_begin + blockIdx.x * G::CPB + ctx.cb;
+  const bool     active = cell_active(p, cell0);
+  const uint32_t cell   = cell0 < p.cell_end ? cell0 : p.cell_end - 1;
+  GeomQ<dim, n, T> geo;
+  geo.load(p, sh, cell, ctx.l, ctx.ii);
+  QTables<dim, T> tb;
+  load_tables<dim, T, BR>(p, qpos(p, (uint32_t)ctx.l, cell), cell, tb);
+  // (J^-1)_{e m}, dense
+  T ji[dim][dim];
+#pragma unroll
+  for (int e = 0; e < dim; ++e)
+#pragma unroll
+    for (int m = 0; m < dim; ++m)
+      ji[e][m] = geo.cart ? (e == m ? geo.ij[e][e] : T(0)) : geo.ij[e][m];
+
+  // coefficient fields of this quadrature point, per component: [A | b_e | K_ee | 2 K_ef (e < f)]
+  T coef[C][NTERM];
+  {
+    const T w = p.weight, nu = p.nu, d1 = tb.d1, d2 = tb.d2;
+    const T th = (BR == BR_NEWTON) ? T(1) : p.theta;
+    const T tw = p.ctd ? w : T(0);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      {
+        T alpha = 0, bg[dim], K[dim][dim];
+        if (c < dim)
+          {
+            T Hcc = 0, r1 = 0;
+            if (BR == BR_NEWTON)
+              {
+                Hcc   = tb.H[c][c];
+                T sgs = 0;
+#pragma unroll
+                for (int j = 0; j < dim; ++j)
+                  sgs += tb.H[c][j] * tb.U[j];
+                T b = tb.P[c] + sgs;
+                if (p.ctd)
+                  b = (tb.U[c] * w + tb.O[c]) + b;
+                r1 = d1 * b;
+              }
+            alpha = w + Hcc;
+#pragma unroll
+            for (int j = 0; j < dim; ++j)
+              {
+                bg[j] = th * tb.U[j] + tb.U[j] * d1 * (tw + Hcc) + (j == c ? r1 : T(0));
+#pragma unroll
+                for (int m = 0; m < dim; ++m)
+                  K[j][m] = (j == m ? nu * th : T(0)) + ((j == c && m == c) ? th * (nu + d2) : T(0)) +
+                            d1 * th * tb.U[j] * tb.U[m];
+              }
+          }
+        else
+          {
+#pragma unroll
+            for (int j = 0; j < dim; ++j)
+              {
+                bg[j] = 0;
+#pragma unroll
+                for (int m = 0; m < dim; ++m)
+                  K[j][m] = (j == m) ? d1 : T(0);
+              }
+          }
+        // to the reference cell: b_e = sum_m J^-1_{e m} bg_m, Khat = J^-1 K J^-T, all times JxW
+        coef[c][0] = geo.jxw * alpha;
+        T kj[dim][dim]; // K J^-T: kj[j][f] = sum_m K[j][m] ji[f][m]
+#pragma unroll
+        for (int j = 0; j < dim; ++j)
+#pragma unroll
+          for (int f = 0; f < dim; ++f)
+            {
+              T s = 0;
+#pragma unroll
+              for (int m = 0; m < dim; ++m)
+                s += K[j][m] * ji[f][m];
+              kj[j][f] = s;
+            }
+        int t = 1 + dim;
+#pragma unroll
+        for (int e = 0; e < dim; ++e)
+          {
+            T s = 0, kee = 0;
+#pragma unroll
+            for (int m = 0; m < dim; ++m)
+              {
+                s += ji[e][m] * bg[m];
+                kee += ji[e][m] * kj[m][e];
+              }
+            coef[c][1 + e]       = geo.jxw * s;
+            coef[c][1 + dim + e] = geo.jxw * kee;
+          }
+        t = 1 + 2 * dim;
+#pragma unroll
+        for (int e = 0; e < dim; ++e)
+#pragma unroll
+          for (int f = e + 1; f < dim; ++f)
+            {
+              T s = 0;
+#pragma unroll
+              for (int m = 0; m < dim; ++m)
+                s += ji[e][m] * kj[m][f];
+              coef[c][t++] = T(2) * geo.jxw * s;
+            }
+      }
+  }
+
+  // contract every field with its triple of 1-D matrices (transposed sweeps of all C components at once)
+  T diag[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    diag[c] = 0;
+  __syncthreads(); // matrices written
+#pragma unroll
+  for (int t = 0; t < NTERM; ++t)
+    {
+      // which direction carries a derivative factor (0 = none) once or twice
+      int de = -1, df = -1;
+      if (t >= 1 && t <= dim)
+        de = t - 1;
+      else if (t > dim && t <= 2 * dim)
+        de = df = t - 1 - dim;
+      else if (t > 2 * dim)
+        {
+          int idx = t - 1 - 2 * dim, cnt = 0;
+#pragma unroll
+          for (int e = 0; e < dim; ++e)
+#pragma unroll
+            for (int f = e + 1; f < dim; ++f)
+              {
+                if (cnt == idx)
+                  {
+                    de = e;
+                    df = f;
+                  }
+                ++cnt;
+              }
+        }
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        ctx.v[ctx.at(c, ctx.l)] = coef[c][t];
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < dim; ++e)
+        {
+          const int cnt = (de == e ? 1 : 0) + (df == e ? 1 : 0);
+          ctx.sweep(cnt == 0 ? mSS : (cnt == 1 ? mSG : mGG), e, true);
+        }
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        diag[c] += ctx.v[ctx.at(c, ctx.l)];
+      __syncthreads();
+    }
+  if (!active || (skip_cell != nullptr && skip_cell[cell]))
+    return;
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    {
+      const uint32_t iv = p.idx[idx_at(p, c * G::n_loc + ctx.l, cell)];
+      if (!(iv & GLSB_CONSTRAINED_BIT))
+        atomic_add(p.dst + iv, diag[c]);
     }
 }
 
@@ -719,6 +966,10 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_diag_columns(const KPa
   const uint32_t cell = dc.cell[li];
   const uint32_t c0 = dc.col_ptr[li], c1 = dc.col_ptr[li + 1];
   const uint32_t nrounds = (c1 - c0 + G::CPB - 1) / G::CPB;
+  GeomQ<dim, n, T> geo;
+  geo.load(p, sh, cell, ctx.l, ctx.ii);
+  QTables<dim, T> tb;
+  load_tables<dim, T, BR>(p, qpos(p, (uint32_t)ctx.l, cell), cell, tb);
   for (uint32_t r = 0; r < nrounds; ++r)
     {
       const uint32_t col = c0 + r * G::CPB + ctx.cb;
@@ -736,7 +987,7 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_diag_columns(const KPa
           ctx.v[ctx.at(c, ctx.l)] = x[c];
         }
       __syncthreads();
-      cell_apply<dim, n, T, BR>(ctx, p, sh, cell);
+      cell_apply<dim, n, T, BR>(ctx, p, geo, tb);
       T s = 0;
 #pragma unroll
       for (int c = 0; c < C; ++c)
