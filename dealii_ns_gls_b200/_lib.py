@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libglsb200.so")
 
-GLSB_ABI_VERSION = 1
+GLSB_ABI_VERSION = 2
 GLSB_F64, GLSB_F32 = 0, 1
 GLSB_GEOM_CARTESIAN, GLSB_GEOM_GENERAL = 0, 2
 GLSB_CELLS_ALL, GLSB_CELLS_INTERIOR, GLSB_CELLS_BOUNDARY = 0, 1, 2
@@ -30,6 +30,8 @@ class GlsbDesc(C.Structure):
         ("geometry_type", C.c_int32), ("inv_jac", C.c_void_p), ("jxw", C.c_void_p),
         ("cell_h_min", C.c_void_p), ("cell_measure", C.c_void_p),
         ("n_export", C.c_uint64), ("export_indices", C.c_void_p),
+        ("n_edge_constrained_indices", C.c_uint32), ("edge_constrained_indices", C.c_void_p),
+        ("has_edge_constrained_indices", C.c_int32),
     ]
 
 
@@ -44,6 +46,11 @@ SYMBOLS = {
     "glsb_vmult_host": (_I, [_P, _P, _P, _D, _P]),
     "glsb_host_register": (_I, [_P, _U64]),
     "glsb_host_unregister": (_I, [_P]),
+    "glsb_edge_begin": (_I, [_P, _P, _P]),
+    "glsb_edge_finish": (_I, [_P, _P, _P, _P]),
+    "glsb_vmult_interface_down": (_I, [_P, _P, _P, _D, _P]),
+    "glsb_vmult_interface_up": (_I, [_P, _P, _P, _D, _P]),
+    "glsb_edge_extract": (_I, [_P, _P, _P, _P]),
     "glsb_vmult_begin": (_I, [_P, _P, _P]),
     "glsb_vmult_cells": (_I, [_P, _P, _P, _D, _I, _P]),
     "glsb_vmult_finish": (_I, [_P, _P, _P, _P]),

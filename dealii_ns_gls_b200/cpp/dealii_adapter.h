@@ -20,6 +20,7 @@
 #include <deal.II/lac/la_parallel_vector.h>
 #include <deal.II/matrix_free/fe_evaluation.h>
 #include <deal.II/matrix_free/matrix_free.h>
+#include <deal.II/multigrid/mg_tools.h>
 
 #include <cuda_runtime.h>
 #include <nccl.h>
@@ -67,7 +68,7 @@ public:
                    nu, c_1, c_2, all_outflow_bcs_cut, all_outflow_bcs_nitsche, time_integrator_data,
                    consider_time_derivative, increment_form, cell_wise_stabilization, mg_level)
   {
-    // boundary-face outflow terms and GMG-LS edge operators are "next" rows of the scope table
+    // boundary-face outflow terms are a "next" row of the scope table
     AssertThrow(all_outflow_bcs_cut.empty() && all_outflow_bcs_nitsche.empty(), ExcNotImplemented());
 
     typename MatrixFree<dim, Number>::AdditionalData ad;
@@ -160,9 +161,28 @@ public:
       for (unsigned int i = range.first; i < range.second; ++i)
         export_indices.push_back(i);
 
+    // GMG-LS: owned dofs on the refinement edge of this level (operator_ns.cc:131-152, :1436-1455)
+    std::vector<uint32_t> edge_constrained_indices;
+    bool                  has_edge = false;
+    if (mg_level != numbers::invalid_unsigned_int)
+      {
+        std::vector<IndexSet> refinement_edge_indices(dof_handler.get_triangulation().n_global_levels());
+        for (unsigned int l = 0; l < refinement_edge_indices.size(); ++l)
+          refinement_edge_indices[l] = IndexSet(dof_handler.n_dofs(l));
+        MGTools::extract_inner_interface_dofs(dof_handler, refinement_edge_indices);
+        const IndexSet &owned = dof_handler.locally_owned_mg_dofs(mg_level);
+        for (const auto g : refinement_edge_indices[mg_level])
+          if (owned.is_element(g))
+            edge_constrained_indices.push_back(owned.index_within_set(g));
+        has_edge = Utilities::MPI::max(edge_constrained_indices.size(), dof_handler.get_communicator()) > 0;
+      }
+
     glsb_desc d{};
     d.abi_version = GLSB_ABI_VERSION;
     cudaGetDevice(&d.device);
+    d.n_edge_constrained_indices   = edge_constrained_indices.size();
+    d.edge_constrained_indices     = edge_constrained_indices.data();
+    d.has_edge_constrained_indices = has_edge;
     d.dim = dim, d.degree = degree, d.number_type = std::is_same<Number, double>::value ? GLSB_F64 : GLSB_F32;
     d.increment_form = increment_form, d.consider_time_derivative = consider_time_derivative;
     d.cell_wise_stabilization = cell_wise_stabilization, d.time_order = time_integrator_data.get_order();
@@ -177,6 +197,7 @@ public:
     d.n_export = export_indices.size(), d.export_indices = export_indices.data();
     AssertThrow(glsb_create(&d, &op) == 0, ExcMessage(glsb_last_error(nullptr)));
     n_local = d.n_owned + d.n_ghost;
+    has_edge_constrained_indices = has_edge;
   }
 
   ~NavierStokesOperatorB200() override { glsb_destroy(op); }
@@ -198,6 +219,7 @@ public:
   {
     MyScope scope(timer, "ns::vmult"); // same section names as the reference (operator_ns.cc:689)
     const double w = time_integrator_data.get_primary_weight();
+    check(glsb_edge_begin(op, const_cast<void *>(dev(src)), stream)); // operator_ns.cc:692-700
     check(glsb_vmult_begin(op, dev(dst), stream));
     update_ghost_values_start(src); // NCCL send/recv of the export block into the ghost block
     check(glsb_vmult_cells_part(op, dev(dst), dev(src), w, GLSB_CELLS_INTERIOR, 0, 2, stream));
@@ -207,6 +229,40 @@ public:
     check(glsb_vmult_cells_part(op, dev(dst), dev(src), w, GLSB_CELLS_INTERIOR, 1, 2, stream));
     compress_finish(dst); // glsb_unpack_add
     check(glsb_vmult_finish(op, dev(dst), dev(src), stream));
+    check(glsb_edge_finish(op, dev(dst), const_cast<void *>(dev(src)), stream)); // operator_ns.cc:724-731
+    finish(dst);
+  }
+
+  void vmult_interface_down(VectorType<Number> &dst, const VectorType<Number> &src) const override
+  {
+    MyScope scope(timer, "ns::vmult_interface_down");
+    const double w = time_integrator_data.get_primary_weight();
+    check(glsb_vmult_begin(op, dev(dst), stream));
+    update_ghost_values_start(src);
+    update_ghost_values_finish();
+    check(glsb_vmult_cells(op, dev(dst), dev(src), w, GLSB_CELLS_ALL, stream));
+    compress_start(dst);
+    compress_finish(dst);
+    check(glsb_vmult_finish(op, dev(dst), dev(src), stream));
+    finish(dst);
+  }
+
+  void vmult_interface_up(VectorType<Number> &dst, const VectorType<Number> &src) const override
+  {
+    MyScope scope(timer, "ns::vmult_interface_up");
+    check(glsb_vmult_begin(op, dev(dst), stream)); // dst = 0
+    if (has_edge_constrained_indices)
+      {
+        VectorType<Number> src_cpy;
+        src_cpy.reinit(src, /*omit_zeroing_entries=*/true);
+        check(glsb_edge_extract(op, dev(src_cpy), dev(src), stream)); // operator_ns.cc:768-774
+        update_ghost_values_start(src_cpy);
+        update_ghost_values_finish();
+        check(glsb_vmult_cells(op, dev(dst), dev(src_cpy), time_integrator_data.get_primary_weight(), GLSB_CELLS_ALL,
+                               stream));
+        compress_start(dst);
+        compress_finish(dst);
+      }
     finish(dst);
   }
 
@@ -301,6 +357,7 @@ private:
   NavierStokesOperator<dim, Number> cpu_operator; // system matrix / constant modes / constraints only
   MatrixFree<dim, Number>           matrix_free;
   glsb_op                          *op      = nullptr;
+  bool                              has_edge_constrained_indices = false;
   std::uint64_t                     n_local = 0;
   cudaStream_t                      stream = nullptr, comm_stream = nullptr;
   ncclComm_t                        nccl   = nullptr;

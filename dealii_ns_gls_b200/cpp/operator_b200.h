@@ -234,6 +234,9 @@ public:
   void              Tvmult(VectorType &dst, const VectorType &src) const { vmult(dst, src); } // operator_base.cc:12-18
   virtual void      initialize_dof_vector(VectorType &vec) const             = 0;
   virtual double    get_max_u(const VectorType &) const { return 1.0; }                      // operator_base.cc:52-56
+  // operator_base.cc:29-50: the base class throws ExcNotImplemented
+  virtual void vmult_interface_down(VectorType &, const VectorType &) const { throw Error("ExcNotImplemented"); }
+  virtual void vmult_interface_up(VectorType &, const VectorType &) const { throw Error("ExcNotImplemented"); }
 };
 
 // the arrays the C ABI takes (what the deal.II adapter extracts)
@@ -243,6 +246,9 @@ struct MeshDescription
   std::uint64_t         n_cells = 0, n_owned = 0, n_ghost = 0, n_global_dofs = 0;
   std::vector<uint32_t> dof_indices, row_dof, row_ptr, entry_col, constrained_indices, export_indices;
   std::vector<double>   entry_val, inv_jac, jxw, cell_h_min, cell_measure;
+  // GMG-LS level operators only (operator_ns.cc:131-152)
+  std::vector<uint32_t> edge_constrained_indices;
+  bool                  has_edge_constrained_indices = false;
 };
 
 template <int dim, typename Number>
@@ -289,6 +295,9 @@ public:
     d.cell_measure          = mesh.cell_measure.data();
     d.n_export              = mesh.export_indices.size();
     d.export_indices        = mesh.export_indices.data();
+    d.n_edge_constrained_indices   = (uint32_t)mesh.edge_constrained_indices.size();
+    d.edge_constrained_indices     = mesh.edge_constrained_indices.data();
+    d.has_edge_constrained_indices = mesh.has_edge_constrained_indices;
     if (glsb_create(&d, &op) != 0)
       throw Error(std::string("glsb_create: ") + glsb_last_error(nullptr));
   }
@@ -332,6 +341,19 @@ public:
   void vmult(VectorType &dst, const VectorType &src) const override
   {
     check(glsb_vmult(op, dst.data(), src.data(), time_integrator_data.get_primary_weight(), stream));
+  }
+  // vmult for callers whose vectors live in host memory (the reference's VectorType, config.h:9-10)
+  void vmult_host(Number *dst_host, const Number *src_host) const
+  {
+    check(glsb_vmult_host(op, dst_host, src_host, time_integrator_data.get_primary_weight(), stream));
+  }
+  void vmult_interface_down(VectorType &dst, const VectorType &src) const override
+  {
+    check(glsb_vmult_interface_down(op, dst.data(), src.data(), time_integrator_data.get_primary_weight(), stream));
+  }
+  void vmult_interface_up(VectorType &dst, const VectorType &src) const override
+  {
+    check(glsb_vmult_interface_up(op, dst.data(), src.data(), time_integrator_data.get_primary_weight(), stream));
   }
   void initialize_dof_vector(VectorType &vec) const override { vec.reinit(n_local); }
   double get_max_u(const VectorType &src) const override

@@ -111,6 +111,29 @@ __global__ void k_unpack_add(T *__restrict__ vec, const T *__restrict__ buf, con
     atomicAdd(vec + idx[t], buf[t]);
 }
 
+// edge-constrained dofs (GMG-LS): save src at the edge indices and zero it there / restore
+template <typename T>
+__global__ void k_edge_save_zero(T *__restrict__ src, T *__restrict__ saved, const uint32_t *__restrict__ idx, uint32_t n)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n)
+    {
+      saved[t]    = src[idx[t]];
+      src[idx[t]] = T(0);
+    }
+}
+template <typename T>
+__global__ void k_edge_restore(T *__restrict__ dst, T *__restrict__ src, const T *__restrict__ saved,
+                               const uint32_t *__restrict__ idx, uint32_t n)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n)
+    {
+      src[idx[t]] = saved[t];
+      dst[idx[t]] = saved[t]; // the reference writes the saved SRC value into dst (operator_ns.cc:729-730)
+    }
+}
+
 // glsb_vmult_host: last[d] = last chunk of cells that touches vector entry d
 __global__ void k_last_touch(const uint32_t *__restrict__ idx, const uint8_t *__restrict__ chunk_of_batch,
                              const uint32_t *__restrict__ row_dof, const uint32_t *__restrict__ row_ptr,
@@ -216,6 +239,9 @@ struct glsb_op
   uint64_t n_export = 0;
   size_t   tsize = 8;
 
+  uint32_t n_edge = 0;
+  int      has_edge = 0;
+  DevBuf   edge_idx, edge_saved, edge_cpy;
   DevBuf perm, idx, cell_flags, row_dof, row_ptr, ecol, eval, cidx, inv_jac, jxw, h_min, measure, export_idx;
   DevBuf Q, d1c, d2c, max_bits;
   int    FT = 0, NL = 1, QG = 1, F_stage = 0;
@@ -877,6 +903,21 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
       }
   }
   ok = ok && op->max_bits.alloc(8);
+  op->n_edge   = d->n_edge_constrained_indices;
+  op->has_edge = d->has_edge_constrained_indices || d->n_edge_constrained_indices > 0;
+  if (op->n_edge)
+    {
+      for (uint32_t i = 0; i < op->n_edge && ok; ++i)
+        if (d->edge_constrained_indices[i] >= d->n_owned)
+          {
+            ok = false;
+            cudaGetLastError();
+            delete op;
+            return fail(nullptr, "glsb_create: edge_constrained_indices must be owned indices");
+          }
+      ok = ok && upload(op->edge_idx, d->edge_constrained_indices, (size_t)op->n_edge * 4) &&
+           op->edge_saved.alloc((size_t)op->n_edge * op->tsize);
+    }
 
   if (!ok)
     {
@@ -994,13 +1035,101 @@ int glsb_vmult_finish(glsb_op *op, void *dst, const void *src, void *stream)
   return 0;
 }
 
-int glsb_vmult(glsb_op *op, void *dst, const void *src, double weight, void *stream)
+int glsb_edge_begin(glsb_op *op, void *src, void *stream)
+{
+  if (!op || !src)
+    return fail(op, "glsb_edge_begin: null argument");
+  if (op->n_edge == 0)
+    return 0;
+  const unsigned g = (op->n_edge + 255) / 256;
+  if (op->number_type == GLSB_F64)
+    k_edge_save_zero<double><<<g, 256, 0, (cudaStream_t)stream>>>((double *)src, op->edge_saved.as<double>(),
+                                                                  op->edge_idx.as<uint32_t>(), op->n_edge);
+  else
+    k_edge_save_zero<float><<<g, 256, 0, (cudaStream_t)stream>>>((float *)src, op->edge_saved.as<float>(),
+                                                                 op->edge_idx.as<uint32_t>(), op->n_edge);
+  op->launches++;
+  return cudaGetLastError() != cudaSuccess ? cuda_fail(op, "glsb_edge_begin") : 0;
+}
+
+int glsb_edge_finish(glsb_op *op, void *dst, void *src, void *stream)
+{
+  if (!op || !dst || !src)
+    return fail(op, "glsb_edge_finish: null argument");
+  if (op->n_edge == 0)
+    return 0;
+  const unsigned g = (op->n_edge + 255) / 256;
+  if (op->number_type == GLSB_F64)
+    k_edge_restore<double><<<g, 256, 0, (cudaStream_t)stream>>>((double *)dst, (double *)src,
+                                                                op->edge_saved.as<double>(),
+                                                                op->edge_idx.as<uint32_t>(), op->n_edge);
+  else
+    k_edge_restore<float><<<g, 256, 0, (cudaStream_t)stream>>>((float *)dst, (float *)src, op->edge_saved.as<float>(),
+                                                               op->edge_idx.as<uint32_t>(), op->n_edge);
+  op->launches++;
+  return cudaGetLastError() != cudaSuccess ? cuda_fail(op, "glsb_edge_finish") : 0;
+}
+
+int glsb_vmult_interface_down(glsb_op *op, void *dst, const void *src, double weight, void *stream)
 {
   int rc = glsb_vmult_begin(op, dst, stream);
   if (rc == 0)
     rc = glsb_vmult_cells(op, dst, src, weight, GLSB_CELLS_ALL, stream);
   if (rc == 0)
     rc = glsb_vmult_finish(op, dst, src, stream);
+  return rc;
+}
+
+int glsb_edge_extract(glsb_op *op, void *cpy, const void *src, void *stream)
+{
+  if (!op || !cpy || !src)
+    return fail(op, "glsb_edge_extract: null argument");
+  if (cudaMemsetAsync(cpy, 0, (op->n_owned + op->n_ghost) * op->tsize, (cudaStream_t)stream) != cudaSuccess)
+    return cuda_fail(op, "glsb_edge_extract: memset");
+  if (op->n_edge == 0)
+    return 0;
+  const unsigned g = (op->n_edge + 255) / 256;
+  if (op->number_type == GLSB_F64)
+    k_copy_indexed<double><<<g, 256, 0, (cudaStream_t)stream>>>((double *)cpy, (const double *)src,
+                                                                op->edge_idx.as<uint32_t>(), op->n_edge);
+  else
+    k_copy_indexed<float><<<g, 256, 0, (cudaStream_t)stream>>>((float *)cpy, (const float *)src,
+                                                               op->edge_idx.as<uint32_t>(), op->n_edge);
+  op->launches++;
+  return cudaGetLastError() != cudaSuccess ? cuda_fail(op, "glsb_edge_extract") : 0;
+}
+
+int glsb_vmult_interface_up(glsb_op *op, void *dst, const void *src, double weight, void *stream)
+{
+  if (!op || !dst || !src)
+    return fail(op, "glsb_vmult_interface_up: null argument");
+  if (op->n_ghost != 0)
+    return fail(op, "glsb_vmult_interface_up: with ghost entries use glsb_edge_extract + ghost import + "
+                    "glsb_vmult_cells + compress");
+  int rc = glsb_vmult_begin(op, dst, stream); // dst = 0
+  if (rc || !op->has_edge)
+    return rc;
+  const size_t bytes = (op->n_owned + op->n_ghost) * op->tsize;
+  if (op->edge_cpy.bytes != bytes && !op->edge_cpy.alloc(bytes))
+    return cuda_fail(op, "glsb_vmult_interface_up: scratch vector");
+  rc = glsb_edge_extract(op, op->edge_cpy.p, src, stream);
+  if (rc == 0)
+    rc = glsb_vmult_cells(op, dst, op->edge_cpy.p, weight, GLSB_CELLS_ALL, stream);
+  return rc; // no identity on the constrained rows here (operator_ns.cc:776-786)
+}
+
+int glsb_vmult(glsb_op *op, void *dst, const void *src, double weight, void *stream)
+{
+  // the reference mutates src at the edge indices during the loop and restores it (operator_ns.cc:692-700)
+  int rc = glsb_edge_begin(op, const_cast<void *>(src), stream);
+  if (rc == 0)
+    rc = glsb_vmult_begin(op, dst, stream);
+  if (rc == 0)
+    rc = glsb_vmult_cells(op, dst, src, weight, GLSB_CELLS_ALL, stream);
+  if (rc == 0)
+    rc = glsb_vmult_finish(op, dst, src, stream);
+  if (rc == 0)
+    rc = glsb_edge_finish(op, dst, const_cast<void *>(src), stream);
   return rc;
 }
 

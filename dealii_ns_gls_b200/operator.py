@@ -148,6 +148,11 @@ def build_desc(mesh: Mesh, *, number, nu, c_1, c_2, theta, time_order, consider_
     d.cell_h_min, d.cell_measure = ptr(keep["h_min"]), ptr(keep["measure"])
     d.n_export = len(export)
     d.export_indices = ptr(keep["export"])
+    edge = np.ascontiguousarray(getattr(mesh, "edge_constrained_indices", np.zeros(0)), dtype=np.uint32)
+    keep["edge"] = edge
+    d.n_edge_constrained_indices = len(edge)
+    d.edge_constrained_indices = ptr(edge)
+    d.has_edge_constrained_indices = int(getattr(mesh, "has_edge_constrained_indices", len(edge) > 0))
     return d, keep
 
 
@@ -236,7 +241,10 @@ class NavierStokesOperator:
         w = self.time_integrator_data.get_primary_weight()
         s = self._stream()
         if self.exchange is not None:
+            d, x = self._vec(dst, "dst"), self._vec(src, "src")
+            self._chk(self._lib.glsb_edge_begin(self._op, x, s), "vmult")
             self.exchange.vmult(self, dst, src, w, kernel_events)
+            self._chk(self._lib.glsb_edge_finish(self._op, d, x, s), "vmult")
         elif kernel_events is None:
             self._chk(self._lib.glsb_vmult(self._op, self._vec(dst, "dst"), self._vec(src, "src"), w, s), "vmult")
         else:
@@ -246,6 +254,35 @@ class NavierStokesOperator:
             self._chk(self._lib.glsb_vmult_cells(self._op, d, x, w, L.GLSB_CELLS_ALL, s), "vmult")
             kernel_events[1].record()
             self._chk(self._lib.glsb_vmult_finish(self._op, d, x, s), "vmult")
+
+    def vmult_interface_down(self, dst: torch.Tensor, src: torch.Tensor):
+        """operator_ns.cc:734-752 (GMG-LS edge matrix, down)."""
+        w = self.time_integrator_data.get_primary_weight()
+        if self.exchange is not None:
+            self.exchange.vmult(self, dst, src, w)
+            return
+        self._chk(self._lib.glsb_vmult_interface_down(self._op, self._vec(dst, "dst"), self._vec(src, "src"), w,
+                                                      self._stream()), "vmult_interface_down")
+
+    def vmult_interface_up(self, dst: torch.Tensor, src: torch.Tensor):
+        """operator_ns.cc:754-787 (GMG-LS edge matrix, up)."""
+        w = self.time_integrator_data.get_primary_weight()
+        s = self._stream()
+        if self.exchange is None:
+            self._chk(self._lib.glsb_vmult_interface_up(self._op, self._vec(dst, "dst"), self._vec(src, "src"), w, s),
+                      "vmult_interface_up")
+            return
+        d = self._vec(dst, "dst")
+        self._chk(self._lib.glsb_vmult_begin(self._op, d, s), "vmult_interface_up")
+        if not getattr(self.mesh, "has_edge_constrained_indices", False):
+            return
+        cpy = torch.empty_like(src)
+        self._chk(self._lib.glsb_edge_extract(self._op, self._vec(cpy, "cpy"), self._vec(src, "src"), s),
+                  "vmult_interface_up")
+        self._update_ghost_values(cpy)
+        self._chk(self._lib.glsb_vmult_cells(self._op, d, self._vec(cpy, "cpy"), w, L.GLSB_CELLS_ALL, s),
+                  "vmult_interface_up")
+        self._compress_add(dst)
 
     def Tvmult(self, dst, src):
         """operator_base.cc:12-18: Tvmult forwards to vmult."""

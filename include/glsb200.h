@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GLSB_ABI_VERSION 1
+#define GLSB_ABI_VERSION 2
 
 typedef struct glsb_op glsb_op;
 
@@ -94,6 +94,14 @@ typedef struct glsb_desc
    * exports, concatenated over neighbours); may be empty */
   uint64_t        n_export;
   const uint32_t *export_indices;
+
+  /* multigrid with local smoothing (GMG-LS, main.cc:569-732): owned indices on the refinement edge of
+   * this level (edge_constrained_indices, operator_ns.cc:131-152); has_edge_constrained_indices is the
+   * MPI::max over all ranks of "the list is not empty" (operator_ns.cc:149-151).  Empty for global
+   * coarsening and for the fine-level operator. */
+  uint32_t        n_edge_constrained_indices;
+  const uint32_t *edge_constrained_indices;
+  int32_t         has_edge_constrained_indices;
 } glsb_desc;
 
 /* ---- life cycle -------------------------------------------------------- */
@@ -137,6 +145,22 @@ int glsb_vmult_finish(glsb_op *op, void *dst, const void *src, void *stream);
  * import behind one half of the interior cells and compress(add) behind the other */
 int glsb_vmult_cells_part(glsb_op *op, void *dst, const void *src, double weight, int which, int part,
                           int n_parts, void *stream);
+/* Edge-constrained dofs around vmult (operator_ns.cc:692-700, :724-731).  glsb_vmult does both itself; a
+ * host layer that drives the pieces calls glsb_edge_begin before the ghost import (saves src at the edge
+ * indices and zeroes it there -- the reference const_casts src the same way) and glsb_edge_finish after
+ * glsb_vmult_finish (src restored, dst = saved src value at the edge indices). */
+int glsb_edge_begin(glsb_op *op, void *src, void *stream);
+int glsb_edge_finish(glsb_op *op, void *dst, void *src, void *stream);
+/* vmult_interface_down (operator_ns.cc:734-752): the cell loop with zeroed dst plus the identity on
+ * constrained rows, without the edge handling of vmult. */
+int glsb_vmult_interface_down(glsb_op *op, void *dst, const void *src, double weight, void *stream);
+/* vmult_interface_up (operator_ns.cc:754-787): dst = A * (src restricted to the edge indices); dst = 0 if
+ * no rank has edge indices; no identity on constrained rows.  Single-rank form. */
+int glsb_vmult_interface_up(glsb_op *op, void *dst, const void *src, double weight, void *stream);
+/* cpy = 0 except cpy[edge] = src[edge] (operator_ns.cc:768-774), for a host layer that imports the ghosts
+ * of cpy itself before glsb_vmult_cells */
+int glsb_edge_extract(glsb_op *op, void *cpy, const void *src, void *stream);
+
 /* leave n_sms multiprocessors free when launching the (persistent) cell kernels, so that
  * communication kernels (NCCL send/recv) can run next to them; 0 = use the whole GPU */
 int glsb_set_sm_reserve(glsb_op *op, int n_sms);

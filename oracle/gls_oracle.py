@@ -536,9 +536,17 @@ class OracleOperator:
 
     # ---------------- public API ---------------- #
 
-    def vmult(self, src, weight):
-        """operator_ns.cc:684-732 (no edge-constrained indices, no face integrals)."""
+    def vmult(self, src, weight, edge_constrained_indices=None):
+        """operator_ns.cc:684-732 (no face integrals).  With edge_constrained_indices (GMG-LS,
+        :692-700, :724-731): src is zeroed there for the loop and dst gets the saved src value."""
         src = np.asarray(src, dtype=self.dtype)
+        if edge_constrained_indices is not None and len(edge_constrained_indices):
+            e = np.asarray(edge_constrained_indices, dtype=np.int64)
+            masked = src.copy()
+            masked[e] = 0
+            dst = self.vmult(masked, weight)
+            dst[e] = src[e]
+            return dst
         x = self._resolve(src)
         loc = self._apply_cells(self._gather(x), weight, residual=False)
         dst = self._distribute_transpose(self._scatter(loc))
@@ -546,6 +554,24 @@ class OracleOperator:
         if len(self.constrained):
             dst[self.constrained] = src[self.constrained]
         return dst
+
+    def vmult_interface_down(self, src, weight):
+        """operator_ns.cc:734-752: the plain cell loop + identity on constrained rows."""
+        return self.vmult(src, weight)
+
+    def vmult_interface_up(self, src, weight, edge_constrained_indices, has_edge=None):
+        """operator_ns.cc:754-787: A applied to src restricted to the edge indices, no identity
+        on constrained rows; zero if no rank has edge indices."""
+        src = np.asarray(src, dtype=self.dtype)
+        e = np.asarray(edge_constrained_indices, dtype=np.int64)
+        if has_edge is None:
+            has_edge = len(e) > 0
+        if not has_edge:
+            return np.zeros_like(src)
+        cpy = np.zeros_like(src)
+        cpy[e] = src[e]
+        loc = self._apply_cells(self._gather(self._resolve(cpy)), weight, residual=False)
+        return np.asarray(self._distribute_transpose(self._scatter(loc)), dtype=self.dtype)
 
     def evaluate_residual(self, src_with_bc, weight):
         """operator_ns.cc:648-682; src must already carry the inhomogeneous BCs."""

@@ -276,3 +276,36 @@ def test_vmult_host_matches_device_vmult(case, number, monkeypatch):
         torch.cuda.synchronize()
         assert not bool(torch.isnan(h_dst).any())
         assert rel_l2(h_dst.numpy(), ref.cpu().numpy()) < (1e-13 if number == "double" else 1e-5)
+
+
+@pytest.mark.parametrize("number", ["double", "float"])
+@pytest.mark.parametrize("dim,degree,kind", [(2, 2, "cube"), (3, 2, "shell"), (3, 1, "cube")])
+def test_gmg_ls_edge_indices_and_interface_operators(dim, degree, kind, number):
+    """GMG-LS level operators (main.cc:569-732, input/rotation.json): vmult with edge-constrained
+    indices (operator_ns.cc:692-700, :724-731) and vmult_interface_down / up (:734-787)."""
+    mesh = _mesh(kind, dim, degree)
+    rng = np.random.default_rng(99)
+    free = np.setdiff1d(np.arange(mesh.n_owned), np.array(sorted(mesh.constraints.keys()), dtype=np.int64))
+    edge = np.sort(rng.choice(free, size=max(3, len(free) // 9), replace=False))
+    mesh.edge_constrained_indices = edge
+    mesh.has_edge_constrained_indices = True
+    ti = TI(2, [15.0, -20.0, 5.0], 0.1)
+    ora, gpu, src, _ = _setup(mesh, ti, number, ctd=True, cell_wise=False, nu=0.01)
+    x = _to_dev(src, number)
+    x0 = x.clone()
+    dst = gpu.initialize_dof_vector()
+    gpu.vmult(dst, x)
+    assert bool((x == x0).all()), "src must come back unchanged"
+    assert rel_l2(dst.cpu().numpy(), ora.vmult(src, 15.0, edge)) < TOL[number]
+    gpu.vmult_interface_down(dst, x)
+    assert rel_l2(dst.cpu().numpy(), ora.vmult_interface_down(src, 15.0)) < TOL[number]
+    gpu.vmult_interface_up(dst, x)
+    assert rel_l2(dst.cpu().numpy(), ora.vmult_interface_up(src, 15.0, edge)) < TOL[number]
+    # no edge indices anywhere: interface_up is the zero operator
+    mesh.edge_constrained_indices = np.zeros(0, dtype=np.int64)
+    mesh.has_edge_constrained_indices = False
+    gpu2 = make_gpu(mesh, ti, number=number, ctd=True, cell_wise=False, nu=0.01)
+    gpu2.set_previous_solution([x, x, x])
+    gpu2.set_linearization_point(x)
+    gpu2.vmult_interface_up(dst, x)
+    assert float(dst.abs().max()) == 0.0
