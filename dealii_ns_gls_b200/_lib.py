@@ -64,6 +64,10 @@ SYMBOLS = {
     "glsb_diagonal_cells": (_I, [_P, _P, _D, _P]),
     "glsb_diagonal_finish": (_I, [_P, _P, _P]),
     "glsb_get_max_u": (_I, [_P, _P, C.POINTER(_D), _P]),
+    "glsb_relaxation_vmult": (_I, [_P, _P, _P, _P, _D, _I, _D, _P]),
+    "glsb_relaxation_step": (_I, [_P, _P, _P, _P, _D, _I, _D, _P]),
+    "glsb_relaxation_update": (_I, [_P, _P, _P, _P, _P, _D, _P]),
+    "glsb_estimate_relaxation": (_I, [_P, _P, _I, _D, _D, _U64, C.POINTER(_D), C.POINTER(_D), _P]),
     "glsb_pack_export": (_I, [_P, _P, _P, _P]),
     "glsb_unpack_add": (_I, [_P, _P, _P, _P]),
     "glsb_n_cells": (_U64, [_P]),

@@ -111,6 +111,87 @@ __global__ void k_unpack_add(T *__restrict__ vec, const T *__restrict__ buf, con
     atomicAdd(vec + idx[t], buf[t]);
 }
 
+// ---- relaxation smoother (PreconditionRelaxation with a DiagonalMatrix, multigrid.h:67-69) ----
+template <typename T>
+__global__ void k_relax_first(T *__restrict__ x, const T *__restrict__ b, const T *__restrict__ d, T omega, uint64_t n)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    x[i] = omega * (d[i] * b[i]);
+}
+template <typename T>
+__global__ void k_relax_update(T *__restrict__ x, const T *__restrict__ t, const T *__restrict__ b,
+                               const T *__restrict__ d, T omega, uint64_t n)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    x[i] += omega * (d[i] * (b[i] - t[i]));
+}
+// power iteration pieces; sums[0..2] are double accumulators on the device
+template <typename T>
+__global__ void k_pi_init(T *__restrict__ e, uint64_t first, uint64_t n, double *__restrict__ sums)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double         v = 0;
+  if (i < n)
+    {
+      v    = (double)((i + first) % 11);
+      e[i] = (T)v;
+    }
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v != 0)
+    atomicAdd(sums, v);
+}
+template <typename T>
+__global__ void k_pi_shift(T *__restrict__ e, const double *__restrict__ sums, uint64_t n)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    e[i] -= (T)(sums[0] / (double)n); // vector.add(-mean_value)
+}
+// v1 = d * v2 (v2 may be null: v1 = e, for the initial normalisation); sums[1] += e . v1, sums[2] += v1 . v1
+template <typename T>
+__global__ void k_pi_apply(T *__restrict__ v1, const T *__restrict__ v2, const T *__restrict__ d,
+                           const T *__restrict__ e, uint64_t n, double *__restrict__ sums)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double         s1 = 0, s2 = 0;
+  if (i < n)
+    {
+      const T x = v2 ? d[i] * v2[i] : e[i];
+      if (v2)
+        v1[i] = x;
+      s1 = (double)e[i] * (double)x;
+      s2 = (double)x * (double)x;
+    }
+  for (int o = 16; o > 0; o >>= 1)
+    {
+      s1 += __shfl_down_sync(0xffffffffu, s1, o);
+      s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    }
+  if ((threadIdx.x & 31) == 0)
+    {
+      atomicAdd(sums + 1, s1);
+      atomicAdd(sums + 2, s2);
+    }
+}
+// e = v1 / |v1|; records lambda = sums[1] into hist[k] and clears the accumulators
+template <typename T>
+__global__ void k_pi_normalise(T *__restrict__ e, const T *__restrict__ v1, uint64_t n,
+                               const double *__restrict__ sums)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    e[i] = (T)((double)v1[i] / sqrt(sums[2]));
+}
+__global__ void k_pi_record(double *__restrict__ sums, double *__restrict__ hist, int k)
+{
+  if (k >= 0)
+    hist[k] = sums[1];
+  sums[0] = sums[1] = sums[2] = 0;
+}
+
 // edge-constrained dofs (GMG-LS): save src at the edge indices and zero it there / restore
 template <typename T>
 __global__ void k_edge_save_zero(T *__restrict__ src, T *__restrict__ saved, const uint32_t *__restrict__ idx, uint32_t n)
@@ -239,6 +320,7 @@ struct glsb_op
   uint64_t n_export = 0;
   size_t   tsize = 8;
 
+  DevBuf   relax_t, pi_e, pi_v1, pi_v2, pi_sums; // smoother scratch vectors
   uint32_t n_edge = 0;
   int      has_edge = 0;
   DevBuf   edge_idx, edge_saved, edge_cpy;
@@ -1345,6 +1427,154 @@ int glsb_host_register(void *ptr, uint64_t bytes)
   return cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault) == cudaSuccess ? 0 : 1;
 }
 int glsb_host_unregister(void *ptr) { return cudaHostUnregister(ptr) == cudaSuccess ? 0 : 1; }
+
+// ---- relaxation smoother -----------------------------------------------------------------------
+extern "C++" {
+template <typename T>
+static int relax_update(glsb_op *op, void *x, const void *t, const void *b, const void *d, double omega, cudaStream_t s)
+{
+  const uint64_t n = op->n_owned; // ghost entries take no part in vector operations
+  if (n == 0)
+    return 0;
+  if (t)
+    k_relax_update<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((T *)x, (const T *)t, (const T *)b, (const T *)d,
+                                                                  (T)omega, n);
+  else
+    k_relax_first<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((T *)x, (const T *)b, (const T *)d, (T)omega, n);
+  op->launches++;
+  return cudaGetLastError() != cudaSuccess;
+}
+} // extern "C++"
+
+static int relax_sweeps(glsb_op *op, void *dst, const void *src, const void *inv_diag, double omega, int n_it,
+                        double weight, bool from_zero, void *stream)
+{
+  if (!op || !dst || !src || !inv_diag)
+    return fail(op, "glsb_relaxation: null argument");
+  if (n_it < 0)
+    return fail(op, "glsb_relaxation: negative n_iterations");
+  if (op->n_ghost != 0)
+    return fail(op, "glsb_relaxation: with ghost entries drive the sweeps from the host layer "
+                    "(exchange-aware vmult + glsb_relaxation_update)");
+  cudaStream_t s     = (cudaStream_t)stream;
+  const size_t bytes = (op->n_owned + op->n_ghost) * op->tsize;
+  if (op->relax_t.bytes != bytes && !op->relax_t.alloc(bytes))
+    return cuda_fail(op, "glsb_relaxation: scratch vector");
+  const bool f64 = op->number_type == GLSB_F64;
+  int        it  = 0;
+  if (from_zero)
+    {
+      if (n_it == 0)
+        return cudaMemsetAsync(dst, 0, bytes, s) != cudaSuccess ? cuda_fail(op, "glsb_relaxation: memset") : 0;
+      if (f64 ? relax_update<double>(op, dst, nullptr, src, inv_diag, omega, s) :
+                relax_update<float>(op, dst, nullptr, src, inv_diag, omega, s))
+        return cuda_fail(op, "glsb_relaxation: first sweep");
+      it = 1;
+    }
+  for (; it < n_it; ++it)
+    {
+      int rc = glsb_vmult(op, op->relax_t.p, dst, weight, stream);
+      if (rc)
+        return rc;
+      if (f64 ? relax_update<double>(op, dst, op->relax_t.p, src, inv_diag, omega, s) :
+                relax_update<float>(op, dst, op->relax_t.p, src, inv_diag, omega, s))
+        return cuda_fail(op, "glsb_relaxation: update");
+    }
+  return 0;
+}
+
+int glsb_relaxation_vmult(glsb_op *op, void *dst, const void *src, const void *inv_diag, double omega,
+                          int n_iterations, double weight, void *stream)
+{
+  return relax_sweeps(op, dst, src, inv_diag, omega, n_iterations, weight, true, stream);
+}
+
+int glsb_relaxation_step(glsb_op *op, void *dst, const void *src, const void *inv_diag, double omega, int n_iterations,
+                         double weight, void *stream)
+{
+  return relax_sweeps(op, dst, src, inv_diag, omega, n_iterations, weight, false, stream);
+}
+
+int glsb_relaxation_update(glsb_op *op, void *x, const void *t, const void *b, const void *inv_diag, double omega,
+                           void *stream)
+{
+  if (!op || !x || !t || !b || !inv_diag)
+    return fail(op, "glsb_relaxation_update: null argument");
+  const int rc = op->number_type == GLSB_F64 ? relax_update<double>(op, x, t, b, inv_diag, omega, (cudaStream_t)stream) :
+                                               relax_update<float>(op, x, t, b, inv_diag, omega, (cudaStream_t)stream);
+  return rc ? cuda_fail(op, "glsb_relaxation_update") : 0;
+}
+
+extern "C++" {
+template <typename T>
+static int estimate_relaxation(glsb_op *op, const void *inv_diag, int n_it, double weight, uint64_t first,
+                               double *lambda, cudaStream_t s)
+{
+  const uint64_t n     = op->n_owned;
+  const size_t   bytes = (op->n_owned + op->n_ghost) * op->tsize;
+  const unsigned g     = (unsigned)((n + 255) / 256);
+  if ((op->pi_e.bytes != bytes && !op->pi_e.alloc(bytes)) || (op->pi_v1.bytes != bytes && !op->pi_v1.alloc(bytes)) ||
+      (op->pi_v2.bytes != bytes && !op->pi_v2.alloc(bytes)) || !op->pi_sums.alloc((size_t)(3 + n_it) * 8))
+    return 1;
+  T      *e = op->pi_e.as<T>(), *v1 = op->pi_v1.as<T>(), *v2 = op->pi_v2.as<T>();
+  double *sums = op->pi_sums.as<double>(), *hist = sums + 3;
+  cudaMemsetAsync(e, 0, bytes, s);
+  cudaMemsetAsync(sums, 0, (size_t)(3 + n_it) * 8, s);
+  // set_initial_guess: (global index) % 11, mean-free; constraints.set_zero; eigenvector /= l2_norm
+  k_pi_init<T><<<g, 256, 0, s>>>(e, first, n, sums);
+  k_pi_shift<T><<<g, 256, 0, s>>>(e, sums, n);
+  if (op->n_constrained)
+    k_set_indexed<T><<<(op->n_constrained + 255) / 256, 256, 0, s>>>(e, op->cidx.as<uint32_t>(), op->n_constrained, T(0));
+  k_pi_record<<<1, 1, 0, s>>>(sums, hist, -1);
+  k_pi_apply<T><<<g, 256, 0, s>>>(v1, (const T *)nullptr, (const T *)nullptr, e, n, sums);
+  k_pi_normalise<T><<<g, 256, 0, s>>>(e, e, n, sums);
+  k_pi_record<<<1, 1, 0, s>>>(sums, hist, -1);
+  op->launches += 6;
+  for (int k = 0; k < n_it; ++k)
+    {
+      if (glsb_vmult(op, v2, e, weight, s))
+        return 1;
+      k_pi_apply<T><<<g, 256, 0, s>>>(v1, v2, (const T *)inv_diag, e, n, sums); // vector1 = D^-1 A e; e . vector1
+      k_pi_normalise<T><<<g, 256, 0, s>>>(e, v1, n, sums);                      // vector1 /= |vector1|; swap
+      k_pi_record<<<1, 1, 0, s>>>(sums, hist, k);
+      op->launches += 3;
+    }
+  if (cudaGetLastError() != cudaSuccess)
+    return 1;
+  *lambda = 0;
+  if (n_it > 0 && cudaMemcpyAsync(lambda, hist + n_it - 1, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    return 1;
+  return cudaStreamSynchronize(s) != cudaSuccess;
+}
+} // extern "C++"
+
+int glsb_estimate_relaxation(glsb_op *op, const void *inv_diag, int n_power_iterations, double smoothing_range,
+                             double weight, uint64_t first_local_index, double *omega_out, double *ev_max_out,
+                             void *stream)
+{
+  if (!op || !inv_diag || !omega_out)
+    return fail(op, "glsb_estimate_relaxation: null argument");
+  if (op->n_ghost != 0)
+    return fail(op, "glsb_estimate_relaxation: single-rank operators only");
+  if (n_power_iterations < 1)
+    return fail(op, "glsb_estimate_relaxation: n_power_iterations must be positive");
+  double    lambda = 0;
+  const int rc     = op->number_type == GLSB_F64 ?
+                       estimate_relaxation<double>(op, inv_diag, n_power_iterations, weight, first_local_index, &lambda,
+                                               (cudaStream_t)stream) :
+                       estimate_relaxation<float>(op, inv_diag, n_power_iterations, weight, first_local_index, &lambda,
+                                              (cudaStream_t)stream);
+  if (rc)
+    return cuda_fail(op, "glsb_estimate_relaxation");
+  // deal.II: max_eigenvalue_estimate = 1.2 * power-iteration value (safety factor);
+  // alpha = max / smoothing_range (smoothing_range > 1), relaxation = 2 / (alpha + max)
+  const double ev_max = 1.2 * lambda;
+  const double alpha  = smoothing_range > 1.0 ? ev_max / smoothing_range : 0.9 * ev_max;
+  *omega_out          = 2.0 / (alpha + ev_max);
+  if (ev_max_out)
+    *ev_max_out = ev_max;
+  return 0;
+}
 
 int glsb_evaluate_residual_cells(glsb_op *op, void *dst, const void *src, double weight, int which, void *stream)
 {

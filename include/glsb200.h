@@ -195,6 +195,32 @@ int glsb_diagonal_finish(glsb_op *op, void *diag, void *stream);
  * synchronises the stream; the MPI::max over ranks stays with the caller. */
 int glsb_get_max_u(glsb_op *op, const void *vec, double *out_host, void *stream);
 
+/* ---- relaxation smoother on the device -------------------------------
+ * The multigrid smoother of the reference is deal.II's PreconditionRelaxation<OperatorBase<MGNumber>,
+ * DiagonalMatrix> (include/multigrid.h:67-69): damped point-Jacobi x <- x + omega D^-1 (b - A x), 5 sweeps,
+ * omega from a 20-step power iteration on D^-1 A with smoothing range 20 (multigrid.h:30-32,
+ * multigrid.cc:290-304, :353-370).  deal.II runs it as op.vmult + separate host vector operations; here all
+ * sweeps of a call are enqueued on the stream back to back (vmult kernel + one fused update kernel per
+ * sweep), nothing returns to the host in between. */
+/* PreconditionRelaxation::vmult: n_iterations sweeps from a ZERO initial guess (the first sweep is
+ * dst = omega * inv_diag * src and needs no operator application) */
+int glsb_relaxation_vmult(glsb_op *op, void *dst, const void *src, const void *inv_diag, double omega,
+                          int n_iterations, double weight, void *stream);
+/* PreconditionRelaxation::step: n_iterations sweeps starting from the current dst */
+int glsb_relaxation_step(glsb_op *op, void *dst, const void *src, const void *inv_diag, double omega,
+                         int n_iterations, double weight, void *stream);
+/* one fused update x += omega * inv_diag * (b - t) for host layers that drive an exchange-aware vmult
+ * themselves (t = A x on entry) */
+int glsb_relaxation_update(glsb_op *op, void *x, const void *t, const void *b, const void *inv_diag, double omega,
+                           void *stream);
+/* PreconditionRelaxation::estimate_eigenvalues with EigenvalueAlgorithm::power_iteration and relaxation = 0:
+ * start vector (i + first_local_index) % 11 minus its mean, zero on constrained dofs, normalised;
+ * n_power_iterations of e <- D^-1 A e / |.|, lambda = e . D^-1 A e; ev_max = 1.2 lambda;
+ * omega = 2 / (ev_max / smoothing_range + ev_max).  Synchronises the stream.  Single-rank operators. */
+int glsb_estimate_relaxation(glsb_op *op, const void *inv_diag, int n_power_iterations, double smoothing_range,
+                             double weight, uint64_t first_local_index, double *omega_out, double *ev_max_out,
+                             void *stream);
+
 /* ---- ghost exchange helpers (update_ghost_values / compress(add)) ------- */
 
 /* buf[i] = vec[export_indices[i]] */

@@ -309,3 +309,35 @@ def test_gmg_ls_edge_indices_and_interface_operators(dim, degree, kind, number):
     gpu2.set_linearization_point(x)
     gpu2.vmult_interface_up(dst, x)
     assert float(dst.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("number", ["float", "double"])
+@pytest.mark.parametrize("dim,degree,kind", [(3, 2, "shell"), (2, 2, "cube"), (3, 1, "cube")])
+def test_relaxation_smoother_on_device(dim, degree, kind, number):
+    """PreconditionRelaxation as PreconditionerGMG configures it (multigrid.cc:290-304): omega from the
+    20-step power iteration, 5 sweeps of vmult (zero guess) and of step, all on the device."""
+    from dealii_ns_gls_b200.smoother import PreconditionRelaxation
+    from oracle.gls_smoother import OracleRelaxation
+    mesh = _mesh(kind, dim, degree)
+    ti = TI(2, [15.0, -20.0, 5.0], 0.1)
+    ora, gpu, src, rng = _setup(mesh, ti, number, ctd=True, cell_wise=False, nu=0.01)
+    inv_diag = gpu.initialize_dof_vector()
+    gpu.compute_inverse_diagonal(inv_diag)
+    sm = PreconditionRelaxation(gpu, inv_diag)
+    ref = OracleRelaxation(ora, 15.0, ora.compute_inverse_diagonal(15.0))
+    tol = 5e-4 if number == "float" else 1e-10  # 20 normalised power iterations amplify round-off
+    assert abs(sm.get_relaxation() - ref.get_relaxation()) < tol * ref.get_relaxation()
+    assert abs(sm.estimate_eigenvalues().max_eigenvalue_estimate - ref.max_eigenvalue_estimate) \
+        < tol * ref.max_eigenvalue_estimate
+    # same omega on both sides for the sweep comparison
+    ref.relaxation = sm.get_relaxation()
+    b = _to_dev(src, number)
+    x = gpu.initialize_dof_vector()
+    sm.vmult(x, b)
+    x_ref = ref.vmult(src)
+    assert rel_l2(x.cpu().numpy(), x_ref) < 20 * TOL[number]
+    sm.step(x, b)
+    assert rel_l2(x.cpu().numpy(), ref.step(x_ref, src)) < 20 * TOL[number]
+    l0 = gpu.launch_count()
+    sm.vmult(x, b)
+    assert gpu.launch_count() - l0 >= 2 * sm.n_iterations - 1  # 4 x (cells + update) + first sweep

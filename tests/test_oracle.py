@@ -264,3 +264,29 @@ def test_c_restatement_matches_numpy_oracle(dim, degree, branch):
     for nt in (1, 3):
         got = co.apply(src, w, n_threads=nt)
         assert np.linalg.norm(got - ref) <= 1e-13 * np.linalg.norm(ref)
+
+
+def test_relaxation_restatement_smooths():
+    """oracle/gls_smoother.py (PreconditionRelaxation as multigrid.cc:290-304 configures it): omega from
+    the power iteration is positive and below 2 / lambda_max, vmult equals n steps from zero, and the
+    sweeps damp the high-frequency start vector of deal.II's eigenvalue estimate."""
+    from dealii_ns_gls_b200 import mesh as gm
+    from oracle.gls_smoother import OracleRelaxation
+    from tests.util import TI, make_oracle
+    mesh = gm.hypercube(2, 4, 2)
+    ti = TI(1, [10.0, -10.0], 0.1)
+    ora = make_oracle(mesh, ti, nu=0.1)
+    rng = np.random.default_rng(3)
+    ora.set_linearization_point(0.1 * rng.uniform(-1, 1, mesh.n_dofs), 0.1)
+    d = ora.compute_inverse_diagonal(10.0)
+    sm = OracleRelaxation(ora, 10.0, d)
+    omega = sm.get_relaxation()
+    assert 0 < omega < 2.0 / (sm.max_eigenvalue_estimate / 1.2)
+    b = rng.uniform(-1, 1, mesh.n_dofs)
+    x = sm.vmult(b)
+    assert np.allclose(x, sm.step(np.zeros_like(b), b), rtol=1e-12, atol=1e-14)
+    e = ((np.arange(mesh.n_dofs)) % 11).astype(float)
+    e -= e.mean()
+    r0 = np.linalg.norm(e)
+    r5 = np.linalg.norm(sm.step(e, np.zeros_like(e)))  # error propagation of 5 sweeps
+    assert r5 < 0.9 * r0
