@@ -30,6 +30,9 @@ namespace glsb
 {
 namespace q2
 {
+#ifndef GLSB_Q2_F64_CTAS
+#define GLSB_Q2_F64_CTAS 2
+#endif
 #ifndef GLSB_Q2_F32_CTAS
 #define GLSB_Q2_F32_CTAS 3 // resident CTAs per SM the float instantiation is compiled for
 #endif
@@ -129,7 +132,7 @@ __device__ __forceinline__ void issue_stage(const KParams<T> &p, int F, T *tab, 
 }
 
 template <typename T, bool GENERAL, bool CTD, bool CELLWISE, int ROWS>
-__global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : 2))
+__global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : GLSB_Q2_F64_CTAS))
   k_vmult_q2_newton(const KParams<T> p, const Shape<T, 3> sh, const int F, const int nst)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -347,10 +350,11 @@ __global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : 2))
                   T        y   = sgu + ugs;
                   if (CTD)
                     y = td + y;
-                  // ---- exchange round 2: the pressure row needs y of the three velocity rows --------
-                  xs[4 * XROW + xpos] = y;
-                  // velocity row c
+                  // velocity row c: SUPG residual of the increment, delta_1 (y + d_c p)
                   const T r0  = d1 * (y + gpc);
+                  // ---- exchange round 2: the pressure row is (grad q, residual_0): it needs r0 of the three
+                  // velocity rows (operator_ns.cc:1166-1172), published as they are
+                  xs[4 * XROW + xpos] = r0;
                   const T sgs = H0 * U0 + H1 * U1 + H2 * U2; // U . grad U_c
                   T       rb  = Pc + sgs;
                   if (CTD)
@@ -362,14 +366,12 @@ __global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : 2))
                   T       o1   = nu * (g1 + Gc1) + U1 * r0 + u1 * rr1 + (c == 1 ? diag : T(0));
                   T       o2   = nu * (g2 + Gc2) + U2 * r0 + u2 * rr1 + (c == 2 ? diag : T(0));
                   __syncwarp();
-                  // pressure row: (q, div u) and delta_1 (grad q, residual_0)
-                  const Pair<T> y01 = *reinterpret_cast<const Pair<T> *>(xs + 4 * XROW + xp0);
-                  const T       y0 = y01.a, y1 = y01.b, y2 = xs[4 * XROW + xp1];
-                  const T q0 = d1 * (y0 + g0), q1 = d1 * (y1 + g1), q2 = d1 * (y2 + g2);
+                  // pressure row: (q, div u) and (grad q, residual_0)
+                  const Pair<T> r01 = *reinterpret_cast<const Pair<T> *>(xs + 4 * XROW + xp0);
                   vo = is_p ? div : vo;
-                  o0 = is_p ? q0 : o0;
-                  o1 = is_p ? q1 : o1;
-                  o2 = is_p ? q2 : o2;
+                  o0 = is_p ? r01.a : o0;
+                  o1 = is_p ? r01.b : o1;
+                  o2 = is_p ? xs[4 * XROW + xp1] : o2;
                   // submit_value / submit_gradient: times JxW, back to the reference cell
                   T ox, oy, oz;
                   if (GENERAL)
@@ -497,7 +499,7 @@ size_t smem_bytes(int F, int nst)
 template <typename T, int ROWS>
 int ring_depth(int F)
 {
-  const int ctas = sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : 2;
+  const int ctas = sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : GLSB_Q2_F64_CTAS;
   int       nst  = 2;
   while (ROWS == 1 && nst < 4 && ctas * (smem_bytes<T, ROWS>(F, nst + 1) + 1024) <= 228 * 1024)
     ++nst;
