@@ -327,6 +327,7 @@ struct glsb_op
   DevBuf perm, idx, cell_flags, row_dof, row_ptr, ecol, eval, cidx, inv_jac, jxw, h_min, measure, export_idx;
   DevBuf Q, d1c, d2c, max_bits;
   int    FT = 0, NL = 1, QG = 1, F_stage = 0;
+  int    packed = 0; // float Q2 operators: two cells per lane in the vmult kernel
   int    fU = -1, fH = -1, fP = -1, fO = -1, fd1q = -1, fd2q = -1, fJ = -1, fjxw = -1, fGold = -1, fgoldp = -1;
   DevBuf diag_skip, dc_cell, dc_col_ptr, dc_col_dof, dc_ent_ptr, dc_ent_loc, dc_ent_val;
   uint32_t dc_n_list = 0;
@@ -425,6 +426,7 @@ KParams<T> base_params(const glsb_op *op)
   p.theta_ne_1 = (op->theta != 1.0);
   p.max_bits   = op->max_bits.as<unsigned long long>();
   p.sm_reserve = op->sm_reserve;
+  p.packed     = op->packed;
   return p;
 }
 
@@ -772,7 +774,9 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
   {
     DevBuf raw;
     ok = ok && upload(raw, d->dof_indices, (size_t)nc * ndof * 4);
-    ok = ok && op->idx.alloc((size_t)(ndof + 1) * op->ncp * 4);
+    // one extra (zeroed) batch behind the last one: the packed float kernel stages batches in pairs
+    ok = ok && op->idx.alloc((size_t)(ndof + 1) * (op->ncp + 32) * 4);
+    ok = ok && cudaMemset(op->idx.p, 0, op->idx.bytes) == cudaSuccess;
     if (ok)
       {
         const uint64_t tot = (uint64_t)(ndof + 1) * op->ncp;
@@ -909,7 +913,12 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
         const size_t layer = (size_t)op->F_stage * 9 * 32 * op->tsize;
         const size_t fixed = (size_t)4 * 2 * 180 * op->tsize + 2 * 109 * 32 * 4 + 256;
         const bool   fits  = 2 * (2 * layer + fixed + 1024) <= 228 * 1024;
-        op->QG             = rows ? (atoi(rows) == 1 ? 3 : 9) : (fits ? 9 : 3);
+        // opt-in (GLSB_Q2_PACK=1): the packed float kernel, two cells per lane with FFMA2.  Measured on config P
+        // in FP32: 48.4 GDoF/s against 47.4 for the scalar kernel (29 % fewer instructions per cell, but the
+        // 64-bit register footprint allows 8 instead of 12 warps per SM), 25.3 against 28.5 on config C: not
+        // the default.  It stages two batches per slot, hence row stages.
+        op->packed         = op->number_type == GLSB_F32 && getenv("GLSB_Q2_PACK") != nullptr;
+        op->QG             = rows ? (atoi(rows) == 1 ? 3 : 9) : ((fits && !op->packed) ? 9 : 3);
         op->NL           = 27 / op->QG;
       }
     else
@@ -917,7 +926,7 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
         op->NL = 1;
         op->QG = op->nq;
       }
-    const size_t bytes = (size_t)op->FT * op->nq * op->ncp * op->tsize;
+    const size_t bytes = (size_t)op->FT * op->nq * (op->ncp + 32) * op->tsize; // + one batch, see idx
     ok = ok && op->Q.alloc(bytes) && op->d1c.alloc(op->ncp * op->tsize) && op->d2c.alloc(op->ncp * op->tsize);
     if (ok)
       ok = cudaMemset(op->Q.p, 0, bytes) == cudaSuccess;

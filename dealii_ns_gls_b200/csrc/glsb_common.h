@@ -50,6 +50,7 @@ struct KParams
   uint32_t cell_begin, cell_end;
   uint32_t hole_begin, hole_end; // padding slots between the interior and the boundary range
   int      sm_reserve;           // multiprocessors to leave free (persistent kernels)
+  int      packed;               // Q2 float kernel: two cells per lane (FFMA2)
   uint64_t ncp;
   const uint32_t *idx; // blocked [ncp/32][ndof + 1][32]: ndof = C*n_loc index rows (see idx_at()), then one
                        // row with a flag word per cell (non-zero: the cell has constrained dofs)

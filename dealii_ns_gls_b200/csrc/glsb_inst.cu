@@ -220,10 +220,17 @@ template <>
 int Kernels<GLSB_DIM, GLSB_REAL>::vmult_q2(const KParams<GLSB_REAL> &p, const ShapeHost &sh, int F, cudaStream_t s)
 {
 #if GLSB_DIM == 3 && defined(GLSB_WITH_Q2)
-  const auto S     = to_shape<GLSB_REAL, 3>(sh);
+  const auto S = to_shape<GLSB_REAL, 3>(sh);
+  if (p.packed) // float only: two cells per lane, FFMA2 arithmetic
+    {
+      const auto S2 = q2::to_packed_shape(S);
+      if (p.geom == GLSB_GEOM_GENERAL)
+        return q2::launch_flags<GLSB_REAL, q2::PackedOf<GLSB_REAL>::type, true>(p, S2, F, s);
+      return q2::launch_flags<GLSB_REAL, q2::PackedOf<GLSB_REAL>::type, false>(p, S2, F, s);
+    }
   if (p.geom == GLSB_GEOM_GENERAL)
-    return q2::launch_flags<GLSB_REAL, true>(p, S, F, s);
-  return q2::launch_flags<GLSB_REAL, false>(p, S, F, s);
+    return q2::launch_flags<GLSB_REAL, GLSB_REAL, true>(p, S, F, s);
+  return q2::launch_flags<GLSB_REAL, GLSB_REAL, false>(p, S, F, s);
 #else
   (void)p, (void)sh, (void)F, (void)s;
   return -1;

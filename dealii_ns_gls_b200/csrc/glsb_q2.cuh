@@ -25,6 +25,7 @@
 #pragma once
 #include "glsb_kernels.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace glsb
 {
@@ -75,10 +76,133 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                : "memory");
 }
 
+// ---- register value types -------------------------------------------------------------------------------
+// V = T (double or float): one cell per lane.  V = F2 with T = float: TWO cells per lane (the same position
+// of two consecutive 32-cell batches) in one 64-bit register, arithmetic with the packed FP32 instructions of
+// sm_100 (add/mul/fma.f32x2 -> FADD2/FMUL2/FFMA2; ptxas contracts mul + add pairs into FFMA2).  The float
+// level operators of the multigrid (config.h:7) then need half the arithmetic and exchange instructions per
+// cell.
+struct F2
+{
+  unsigned long long v;
+};
+__host__ __device__ __forceinline__ F2 f2_pack(float lo, float hi)
+{
+  F2 r;
+#ifdef __CUDA_ARCH__
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+#else
+  uint32_t a, b;
+  memcpy(&a, &lo, 4);
+  memcpy(&b, &hi, 4);
+  r.v = (unsigned long long)a | ((unsigned long long)b << 32);
+#endif
+  return r;
+}
+__device__ __forceinline__ float f2_lo(F2 a) { return __uint_as_float((unsigned)(a.v & 0xffffffffull)); }
+__device__ __forceinline__ float f2_hi(F2 a) { return __uint_as_float((unsigned)(a.v >> 32)); }
+__device__ __forceinline__ F2 operator+(F2 a, F2 b)
+{
+  F2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+__device__ __forceinline__ F2 operator-(F2 a, F2 b)
+{
+  F2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+__device__ __forceinline__ F2 operator*(F2 a, F2 b)
+{
+  F2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+__device__ __forceinline__ F2 &operator+=(F2 &a, F2 b) { return a = a + b; }
+__device__ __forceinline__ F2 &operator*=(F2 &a, F2 b) { return a = a * b; }
+
+template <typename V, typename T>
+struct VOps // V == T
+{
+  static constexpr int VW = 1;
+  static __host__ __device__ __forceinline__ V bcast(T s) { return s; }
+  static __device__ __forceinline__ V          zero() { return V(0); }
+  // element `i` of the first batch's block; the second batch's block is `sb` elements further
+  static __device__ __forceinline__ V load(const T *base, int i, int) { return base[i]; }
+};
+template <>
+struct VOps<F2, float>
+{
+  static constexpr int VW = 2;
+  static __host__ __device__ __forceinline__ F2 bcast(float s) { return f2_pack(s, s); }
+  static __device__ __forceinline__ F2          zero()
+  {
+    F2 r;
+    r.v = 0ull;
+    return r;
+  }
+  static __device__ __forceinline__ F2 load(const float *base, int i, int sb) { return f2_pack(base[i], base[i + sb]); }
+};
+
+template <typename T>
+struct PackedOf
+{
+  using type = T;
+};
+template <>
+struct PackedOf<float>
+{
+  using type = F2;
+};
+// 1-D tables with every entry duplicated into both halves of the packed type
+template <typename T>
+static Shape<typename PackedOf<T>::type, 3> to_packed_shape(const Shape<T, 3> &s)
+{
+  using V = typename PackedOf<T>::type;
+  Shape<V, 3> r;
+  for (int i = 0; i < 9; ++i)
+    {
+      r.S[i]  = VOps<V, T>::bcast(s.S[i]);
+      r.D[i]  = VOps<V, T>::bcast(s.D[i]);
+      r.G[i]  = VOps<V, T>::bcast(s.G[i]);
+      r.Sw[i] = VOps<V, T>::bcast(s.Sw[i]);
+      r.Gw[i] = VOps<V, T>::bcast(s.Gw[i]);
+      r.Dt[i] = VOps<V, T>::bcast(s.Dt[i]);
+    }
+  for (int i = 0; i < 3; ++i)
+    r.w[i] = VOps<V, T>::bcast(s.w[i]);
+  return r;
+}
+
+// the value of cell v (0 or 1) held by a register value
+template <typename T>
+__device__ __forceinline__ T lane_value(T a, int)
+{
+  return a;
+}
+template <typename T>
+__device__ __forceinline__ T lane_value(F2 a, int v)
+{
+  return v == 0 ? f2_lo(a) : f2_hi(a);
+}
+
+// c ? a : b as a data select (a ternary on the F2 struct compiles to a branch)
+template <typename T>
+__device__ __forceinline__ T vsel(bool c, T a, T b)
+{
+  return c ? a : b;
+}
+__device__ __forceinline__ F2 vsel(bool c, F2 a, F2 b)
+{
+  F2 r;
+  r.v = c ? a.v : b.v;
+  return r;
+}
 template <typename T>
 __device__ __forceinline__ T sel3(int c, T a0, T a1, T a2)
 {
-  return c == 0 ? a0 : (c == 1 ? a1 : a2);
+  return vsel(c == 0, a0, vsel(c == 1, a1, a2));
 }
 
 // a ring stage holds ROWS rows (qz, qy) of 3 quadrature points: ROWS = 1 (9 stages per batch) or 3 (one
@@ -114,32 +238,48 @@ struct alignas(8) Pair<float>
 {
   float a, b;
 };
+template <>
+struct alignas(16) Pair<F2>
+{
+  F2 a, b;
+};
 
 // issue the bulk copy of stage j (row j % 9 of quadrature points of this CTA's batch j / 9) into ring slot
 // `slot`; called by one thread.  There is no producer warp: the slot is refilled by whichever warp is the
 // last to release it (an arrival counter per slot), so no warp ever waits for another one's progress.
-template <typename T, int ROWS>
+// A CTA works on units of VW consecutive batches (VW = 2 for the packed float kernel): a stage / an index
+// slot then holds the VW blocks one after the other.
+template <typename T, int ROWS, int VW>
 __device__ __forceinline__ void issue_stage(const KParams<T> &p, int F, T *tab, uint64_t *full, uint32_t j,
                                             uint32_t slot)
 {
   constexpr uint32_t SPB   = 9 / ROWS; // stages per batch
   const uint32_t     bytes = (uint32_t)(stage_elems<T, ROWS>(F) * sizeof(T));
-  const uint32_t     batch = blockIdx.x + (j / SPB) * gridDim.x, row = j % SPB;
-  const T *src = p.Q + (((uint64_t)((p.cell_begin >> 5) + batch) * SPB + row) * p.FT) * (3 * ROWS * CELLS);
+  const uint32_t     unit = blockIdx.x + (j / SPB) * gridDim.x, row = j % SPB;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  mbar_expect_tx(&full[slot], bytes);
-  bulk_g2s(tab + (size_t)slot * stage_elems<T, ROWS>(F), src, bytes, &full[slot]);
+  mbar_expect_tx(&full[slot], VW * bytes);
+#pragma unroll
+  for (int v = 0; v < VW; ++v)
+    {
+      const uint64_t batch = (uint64_t)(p.cell_begin >> 5) + (uint64_t)unit * VW + v;
+      const T       *src   = p.Q + ((batch * SPB + row) * p.FT) * (3 * ROWS * CELLS);
+      bulk_g2s(tab + ((size_t)slot * VW + v) * stage_elems<T, ROWS>(F), src, bytes, &full[slot]);
+    }
 }
 
-template <typename T, bool GENERAL, bool CTD, bool CELLWISE, int ROWS>
-__global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : GLSB_Q2_F64_CTAS))
-  k_vmult_q2_newton(const KParams<T> p, const Shape<T, 3> sh, const int F, const int nst)
+template <typename T, typename V, bool GENERAL, bool CTD, bool CELLWISE, int ROWS>
+__global__ void __launch_bounds__(TPB, (sizeof(V) == 4 ? GLSB_Q2_F32_CTAS : GLSB_Q2_F64_CTAS))
+  k_vmult_q2_newton(const KParams<T> p, const Shape<V, 3> sh, const int F, const int nst)
 {
+  using VO          = VOps<V, T>;
+  constexpr int VW  = VO::VW;
+  constexpr int ISL = VW * IDX_ELEMS;               // index ring slot: the blocks of the unit's VW batches
+  const int     SB  = (int)stage_elems<T, ROWS>(F); // table stage: offset of the second batch's block
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T        *tab   = reinterpret_cast<T *>(smem_raw);
-  T        *xch   = tab + nst * stage_elems<T, ROWS>(F);              // [warp][2][XSLOT]
-  uint32_t *ibuf  = reinterpret_cast<uint32_t *>(xch + (TPB / 32) * 2 * XSLOT); // [2][109][32] dof indices, flags
-  uint64_t *full  = reinterpret_cast<uint64_t *>(ibuf + 2 * IDX_ELEMS);
+  V        *xch   = reinterpret_cast<V *>(tab + nst * VW * stage_elems<T, ROWS>(F)); // [warp][2][XSLOT]
+  uint32_t *ibuf  = reinterpret_cast<uint32_t *>(xch + (TPB / 32) * 2 * XSLOT);      // [2][VW][109][32] indices, flags
+  uint64_t *full  = reinterpret_cast<uint64_t *>(ibuf + 2 * ISL);
   uint64_t *ifull = full + MAX_NST;
   uint32_t *cnt   = reinterpret_cast<uint32_t *>(ifull + 2); // [MAX_NST + 2] release counters (tables, indices)
 
@@ -150,7 +290,7 @@ __global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : GLSB
   // exchange rows: the pairs (components 0/1 and 2/3) of this lane's cell, and the element this lane owns
   const int      xp0 = 2 * (lane >> 2), xp1 = 2 * (8 + (((lane >> 2) + 4) & 7));
   const int      xpos = ((c >> 1) ? xp1 : xp0) + (c & 1);
-  T             *xw   = xch + warp * 2 * XSLOT;
+  V             *xw   = xch + warp * 2 * XSLOT;
   // column of this lane's cell in a 32-cell table row, for fields of component row 0, 1, 2 and cv
   const int      colr[4] = {col, (col + 4) & 31, (col + 8) & 31, (col + 4 * cv) & 31};
   // this lane's entries of an index block: dof (c, j) at ixo + j * CELLS, the cell's flag word at flo
@@ -169,7 +309,7 @@ __global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : GLSB
     }
   __syncthreads();
 
-  const uint32_t n_batches = (p.cell_end - p.cell_begin + CELLS - 1) / CELLS;
+  const uint32_t n_batches = ((p.cell_end - p.cell_begin + CELLS - 1) / CELLS + VW - 1) / VW; // units
   const uint32_t my_n      = (blockIdx.x < n_batches) ? (n_batches - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const uint32_t n_stages  = my_n * (9 / ROWS);
   if (my_n == 0)
@@ -178,10 +318,10 @@ __global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : GLSB
   // dof indices of batch bi of this CTA -> index ring slot bi & 1 (one bulk copy of 13.6 KB); one thread
   auto issue_idx = [&](uint32_t bi) {
     const uint32_t b     = bi & 1;
-    const uint32_t batch = (p.cell_begin >> 5) + blockIdx.x + bi * gridDim.x;
+    const uint64_t batch = (uint64_t)(p.cell_begin >> 5) + (uint64_t)(blockIdx.x + bi * gridDim.x) * VW;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(&ifull[b], IDX_ELEMS * 4);
-    bulk_g2s(ibuf + b * IDX_ELEMS, p.idx + (uint64_t)batch * IDX_ELEMS, IDX_ELEMS * 4, &ifull[b]);
+    mbar_expect_tx(&ifull[b], ISL * 4);
+    bulk_g2s(ibuf + b * ISL, p.idx + batch * IDX_ELEMS, ISL * 4, &ifull[b]); // consecutive batches are contiguous
   };
   // prologue: indices of the first two batches, all ring slots
   if (threadIdx.x == 0)
@@ -190,58 +330,75 @@ __global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : GLSB
       if (my_n > 1)
         issue_idx(1);
       for (uint32_t j = 0; j < (uint32_t)nst && j < n_stages; ++j)
-        issue_stage<T, ROWS>(p, F, tab, full, j, j);
+        issue_stage<T, ROWS, VW>(p, F, tab, full, j, j);
     }
 
-  const T  w = p.weight, nu = p.nu;
+  const V  w = VO::bcast(p.weight), nu = VO::bcast(p.nu);
   uint32_t it = 0, slot = 0, par = 0; // stage counter, its ring slot and phase parity
   for (uint32_t bi = 0; bi < my_n; ++bi)
     {
-      const uint32_t batch  = blockIdx.x + bi * gridDim.x;
-      const uint32_t cell0  = p.cell_begin + batch * CELLS;
-      const uint32_t cellr  = cell0 + col;
-      const bool     active = cell_active(p, cellr);
-      const uint32_t cell   = cellr < p.cell_end ? cellr : p.cell_end - 1;
-      const uint32_t *ixs   = ibuf + (bi & 1) * IDX_ELEMS + ixo;
-      // this batch's index block (dof indices + one flag word per cell); cells with constrained dofs are
+      const uint32_t unit   = blockIdx.x + bi * gridDim.x;
+      // this lane's cell(s): position `col` of batch unit * VW (and of the next batch for the packed kernel)
+      const uint32_t cellrA = p.cell_begin + (unit * VW) * CELLS + col, cellrB = cellrA + CELLS;
+      const bool     actA = cell_active(p, cellrA), actB = (VW == 2) && cell_active(p, cellrB);
+      const uint32_t cellA = cellrA < p.cell_end ? cellrA : p.cell_end - 1;
+      const uint32_t cellB = cellrB < p.cell_end ? cellrB : p.cell_end - 1;
+      const uint32_t *ixs   = ibuf + (bi & 1) * ISL + ixo;
+      // this unit's index block(s) (dof indices + one flag word per cell); cells with constrained dofs are
       // rare: one warp-uniform test instead of one per dof
       mbar_wait(&ifull[bi & 1], (bi >> 1) & 1);
-      const bool slow = __any_sync(0xffffffffu, ibuf[(bi & 1) * IDX_ELEMS + flo] != 0);
+      const bool slow = __any_sync(0xffffffffu, ibuf[(bi & 1) * ISL + flo] != 0 ||
+                                                  (VW == 2 && ibuf[(bi & 1) * ISL + IDX_ELEMS + flo] != 0));
 
       // ---- gather (read_dof_values) ------------------------------------------------------
-      T t[27];
+      V t[27];
       if (!slow)
         {
 #pragma unroll
           for (int j = 0; j < 27; ++j)
-            t[j] = p.src[ixs[j * CELLS]];
+            {
+              if (VW == 1)
+                t[j] = VO::load(p.src, ixs[j * CELLS], 0);
+              else
+                t[j] = VO::load(p.src, ixs[j * CELLS], (int)ixs[j * CELLS + IDX_ELEMS] - (int)ixs[j * CELLS]);
+            }
         }
       else
         {
 #pragma unroll
           for (int j = 0; j < 27; ++j)
-            t[j] = gather_resolved(p, p.src, ixs[j * CELLS]);
+            {
+              const T a = gather_resolved(p, p.src, ixs[j * CELLS]);
+              if (VW == 1)
+                t[j] = VO::load(&a, 0, 0);
+              else
+                {
+                  const T ab[2] = {a, gather_resolved(p, p.src, ixs[j * CELLS + IDX_ELEMS])};
+                  t[j]          = VO::load(ab, 0, 1);
+                }
+            }
         }
-      T ij0 = 0, ij1 = 0, ij2 = 0, cdet = 0;
+      const int cAB = (int)cellB - (int)cellA;
+      V ij0 = VO::zero(), ij1 = VO::zero(), ij2 = VO::zero(), cdet = VO::zero();
       if (!GENERAL)
         {
-          ij0  = p.inv_jac[cell];
-          ij1  = p.inv_jac[p.ncp + cell];
-          ij2  = p.inv_jac[2 * p.ncp + cell];
-          cdet = p.jxw[cell];
+          ij0  = VO::load(p.inv_jac, cellA, cAB);
+          ij1  = VO::load(p.inv_jac + p.ncp, cellA, cAB);
+          ij2  = VO::load(p.inv_jac + 2 * p.ncp, cellA, cAB);
+          cdet = VO::load(p.jxw, cellA, cAB);
         }
-      T d1c = 0, d2c = 0;
+      V d1c = VO::zero(), d2c = VO::zero();
       if (CELLWISE)
         {
-          d1c = p.d1c[cell];
-          d2c = p.d2c[cell];
+          d1c = VO::load(p.d1c, cellA, cAB);
+          d2c = VO::load(p.d2c, cellA, cAB);
         }
 
       // ---- interpolate to the quadrature points in x and y (registers only) --------------
 #pragma unroll
       for (int l = 0; l < 9; ++l)
         {
-          const T a = t[3 * l], b = t[3 * l + 1], d = t[3 * l + 2];
+          const V a = t[3 * l], b = t[3 * l + 1], d = t[3 * l + 2];
 #pragma unroll
           for (int q = 0; q < 3; ++q)
             t[3 * l + q] = sh.S[q * 3] * a + sh.S[q * 3 + 1] * b + sh.S[q * 3 + 2] * d;
@@ -251,62 +408,66 @@ __global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : GLSB
 #pragma unroll
         for (int i = 0; i < 3; ++i)
           {
-            const T a = t[i + 9 * k], b = t[i + 3 + 9 * k], d = t[i + 6 + 9 * k];
+            const V a = t[i + 9 * k], b = t[i + 3 + 9 * k], d = t[i + 6 + 9 * k];
 #pragma unroll
             for (int q = 0; q < 3; ++q)
               t[i + 3 * q + 9 * k] = sh.S[q * 3] * a + sh.S[q * 3 + 1] * b + sh.S[q * 3 + 2] * d;
           }
 
-      T acc[27];
+      V acc[27];
 #pragma unroll
       for (int j = 0; j < 27; ++j)
-        acc[j] = 0;
+        acc[j] = VO::zero();
 
       // ---- quadrature layers --------------------------------------------------------------
 #pragma unroll 1
       for (int qz = 0; qz < 3; ++qz)
         {
           // runtime (CTA-uniform) layer index: select from the constant bank instead of indexing it
-          const T sz0 = sel3<T>(qz, sh.S[0], sh.S[3], sh.S[6]), sz1 = sel3<T>(qz, sh.S[1], sh.S[4], sh.S[7]),
-                  sz2 = sel3<T>(qz, sh.S[2], sh.S[5], sh.S[8]);
-          const T gz0 = sel3<T>(qz, sh.G[0], sh.G[3], sh.G[6]), gz1 = sel3<T>(qz, sh.G[1], sh.G[4], sh.G[7]),
-                  gz2 = sel3<T>(qz, sh.G[2], sh.G[5], sh.G[8]);
+          const V sz0 = sel3<V>(qz, sh.S[0], sh.S[3], sh.S[6]), sz1 = sel3<V>(qz, sh.S[1], sh.S[4], sh.S[7]),
+                  sz2 = sel3<V>(qz, sh.S[2], sh.S[5], sh.S[8]);
+          const V gz0 = sel3<V>(qz, sh.G[0], sh.G[3], sh.G[6]), gz1 = sel3<V>(qz, sh.G[1], sh.G[4], sh.G[7]),
+                  gz2 = sel3<V>(qz, sh.G[2], sh.G[5], sh.G[8]);
           // test side: Cartesian cells carry the quadrature weights in the sweep matrices (Shape::Sw/Gw/Dt),
           // general cells get them with JxW from the table
-          const T wz  = sel3<T>(qz, sh.w[0], sh.w[1], sh.w[2]);
-          const T tz0 = GENERAL ? sz0 : sz0 * wz, tz1 = GENERAL ? sz1 : sz1 * wz, tz2 = GENERAL ? sz2 : sz2 * wz;
-          const T hz0 = GENERAL ? gz0 : gz0 * wz, hz1 = GENERAL ? gz1 : gz1 * wz, hz2 = GENERAL ? gz2 : gz2 * wz;
-          T       vl[9], wl[9];
+          const V wz  = sel3<V>(qz, sh.w[0], sh.w[1], sh.w[2]);
+          V tz0 = sz0, tz1 = sz1, tz2 = sz2, hz0 = gz0, hz1 = gz1, hz2 = gz2;
+          if (!GENERAL)
+            {
+              tz0 = sz0 * wz, tz1 = sz1 * wz, tz2 = sz2 * wz;
+              hz0 = gz0 * wz, hz1 = gz1 * wz, hz2 = gz2 * wz;
+            }
+          V       vl[9], wl[9];
 #pragma unroll
           for (int a = 0; a < 9; ++a)
             {
               vl[a] = sz0 * t[a] + sz1 * t[a + 9] + sz2 * t[a + 18];
-              wl[a] = 0;
+              wl[a] = VO::zero();
             }
-          const T *tb = nullptr;
+          const T *tb = nullptr; // first batch's block of the stage; the second one is SB elements further
 #pragma unroll
           for (int qy = 0; qy < 3; ++qy)
             {
               if (qy % ROWS == 0)
                 {
                   mbar_wait(&full[slot], par);
-                  tb = tab + (size_t)slot * stage_elems<T, ROWS>(F);
+                  tb = tab + (size_t)slot * VW * SB;
                 }
               constexpr int QPS = 3 * ROWS;
               const int     qlo = (qy % ROWS) * 3; // first point of this row inside the stage
-#define GLSB_TAB(f, x) tb[((f)*QPS + qlo + (x)) * CELLS + col]          /* fields without a component row */
-#define GLSB_TABR(f, x, r) tb[((f)*QPS + qlo + (x)) * CELLS + colr[r]] /* rotated by 4 * row, see qoff() */
+#define GLSB_TAB(f, x) VO::load(tb, ((f)*QPS + qlo + (x)) * CELLS + col, SB)          /* fields without a component row */
+#define GLSB_TABR(f, x, r) VO::load(tb, ((f)*QPS + qlo + (x)) * CELLS + colr[r], SB) /* rotated by 4 * row, see qoff() */
 #pragma unroll
               for (int qx = 0; qx < 3; ++qx)
                 {
                   const int a   = 3 * qy + qx;
-                  const T   val = vl[a];
-                  const T rx = sh.D[qx * 3] * vl[3 * qy] + sh.D[qx * 3 + 1] * vl[3 * qy + 1] + sh.D[qx * 3 + 2] * vl[3 * qy + 2];
-                  const T ry = sh.D[qy * 3] * vl[qx] + sh.D[qy * 3 + 1] * vl[qx + 3] + sh.D[qy * 3 + 2] * vl[qx + 6];
-                  const T rz = gz0 * t[a] + gz1 * t[a + 9] + gz2 * t[a + 18];
+                  const V   val = vl[a];
+                  const V rx = sh.D[qx * 3] * vl[3 * qy] + sh.D[qx * 3 + 1] * vl[3 * qy + 1] + sh.D[qx * 3 + 2] * vl[3 * qy + 2];
+                  const V ry = sh.D[qy * 3] * vl[qx] + sh.D[qy * 3 + 1] * vl[qx + 3] + sh.D[qy * 3 + 2] * vl[qx + 6];
+                  const V rz = gz0 * t[a] + gz1 * t[a + 9] + gz2 * t[a + 18];
                   // geometry: physical gradient of this lane's component
-                  T g0, g1, g2, jq = 0;
-                  T J00, J01, J02, J10, J11, J12, J20, J21, J22;
+                  V g0, g1, g2, jq = VO::zero();
+                  V J00, J01, J02, J10, J11, J12, J20, J21, J22;
                   if (GENERAL)
                     {
                       J00 = GLSB_TAB(p.fJ + 0, qx), J01 = GLSB_TAB(p.fJ + 1, qx), J02 = GLSB_TAB(p.fJ + 2, qx);
@@ -322,64 +483,71 @@ __global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : GLSB
                       g0 = rx * ij0, g1 = ry * ij1, g2 = rz * ij2;
                     }
                   // ---- exchange round 1: publish value and gradient of this component --------------
-                  T *xs = xw + (a & 1) * XSLOT;
+                  V *xs = xw + (a & 1) * XSLOT;
                   xs[xpos]            = val;
                   xs[XROW + xpos]     = g0;
                   xs[2 * XROW + xpos] = g1;
                   xs[3 * XROW + xpos] = g2;
                   // tables (field offsets of the prefix are fixed: U 0..2, grad U 3..11, grad P 12..14)
-                  const T U0 = GLSB_TABR(0, qx, 0), U1 = GLSB_TABR(1, qx, 1), U2 = GLSB_TABR(2, qx, 2);
-                  const T H0 = GLSB_TABR(3 + 3 * cv, qx, 3), H1 = GLSB_TABR(4 + 3 * cv, qx, 3),
+                  const V U0 = GLSB_TABR(0, qx, 0), U1 = GLSB_TABR(1, qx, 1), U2 = GLSB_TABR(2, qx, 2);
+                  const V H0 = GLSB_TABR(3 + 3 * cv, qx, 3), H1 = GLSB_TABR(4 + 3 * cv, qx, 3),
                           H2 = GLSB_TABR(5 + 3 * cv, qx, 3);
-                  const T Pc = GLSB_TABR(12 + cv, qx, 3);
-                  const T d1 = CELLWISE ? d1c : GLSB_TAB(p.fd1q, qx);
-                  const T d2 = CELLWISE ? d2c : GLSB_TAB(p.fd2q, qx);
+                  const V Pc = GLSB_TABR(12 + cv, qx, 3);
+                  const V d1 = CELLWISE ? d1c : GLSB_TAB(p.fd1q, qx);
+                  const V d2 = CELLWISE ? d2c : GLSB_TAB(p.fd2q, qx);
                   __syncwarp();
-                  const Pair<T> u01 = *reinterpret_cast<const Pair<T> *>(xs + xp0),
-                                u2p = *reinterpret_cast<const Pair<T> *>(xs + xp1);
-                  const T u0 = u01.a, u1 = u01.b, u2 = u2p.a, pp = u2p.b;
-                  const T div = xs[XROW + xp0] + xs[2 * XROW + xp0 + 1] + xs[3 * XROW + xp1];
+                  const Pair<V> u01 = *reinterpret_cast<const Pair<V> *>(xs + xp0),
+                                u2p = *reinterpret_cast<const Pair<V> *>(xs + xp1);
+                  const V u0 = u01.a, u1 = u01.b, u2 = u2p.a, pp = u2p.b;
+                  const V div = xs[XROW + xp0] + xs[2 * XROW + xp0 + 1] + xs[3 * XROW + xp1];
                   // column c of grad u and d_c p: row (1 + c), the 4 elements of this cell
-                  const T      *xc  = xs + (1 + cv) * XROW;
-                  const Pair<T> G01 = *reinterpret_cast<const Pair<T> *>(xc + xp0),
-                                G2p = *reinterpret_cast<const Pair<T> *>(xc + xp1);
-                  const T Gc0 = G01.a, Gc1 = G01.b, Gc2 = G2p.a, gpc = G2p.b;
-                  const T  td  = val * w;
-                  const T  sgu = g0 * U0 + g1 * U1 + g2 * U2; // U . grad u_c
-                  const T  ugs = H0 * u0 + H1 * u1 + H2 * u2; // u . grad U_c
-                  T        y   = sgu + ugs;
+                  const V      *xc  = xs + (1 + cv) * XROW;
+                  const Pair<V> G01 = *reinterpret_cast<const Pair<V> *>(xc + xp0),
+                                G2p = *reinterpret_cast<const Pair<V> *>(xc + xp1);
+                  const V Gc0 = G01.a, Gc1 = G01.b, Gc2 = G2p.a, gpc = G2p.b;
+                  const V  td  = val * w;
+                  const V  sgu = g0 * U0 + g1 * U1 + g2 * U2; // U . grad u_c
+                  const V  ugs = H0 * u0 + H1 * u1 + H2 * u2; // u . grad U_c
+                  V        y   = sgu + ugs;
                   if (CTD)
                     y = td + y;
                   // velocity row c: SUPG residual of the increment, delta_1 (y + d_c p)
-                  const T r0  = d1 * (y + gpc);
+                  const V r0  = d1 * (y + gpc);
                   // ---- exchange round 2: the pressure row is (grad q, residual_0): it needs r0 of the three
                   // velocity rows (operator_ns.cc:1166-1172), published as they are
                   xs[4 * XROW + xpos] = r0;
-                  const T sgs = H0 * U0 + H1 * U1 + H2 * U2; // U . grad U_c
-                  T       rb  = Pc + sgs;
+                  const V sgs = H0 * U0 + H1 * U1 + H2 * U2; // U . grad U_c
+                  V       rb  = Pc + sgs;
                   if (CTD)
                     rb = (GLSB_TABR(cv, qx, 3) * w + GLSB_TABR(p.fO + cv, qx, 3)) + rb;
-                  const T rr1  = d1 * rb;
-                  const T diag = d2 * div - pp;
-                  T       vo   = td + sgu + ugs;
-                  T       o0   = nu * (g0 + Gc0) + U0 * r0 + u0 * rr1 + (c == 0 ? diag : T(0));
-                  T       o1   = nu * (g1 + Gc1) + U1 * r0 + u1 * rr1 + (c == 1 ? diag : T(0));
-                  T       o2   = nu * (g2 + Gc2) + U2 * r0 + u2 * rr1 + (c == 2 ? diag : T(0));
+                  const V rr1  = d1 * rb;
+                  const V diag = d2 * div - pp;
+                  V       vo   = td + sgu + ugs;
+                  V       o0   = nu * (g0 + Gc0) + U0 * r0 + u0 * rr1 + vsel(c == 0, diag, VO::zero());
+                  V       o1   = nu * (g1 + Gc1) + U1 * r0 + u1 * rr1 + vsel(c == 1, diag, VO::zero());
+                  V       o2   = nu * (g2 + Gc2) + U2 * r0 + u2 * rr1 + vsel(c == 2, diag, VO::zero());
                   __syncwarp();
                   // pressure row: (q, div u) and (grad q, residual_0)
-                  const Pair<T> r01 = *reinterpret_cast<const Pair<T> *>(xs + 4 * XROW + xp0);
-                  vo = is_p ? div : vo;
-                  o0 = is_p ? r01.a : o0;
-                  o1 = is_p ? r01.b : o1;
-                  o2 = is_p ? xs[4 * XROW + xp1] : o2;
+                  const Pair<V> r01 = *reinterpret_cast<const Pair<V> *>(xs + 4 * XROW + xp0);
+                  vo = vsel(is_p, div, vo);
+                  o0 = vsel(is_p, r01.a, o0);
+                  o1 = vsel(is_p, r01.b, o1);
+                  o2 = vsel(is_p, xs[4 * XROW + xp1], o2);
                   // submit_value / submit_gradient: times JxW, back to the reference cell
-                  T ox, oy, oz;
+                  V ox, oy, oz;
                   if (GENERAL)
                     {
-                      vo *= jq;
-                      ox = (J00 * o0 + J01 * o1 + J02 * o2) * jq;
-                      oy = (J10 * o0 + J11 * o1 + J12 * o2) * jq;
-                      oz = (J20 * o0 + J21 * o1 + J22 * o2) * jq;
+                      // at the 255-register limit (FP64): JxW and one row of J^-1 are read again here
+                      // instead of being kept in 8 registers across the physics
+                      constexpr bool RELOAD = sizeof(V) == 8 && VW == 1;
+                      const V        jw = RELOAD ? GLSB_TAB(p.fjxw, qx) : jq;
+                      vo *= jw;
+                      if (RELOAD)
+                        ox = (GLSB_TAB(p.fJ + 0, qx) * o0 + GLSB_TAB(p.fJ + 1, qx) * o1 + GLSB_TAB(p.fJ + 2, qx) * o2) * jw;
+                      else
+                        ox = (J00 * o0 + J01 * o1 + J02 * o2) * jw;
+                      oy = (J10 * o0 + J11 * o1 + J12 * o2) * jw;
+                      oz = (J20 * o0 + J21 * o1 + J22 * o2) * jw;
                     }
                   else
                     {
@@ -410,7 +578,7 @@ __global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : GLSB
                         {
                           cnt[slot] = 0;
                           if (it + nst < n_stages)
-                            issue_stage<T, ROWS>(p, F, tab, full, it + nst, slot);
+                            issue_stage<T, ROWS, VW>(p, F, tab, full, it + nst, slot);
                         }
                     }
                   ++it;
@@ -436,7 +604,7 @@ __global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : GLSB
 #pragma unroll
         for (int i = 0; i < 3; ++i)
           {
-            const T a = acc[i + 9 * k], b = acc[i + 3 + 9 * k], d = acc[i + 6 + 9 * k];
+            const V a = acc[i + 9 * k], b = acc[i + 3 + 9 * k], d = acc[i + 6 + 9 * k];
 #pragma unroll
             for (int q = 0; q < 3; ++q)
               acc[i + 3 * q + 9 * k] = GENERAL ? sh.S[q] * a + sh.S[3 + q] * b + sh.S[6 + q] * d :
@@ -445,7 +613,7 @@ __global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : GLSB
 #pragma unroll
       for (int l = 0; l < 9; ++l)
         {
-          const T a = acc[3 * l], b = acc[3 * l + 1], d = acc[3 * l + 2];
+          const V a = acc[3 * l], b = acc[3 * l + 1], d = acc[3 * l + 2];
 #pragma unroll
           for (int q = 0; q < 3; ++q)
             acc[3 * l + q] = GENERAL ? sh.S[q] * a + sh.S[3 + q] * b + sh.S[6 + q] * d :
@@ -459,21 +627,28 @@ __global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : GLSB
         }
 
       // ---- scatter (distribute_local_to_global) ------------------------------------------
-      if (active)
-        {
-          if (!slow)
-            {
 #pragma unroll
-              for (int j = 0; j < 27; ++j)
-                atomic_add(p.dst + ixs[j * CELLS], acc[j]);
-            }
-          else
-            {
+      for (int v = 0; v < VW; ++v)
+        if (v == 0 ? actA : actB)
+          {
+            const uint32_t *ix = ixs + v * IDX_ELEMS;
+            T               r[27];
 #pragma unroll
-              for (int j = 0; j < 27; ++j)
-                scatter_resolved(p, p.dst, ixs[j * CELLS], acc[j]);
-            }
-        }
+            for (int j = 0; j < 27; ++j)
+              r[j] = lane_value<T>(acc[j], v);
+            if (!slow)
+              {
+#pragma unroll
+                for (int j = 0; j < 27; ++j)
+                  atomic_add(p.dst + ix[j * CELLS], r[j]);
+              }
+            else
+              {
+#pragma unroll
+                for (int j = 0; j < 27; ++j)
+                  scatter_resolved(p, p.dst, ix[j * CELLS], r[j]);
+              }
+          }
       // release the index ring slot; the last warp refills it with the block two batches ahead
       __syncwarp();
       if (lane == 0)
@@ -488,32 +663,33 @@ __global__ void __launch_bounds__(TPB, (sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : GLSB
     }
 }
 
-template <typename T, int ROWS>
+template <typename T, int ROWS, int VW>
 size_t smem_bytes(int F, int nst)
 {
-  return (nst * stage_elems<T, ROWS>(F) + (TPB / 32) * 2 * XSLOT) * sizeof(T) +
-         2 * IDX_ELEMS * 4 + (MAX_NST + 2) * (sizeof(uint64_t) + sizeof(uint32_t));
+  return nst * VW * stage_elems<T, ROWS>(F) * sizeof(T) + (size_t)(TPB / 32) * 2 * XSLOT * (VW * sizeof(T)) +
+         2 * VW * IDX_ELEMS * 4 + (MAX_NST + 2) * (sizeof(uint64_t) + sizeof(uint32_t));
 }
 
 // ring depth: 2 stages of a whole layer; with row stages as deep as the target occupancy allows (<= 4)
-template <typename T, int ROWS>
+template <typename T, int ROWS, int VW>
 int ring_depth(int F)
 {
-  const int ctas = sizeof(T) == 4 ? GLSB_Q2_F32_CTAS : GLSB_Q2_F64_CTAS;
+  const int ctas = (VW * sizeof(T) == 4) ? GLSB_Q2_F32_CTAS : GLSB_Q2_F64_CTAS;
   int       nst  = 2;
-  while (ROWS == 1 && nst < 4 && ctas * (smem_bytes<T, ROWS>(F, nst + 1) + 1024) <= 228 * 1024)
+  while (ROWS == 1 && nst < 4 && ctas * (smem_bytes<T, ROWS, VW>(F, nst + 1) + 1024) <= 228 * 1024)
     ++nst;
   return nst;
 }
 
-template <typename T, bool GENERAL, bool CTD, bool CELLWISE, int ROWS>
-static int launch_rows(const KParams<T> &p, const Shape<T, 3> &S, int F, cudaStream_t s)
+template <typename T, typename V, bool GENERAL, bool CTD, bool CELLWISE, int ROWS>
+static int launch_rows(const KParams<T> &p, const Shape<V, 3> &S, int F, cudaStream_t s)
 {
+  constexpr int VW = VOps<V, T>::VW;
   static int   n_sm = 0;
   static const int env_nst = getenv("GLSB_Q2_NST") ? atoi(getenv("GLSB_Q2_NST")) : 0;
-  const int    nst  = env_nst >= 2 && env_nst <= MAX_NST ? env_nst : ring_depth<T, ROWS>(F);
-  const size_t smem = smem_bytes<T, ROWS>(F, nst);
-  auto         kern = k_vmult_q2_newton<T, GENERAL, CTD, CELLWISE, ROWS>;
+  const int    nst  = env_nst >= 2 && env_nst <= MAX_NST ? env_nst : ring_depth<T, ROWS, VW>(F);
+  const size_t smem = smem_bytes<T, ROWS, VW>(F, nst);
+  auto         kern = k_vmult_q2_newton<T, V, GENERAL, CTD, CELLWISE, ROWS>;
   if (smem > 227 * 1024)
     return -1;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -527,27 +703,27 @@ static int launch_rows(const KParams<T> &p, const Shape<T, 3> &S, int F, cudaStr
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     }
-  const uint32_t n_batches = (p.cell_end - p.cell_begin + CELLS - 1) / CELLS;
-  const int      use_sm    = (p.sm_reserve > 0 && p.sm_reserve < n_sm) ? n_sm - p.sm_reserve : n_sm;
-  const uint32_t grid      = n_batches < (uint32_t)(use_sm * bps) ? n_batches : (uint32_t)(use_sm * bps);
+  const uint32_t n_units = ((p.cell_end - p.cell_begin + CELLS - 1) / CELLS + VW - 1) / VW;
+  const int      use_sm  = (p.sm_reserve > 0 && p.sm_reserve < n_sm) ? n_sm - p.sm_reserve : n_sm;
+  const uint32_t grid    = n_units < (uint32_t)(use_sm * bps) ? n_units : (uint32_t)(use_sm * bps);
   kern<<<grid, TPB, smem, s>>>(p, S, F, nst);
   return cudaGetLastError() != cudaSuccess;
 }
 
-template <typename T, bool GENERAL, bool CTD, bool CELLWISE>
-static int launch(const KParams<T> &p, const Shape<T, 3> &S, int F, cudaStream_t s)
+template <typename T, typename V, bool GENERAL, bool CTD, bool CELLWISE>
+static int launch(const KParams<T> &p, const Shape<V, 3> &S, int F, cudaStream_t s)
 {
   if (p.QG == 9)
-    return launch_rows<T, GENERAL, CTD, CELLWISE, 3>(p, S, F, s);
-  return launch_rows<T, GENERAL, CTD, CELLWISE, 1>(p, S, F, s);
+    return launch_rows<T, V, GENERAL, CTD, CELLWISE, 3>(p, S, F, s);
+  return launch_rows<T, V, GENERAL, CTD, CELLWISE, 1>(p, S, F, s);
 }
 
-template <typename T, bool GENERAL>
-static int launch_flags(const KParams<T> &p, const Shape<T, 3> &S, int F, cudaStream_t s)
+template <typename T, typename V, bool GENERAL>
+static int launch_flags(const KParams<T> &p, const Shape<V, 3> &S, int F, cudaStream_t s)
 {
   if (p.ctd)
-    return p.cell_wise ? launch<T, GENERAL, true, true>(p, S, F, s) : launch<T, GENERAL, true, false>(p, S, F, s);
-  return p.cell_wise ? launch<T, GENERAL, false, true>(p, S, F, s) : launch<T, GENERAL, false, false>(p, S, F, s);
+    return p.cell_wise ? launch<T, V, GENERAL, true, true>(p, S, F, s) : launch<T, V, GENERAL, true, false>(p, S, F, s);
+  return p.cell_wise ? launch<T, V, GENERAL, false, true>(p, S, F, s) : launch<T, V, GENERAL, false, false>(p, S, F, s);
 }
 
 } // namespace q2

@@ -341,3 +341,18 @@ def test_relaxation_smoother_on_device(dim, degree, kind, number):
     l0 = gpu.launch_count()
     sm.vmult(x, b)
     assert gpu.launch_count() - l0 >= 2 * sm.n_iterations - 1  # 4 x (cells + update) + first sweep
+
+
+@pytest.mark.parametrize("kind,ctd,cell_wise", [("cube", False, True), ("shell", True, False)])
+def test_q2_packed_float_kernel(kind, ctd, cell_wise, monkeypatch):
+    """Opt-in packed FP32 variant of the Q2 kernel (two cells per lane, FFMA2; GLSB_Q2_PACK=1): same
+    result as the oracle, odd and even numbers of 32-cell batches, with Dirichlet rows."""
+    monkeypatch.setenv("GLSB_Q2_PACK", "1")
+    for shape in ((5, 5, 5), (4, 4, 6)) if kind == "cube" else ((3, 7, 3), (2, 8, 2)):
+        mesh = gm.hypercube(3, shape, 2) if kind == "cube" else gm.cylinder_shell(shape, 2)
+        ti = TI(2, [15.0, -20.0, 5.0], 0.1)
+        ora, gpu, src, _ = _setup(mesh, ti, "float", ctd=ctd, cell_wise=cell_wise, nu=0.01)
+        dst = gpu.initialize_dof_vector()
+        gpu.vmult(dst, _to_dev(src, "float"))
+        assert gpu.vmult_variant() == "q2_regtile_tma"
+        assert rel_l2(dst.cpu().numpy(), ora.vmult(src, 15.0)) < TOL["float"]
