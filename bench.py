@@ -193,6 +193,19 @@ def shell_shape(args):
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
+def _bind_to_gpu_numa_node(index):
+    """Run this rank on the CPUs next to its GPU (NVML's ideal affinity) before any pinned host memory is
+    allocated: with one rank per GPU on a two-socket box the page-locked vectors of the end-to-end leg are
+    otherwise first-touched on whatever node the process happens to start on."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+    except Exception:
+        pass
+
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -209,6 +222,7 @@ def run_gpu(args):
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    _bind_to_gpu_numa_node(local_rank)
     exchange = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
