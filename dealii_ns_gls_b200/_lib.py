@@ -35,6 +35,18 @@ class GlsbDesc(C.Structure):
     ]
 
 
+class GlsbTransferDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("device", C.c_int32), ("dim", C.c_int32), ("degree", C.c_int32),
+        ("number_type", C.c_int32),
+        ("n_coarse_cells", C.c_uint64), ("n_fine_dofs", C.c_uint64), ("n_coarse_dofs", C.c_uint64),
+        ("coarse_dof_indices", C.c_void_p), ("fine_dof_indices", C.c_void_p),
+        ("n_constraint_rows", C.c_uint32),
+        ("row_ptr", C.c_void_p), ("entry_col", C.c_void_p), ("entry_val", C.c_void_p),
+        ("weights", C.c_void_p),
+    ]
+
+
 # every symbol include/glsb200.h declares: name -> (restype, argtypes)
 _P, _D, _I, _U64 = C.c_void_p, C.c_double, C.c_int, C.c_uint64
 SYMBOLS = {
@@ -68,6 +80,18 @@ SYMBOLS = {
     "glsb_relaxation_step": (_I, [_P, _P, _P, _P, _D, _I, _D, _P]),
     "glsb_relaxation_update": (_I, [_P, _P, _P, _P, _P, _D, _P]),
     "glsb_estimate_relaxation": (_I, [_P, _P, _I, _D, _D, _U64, C.POINTER(_D), C.POINTER(_D), _P]),
+    "glsb_transfer_create": (_I, [C.POINTER(GlsbTransferDesc), C.POINTER(_P)]),
+    "glsb_transfer_destroy": (None, [_P]),
+    "glsb_transfer_last_error": (C.c_char_p, [_P]),
+    "glsb_transfer_prolongate_and_add": (_I, [_P, _P, _P, _P]),
+    "glsb_transfer_restrict_and_add": (_I, [_P, _P, _P, _P]),
+    "glsb_transfer_interpolate": (_I, [_P, _P, _P, _P]),
+    "glsb_vec_multi_dot": (_I, [_P, _P, _U64, _I, _P, _U64, _I, _P]),
+    "glsb_vec_multi_axpy": (_I, [_P, _P, _U64, _I, _P, _D, _U64, _I, _P]),
+    "glsb_vec_axpby": (_I, [_P, _D, _P, _D, _U64, _I, _P]),
+    "glsb_vec_convert": (_I, [_P, _I, _P, _I, _U64, _P]),
+    "glsb_vec_set_zero_indexed": (_I, [_P, _P, _U64, _I, _P]),
+    "glsb_dense_apply": (_I, [_P, _P, _P, C.c_uint32, C.c_uint32, _I, _P]),
     "glsb_pack_export": (_I, [_P, _P, _P, _P]),
     "glsb_unpack_add": (_I, [_P, _P, _P, _P]),
     "glsb_n_cells": (_U64, [_P]),

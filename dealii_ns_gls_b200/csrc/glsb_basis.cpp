@@ -146,4 +146,34 @@ void compute_shape_host(int degree, ShapeHost &out)
     }
 }
 
+// 1-D matrices of the two-level transfer between a cell and its two children per direction
+// (what deal.II's MGTwoLevelTransfer takes from FE_Q::get_prolongation_matrix / get_restriction_matrix):
+//   P[a][l][j] = phi^coarse_j((x_l + a) / 2)              value of coarse basis j at node l of child a
+//   R[j][l]    = phi^fine_l(2 x_j - rchild[j])            interpolation: fine function of child rchild[j]
+//                                                         evaluated at coarse node j
+void compute_transfer_host(int degree, double *P, double *R, int *rchild)
+{
+  const int n = degree + 1;
+  ld        nodes[MAX_N];
+  gauss_lobatto(degree, nodes);
+  for (int i = 0; i < n; ++i)
+    nodes[i] = 0.5L * (nodes[i] + 1);
+  ld v[MAX_N], d[MAX_N];
+  for (int a = 0; a < 2; ++a)
+    for (int l = 0; l < n; ++l)
+      {
+        lagrange(n, nodes, (nodes[l] + a) / 2, v, d);
+        for (int j = 0; j < n; ++j)
+          P[(a * n + l) * n + j] = (fabsl(v[j]) < 1e-17L) ? 0.0 : (double)v[j];
+      }
+  for (int j = 0; j < n; ++j)
+    {
+      const int a = (nodes[j] <= 0.5L) ? 0 : 1; // x = 1/2 belongs to both children (same value: continuity)
+      rchild[j]   = a;
+      lagrange(n, nodes, 2 * nodes[j] - a, v, d);
+      for (int l = 0; l < n; ++l)
+        R[j * n + l] = (fabsl(v[l]) < 1e-17L) ? 0.0 : (double)v[l];
+    }
+}
+
 } // namespace glsb

@@ -34,6 +34,8 @@ struct ShapeHost
   double nodes[MAX_N];
 };
 void compute_shape_host(int degree, ShapeHost &out);
+// P[2][n][n], R[n][n], rchild[n]: two-level transfer matrices (glsb_basis.cpp)
+void compute_transfer_host(int degree, double *P, double *R, int *rchild);
 
 enum Branch : int
 {

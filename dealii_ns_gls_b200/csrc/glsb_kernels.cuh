@@ -10,6 +10,10 @@
 #include "glsb_common.h"
 #include "../../include/glsb200.h"
 
+#ifndef GLSB_GEN_CTAS
+#define GLSB_GEN_CTAS 2 // resident CTAs per SM the generic vmult kernel is compiled for (3 measured slower: spills)
+#endif
+
 namespace glsb
 {
 template <int dim, int n>
@@ -516,7 +520,7 @@ __device__ __forceinline__ void cell_apply(Ctx<dim, n, T> &ctx, const KParams<T>
 }
 
 template <int dim, int n, typename T, int BR>
-__global__ void __launch_bounds__(Geo<dim, n>::THREADS) k_vmult_generic(const KParams<T> p, const Shape<T, n> sh)
+__global__ void __launch_bounds__(Geo<dim, n>::THREADS, GLSB_GEN_CTAS) k_vmult_generic(const KParams<T> p, const Shape<T, n> sh)
 {
   using G = Geo<dim, n>;
   extern __shared__ __align__(16) unsigned char smem[];

@@ -1,0 +1,217 @@
+"""The wiring of the reference's Driver<dim>::run (main.cc:220-1000) around the device operator, for the
+synthetic structured meshes of mesh.py: constraints (main.cc:258-310), fine operator (:326-348), the
+global-coarsening hierarchy with level operators and the two transfer objects (:396-568), the solver hooks
+(:772-869) and the time loop (:908-990).  Used by the tests (iteration counts against the CPU oracle) and by
+``bench.py --workload step`` (wall time per time step); it is the *caller* of the hot path, kept as close to
+the reference's control flow as the synthetic setting allows.  Only the channel simulation
+(simulation.cc:143-189, input/input_channel.json) is described here.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .mesh import Mesh, dof_components, dof_coordinates, structured_mesh
+from .multigrid import (DeviceVectorOps, MGTransferGlobalCoarsening, MGTwoLevelTransfer, PreconditionerGMG,
+                        PreconditionerGMGAdditionalData)
+from .operator import AffineConstraints, NavierStokesOperator
+from .solvers import LinearSolverGMRES, NonLinearSolverNewton
+from .time_integration import SolutionHistory, TimeIntegratorDataBDF, TimeIntegratorDataNone
+
+
+class ChannelParameters:
+    """input/input_channel.json + the defaults of main.cc:66-192 that the device path reads."""
+
+    def __init__(self, **kw):
+        self.dim = 2
+        self.fe_degree = 1
+        self.n_global_refinements = 2
+        self.cfl = 0.1
+        self.dt = 0.0
+        self.bdf_order = 1
+        self.time_integration = "bdf"
+        self.c_1, self.c_2, self.nu = 2.0, 1.0, 0.0
+        self.consider_time_derivative = True
+        self.cell_wise_stabilization = True
+        self.lin_n_max_iterations = 10000
+        self.lin_absolute_tolerance = 1e-12
+        self.lin_relative_tolerance = 1e-2
+        self.newton_inexact = False
+        self.mg_number = "float"      # config.h:7
+        self.n_stretching = 4         # simulation.cc:143-145
+        self.gmg = PreconditionerGMGAdditionalData()
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise TypeError(f"unknown parameter {k}")
+            setattr(self, k, v)
+
+
+def channel_level_mesh(params: ChannelParameters, level: int) -> Mesh:
+    """SimulationChannel::create_triangulation (simulation.cc:150-170): n_stretching x 1 (x 1) unit blocks,
+    refined `level` times; boundary ids 0/1 = x faces, 2/3 = y, 4/5 = z (colorize = true).  The zero
+    constraints are constraints_homogeneous of main.cc:258-305: no-slip walls (ids >= 2), the inflow face
+    (id 0) for the velocity, pressure = 0 on the outflow face (id 1)."""
+    dim, ns = params.dim, params.n_stretching
+    shape = (ns * 2 ** level,) + (2 ** level,) * (dim - 1)
+    extent = (float(ns),) + (1.0,) * (dim - 1)
+    eps = 1e-12
+
+    def zero_constrained(x, c):
+        if c == dim:
+            return np.abs(x[:, 0] - extent[0]) < eps
+        m = np.abs(x[:, 0]) < eps
+        for e in range(1, dim):
+            m |= (np.abs(x[:, e]) < eps) | (np.abs(x[:, e] - 1.0) < eps)
+        return m
+
+    return structured_mesh(dim, shape, params.fe_degree, extent=extent, dirichlet=zero_constrained)
+
+
+def channel_inhomogeneous_constraints(params: ChannelParameters, mesh: Mesh) -> AffineConstraints:
+    """constraints_inhomogeneous of the time loop (main.cc:877-895): the zero constraints of the walls and the
+    outflow pressure, plus u = (1, 0, 0) on the inflow face where no wall constraint exists yet
+    (InflowBoundaryValues::Channel(0, 1), simulation.cc:176-177)."""
+    dim = params.dim
+    x, comp = dof_coordinates(mesh), dof_components(mesh)
+    eps = 1e-12
+    wall = np.zeros(mesh.n_dofs, dtype=bool)
+    for e in range(1, dim):
+        wall |= (np.abs(x[:, e]) < eps) | (np.abs(x[:, e] - 1.0) < eps)
+    rows, inhom = {}, {}
+    for d in mesh.constraints:
+        rows[d] = []
+        if comp[d] == 0 and abs(x[d, 0]) < eps and not wall[d]:
+            inhom[d] = 1.0
+    return AffineConstraints(rows, inhom)
+
+
+class Driver:
+    """Driver<dim>::run for the channel with "preconditioner": "GMG", "nonlinear solver": "Newton"."""
+
+    def __init__(self, params: ChannelParameters, device=None, verbose=False):
+        self.params, self.verbose = params, verbose
+        p = params
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        n_levels = 2 + p.n_global_refinements  # refine_global(2) + n (simulation.cc:166-169)
+        self.meshes = {l: channel_level_mesh(p, l) for l in range(n_levels + 1)}
+        self.minlevel, self.maxlevel = 0, n_levels
+        fine = self.meshes[self.maxlevel]
+        if p.time_integration == "bdf":
+            self.time_integrator_data = TimeIntegratorDataBDF(p.bdf_order)
+        elif p.time_integration == "none":
+            self.time_integrator_data = TimeIntegratorDataNone()
+        else:
+            raise NotImplementedError(p.time_integration)
+        tid = self.time_integrator_data
+        self.constraints_inhomogeneous = channel_inhomogeneous_constraints(p, fine)
+        increment_form = True  # Newton (main.cc:331)
+        # main.cc:333-348
+        self.ns_operator = NavierStokesOperator(fine, self.constraints_inhomogeneous, p.nu, p.c_1, p.c_2, tid,
+                                                p.consider_time_derivative, increment_form,
+                                                p.cell_wise_stabilization, number="double", device=self.device)
+        # main.cc:396-568: level operators (MGNumber) and transfers
+        self.mg_ns_operators = {}
+        for l in range(self.minlevel, self.maxlevel + 1):
+            self.mg_ns_operators[l] = NavierStokesOperator(self.meshes[l], None, p.nu, p.c_1, p.c_2, tid,
+                                                           p.consider_time_derivative, increment_form,
+                                                           p.cell_wise_stabilization, number=p.mg_number,
+                                                           device=self.device)
+        t_nc, t_c = {}, {}
+        for l in range(self.minlevel + 1, self.maxlevel + 1):
+            mf, mc = self.meshes[l], self.meshes[l - 1]
+            t_nc[l] = MGTwoLevelTransfer().reinit(mf, mc, None, None, number=p.mg_number, device=self.device)
+            t_c[l] = MGTwoLevelTransfer().reinit(mf, mc, AffineConstraints(mf.constraints),
+                                                 AffineConstraints(mc.constraints), number=p.mg_number,
+                                                 device=self.device)
+        init = lambda l: self.mg_ns_operators[l].initialize_dof_vector()  # noqa: E731
+        self.mg_transfer_no_constraints = MGTransferGlobalCoarsening(t_nc, init)
+        self.transfer = MGTransferGlobalCoarsening(t_c, init)
+        self.preconditioner = PreconditionerGMG(self.mg_ns_operators, self.transfer, p.gmg)
+        self.linear_solver = LinearSolverGMRES(self.ns_operator, self.preconditioner, p.lin_n_max_iterations,
+                                               p.lin_absolute_tolerance, p.lin_relative_tolerance)
+        self.nonlinear_solver = NonLinearSolverNewton(p.newton_inexact)
+        self._ops = DeviceVectorOps()
+        self._hom_idx = torch.tensor(sorted(fine.constraints.keys()), dtype=torch.int32, device=self.device)
+        self._wire_hooks()
+        self.solution = SolutionHistory(tid.get_order() + 1)
+        self.solution.solutions = [self.ns_operator.initialize_dof_vector() for _ in range(tid.get_order() + 1)]
+        self.constraints_inhomogeneous.distribute(self.solution.get_current_solution())
+        self.t, self.counter = 0.0, 1
+        h = 1.0 / 2 ** self.maxlevel
+        self.min_dx = h * math.sqrt(p.dim)  # GridTools::minimal_cell_diameter of a cube
+        self.log = []
+
+    # ---- main.cc:772-869 ------------------------------------------------------------------------------
+    def _wire_hooks(self):
+        nl, tid = self.nonlinear_solver, self.time_integrator_data
+
+        def setup_jacobian(src):
+            self.ns_operator.set_linearization_point(src)
+
+        def setup_preconditioner(solution):
+            mg_solution = {}
+            self.mg_transfer_no_constraints.interpolate_to_mg(mg_solution, solution)
+            for l, op in self.mg_ns_operators.items():
+                op.set_linearization_point(mg_solution[l])
+            self.preconditioner.initialize()
+            self.linear_solver.initialize()
+
+        def evaluate_rhs(dst):
+            self.ns_operator.evaluate_rhs(dst)
+
+        def evaluate_residual(dst, src):
+            self.ns_operator.evaluate_residual(dst, src)
+
+        def solve_with_jacobian(dst, src):
+            self._ops.set_zero_indexed(src, self._hom_idx)  # constraints_homogeneous.set_zero(src)
+            self.linear_solver.solve(dst, src)
+            self.ns_operator.get_constraints().distribute(dst)
+
+        nl.setup_jacobian, nl.setup_preconditioner = setup_jacobian, setup_preconditioner
+        nl.evaluate_rhs, nl.evaluate_residual = evaluate_rhs, evaluate_residual
+        nl.solve_with_jacobian = solve_with_jacobian
+
+    def set_previous_solution(self, solution: SolutionHistory):
+        """main.cc:772-803"""
+        tid = self.time_integrator_data
+        self.ns_operator.set_previous_solution(solution)
+        order = tid.get_order()
+        if order == 0:
+            return
+        all_mg = {l: [None] * (order + 1) for l in self.mg_ns_operators}
+        for i in range(1, order + 1):
+            mg_solution = {}
+            self.mg_transfer_no_constraints.interpolate_to_mg(mg_solution, solution.get_vectors()[i])
+            for l in self.mg_ns_operators:
+                all_mg[l][i] = mg_solution[l]
+        for l, op in self.mg_ns_operators.items():
+            all_mg[l][0] = all_mg[l][1]  # slot 0 (the current solution) is not read (operator_ns.cc:246-258)
+            op.set_previous_solution(all_mg[l])
+
+    def step(self):
+        """one pass of the time loop body, main.cc:908-978"""
+        p, tid = self.params, self.time_integrator_data
+        cur = self.solution.get_current_solution()
+        u_max = self.ns_operator.get_max_u(cur)
+        dt = p.dt if p.dt != 0.0 else self.min_dx * p.cfl / max(u_max, 1.0)
+        tid.update_dt(dt)
+        self.ns_operator.invalidate_system()
+        for op in self.mg_ns_operators.values():
+            op.invalidate_system()
+        self.solution.commit_solution()
+        self.set_previous_solution(self.solution)
+        cur = self.solution.get_current_solution()
+        n_lin_before = len(self.linear_solver.n_iterations)
+        n_newton = self.nonlinear_solver.solve(cur)
+        self.constraints_inhomogeneous.distribute(cur)
+        self.t += dt
+        rec = dict(cycle=self.counter, t=self.t, dt=dt, u_max=u_max, newton_iterations=n_newton,
+                   newton_residuals=list(self.nonlinear_solver.residuals),
+                   linear_iterations=list(self.linear_solver.n_iterations[n_lin_before:]))
+        self.log.append(rec)
+        if self.verbose:
+            print(rec)
+        self.counter += 1
+        return rec

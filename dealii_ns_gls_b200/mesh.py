@@ -87,6 +87,10 @@ class Mesh:
     n_global_dofs: int = 0
     cell_is_boundary: np.ndarray | None = None  # touches ghost dofs
     canonical_ids: np.ndarray | None = None     # slab meshes: partition-independent id of each local dof
+    cell_coords: np.ndarray | None = None       # structured blocks: integer cell coordinates [n_cells, dim]
+    shape: tuple | None = None                  # structured blocks: cells per direction
+    extent: np.ndarray | None = None            # structured blocks: size of the block
+    origin: np.ndarray | None = None
 
     @property
     def C(self):
@@ -286,7 +290,8 @@ def structured_mesh(dim, shape, degree, *, deform=None, mapping_degree=1, period
                 cell_dofs=local.astype(index_dtype), geometry_type=0 if deform is None else 2,
                 cell_points=pts, mapping_degree=k, constraints={}, cell_h_min=h_min,
                 cell_measure=meas, partition=part, node_compact=(numbering == "node"),
-                n_global_dofs=n_global_dofs)
+                n_global_dofs=n_global_dofs, cell_coords=np.ascontiguousarray(cc[my_cells]), shape=shape,
+                extent=extent, origin=origin)
     if deform is None:
         mesh.cart_inv_jac = np.broadcast_to(1.0 / hcell, (ncell_loc, dim)).copy()
         mesh.cart_det = np.full(ncell_loc, float(np.prod(hcell)))
@@ -302,6 +307,45 @@ def structured_mesh(dim, shape, degree, *, deform=None, mapping_degree=1, period
             for dof in np.unique(dofs):
                 mesh.constraints[int(dof)] = []
     return mesh
+
+
+def dof_coordinates(mesh: Mesh) -> np.ndarray:
+    """[n_dofs, dim] coordinates of the support point of every local dof of an undeformed structured block
+    (what DoFTools::map_dofs_to_support_points gives; used for boundary values)."""
+    dim, p = mesh.dim, mesh.degree
+    n = p + 1
+    gp = gauss_lobatto_points(p)
+    loc = np.stack(np.meshgrid(*[np.arange(n)] * dim, indexing="ij"), axis=-1).reshape(-1, dim)[:, ::-1]
+    hcell = mesh.extent / np.asarray(mesh.shape, dtype=np.float64)
+    x = mesh.origin[None, None, :] + (mesh.cell_coords[:, None, :] + gp[loc][None, :, :]) * hcell[None, None, :]
+    out = np.zeros((mesh.n_dofs, dim))
+    for c in range(dim + 1):
+        out[mesh.cell_dofs[:, c * mesh.n_loc:(c + 1) * mesh.n_loc].astype(np.int64).reshape(-1)] = x.reshape(-1, dim)
+    return out
+
+
+def dof_components(mesh: Mesh) -> np.ndarray:
+    """[n_dofs] component (0..dim) of every local dof."""
+    out = np.zeros(mesh.n_dofs, dtype=np.int64)
+    for c in range(mesh.dim + 1):
+        out[mesh.cell_dofs[:, c * mesh.n_loc:(c + 1) * mesh.n_loc].astype(np.int64).reshape(-1)] = c
+    return out
+
+
+def child_cells(coarse: Mesh, fine: Mesh) -> np.ndarray:
+    """[n_coarse_cells, 2^dim] indices of the children of every coarse cell in the once-refined structured
+    block `fine` (child number cx + 2 cy + 4 cz, like GeometryInfo); what MGTwoLevelTransfer::reinit finds by
+    walking the two triangulations (main.cc:540-556)."""
+    dim = coarse.dim
+    assert fine.shape == tuple(2 * s for s in coarse.shape), "fine must be the global refinement of coarse"
+    lookup = np.full(fine.shape[::-1], -1, dtype=np.int64)  # indexed [z][y][x]
+    lookup[tuple(fine.cell_coords[:, e] for e in reversed(range(dim)))] = np.arange(fine.n_cells)
+    out = np.empty((coarse.n_cells, 2 ** dim), dtype=np.int64)
+    for ch in range(2 ** dim):
+        fc = 2 * coarse.cell_coords + np.array([(ch >> e) & 1 for e in range(dim)])
+        out[:, ch] = lookup[tuple(fc[:, e] for e in reversed(range(dim)))]
+    assert (out >= 0).all()
+    return out
 
 
 def hypercube(dim, n_per_dir, degree, **kw):

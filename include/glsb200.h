@@ -221,6 +221,73 @@ int glsb_estimate_relaxation(glsb_op *op, const void *inv_diag, int n_power_iter
                              double weight, uint64_t first_local_index, double *omega_out, double *ev_max_out,
                              void *stream);
 
+/* ---- multigrid transfer on the device ---------------------------------
+ * The reference moves vectors between the levels of its global-coarsening multigrid with deal.II's
+ * MGTransferGlobalCoarsening over one MGTwoLevelTransfer per level pair (main.cc:540-563); the V-cycle
+ * calls prolongate_and_add / restrict_and_add (multigrid.cc:534-548 -> deal.II Multigrid), and the level
+ * operators get their linearization point and history through interpolate_to_mg (main.cc:789-790,
+ * :825-827).  A glsb_transfer is one MGTwoLevelTransfer between a level and the next coarser one (same
+ * FE_Q(degree)^(dim+1), every coarse cell refined once):
+ *   prolongate_and_add : fine   += W P C_c coarse      (C_c resolves the coarse constraints, W = weights)
+ *   restrict_and_add   : coarse += C_c^T P^T W fine
+ *   interpolate        : coarse  = value of the fine function at the coarse support points (FE_Q restriction
+ *                        matrices; used with a transfer built WITHOUT constraints, main.cc:540-549)
+ * All vectors are device pointers of the transfer's number type. */
+typedef struct glsb_transfer glsb_transfer;
+
+typedef struct glsb_transfer_desc
+{
+  int32_t abi_version; /* GLSB_ABI_VERSION */
+  int32_t device;
+  int32_t dim, degree;
+  int32_t number_type; /* GLSB_F32 for the level vectors of the reference (config.h:7) */
+  uint64_t n_coarse_cells;
+  uint64_t n_fine_dofs, n_coarse_dofs; /* local vector lengths */
+  /* [n_coarse_cells][(dim+1)(degree+1)^dim] component-blocked lexicographic local indices into the coarse
+   * vector, or GLSB_CONSTRAINED_BIT | row (constraints of the coarse level, main.cc:552-556) */
+  const uint32_t *coarse_dof_indices;
+  /* [n_coarse_cells][2^dim][(dim+1)(degree+1)^dim] plain indices into the fine vector; child number
+   * cx + 2 cy (+ 4 cz) like GeometryInfo */
+  const uint32_t *fine_dof_indices;
+  uint32_t        n_constraint_rows; /* coarse constraint rows as CSR (may be 0) */
+  const uint32_t *row_ptr;
+  const uint32_t *entry_col;
+  const double   *entry_val;
+  /* [n_fine_dofs] deal.II's transfer weights: 1 / (number of fine cells touching the dof), 0 on constrained
+   * fine dofs; NULL = all ones (discontinuous / tests) */
+  const double *weights;
+} glsb_transfer_desc;
+
+int  glsb_transfer_create(const glsb_transfer_desc *desc, glsb_transfer **out);
+void glsb_transfer_destroy(glsb_transfer *t);
+const char *glsb_transfer_last_error(const glsb_transfer *t);
+int glsb_transfer_prolongate_and_add(glsb_transfer *t, void *dst_fine, const void *src_coarse, void *stream);
+int glsb_transfer_restrict_and_add(glsb_transfer *t, void *dst_coarse, const void *src_fine, void *stream);
+int glsb_transfer_interpolate(glsb_transfer *t, void *dst_coarse, const void *src_fine, void *stream);
+
+/* ---- device-resident Krylov vectors ----------------------------------
+ * deal.II's SolverGMRES (solver_l.cc:46-74: restart 30, right preconditioning) orthogonalises every new
+ * Krylov vector against up to 30 basis vectors with host loops over LinearAlgebra::distributed::Vector.
+ * These are the same vector operations on device vectors, batched: one pass over the data for all k inner
+ * products, one for the k-term update.  type = GLSB_F64 / GLSB_F32; results of reductions are double. */
+/* out_dev[j] = sum_i V[j * stride + i] * w[i], j < k  (out_dev: k doubles on the device, overwritten;
+ * deterministic two-stage reduction) */
+int glsb_vec_multi_dot(double *out_dev, const void *V, uint64_t stride, int k, const void *w, uint64_t n, int type,
+                       void *stream);
+/* w[i] += scale * sum_j coef_dev[j] * V[j * stride + i]  (coef_dev: k doubles on the device) */
+int glsb_vec_multi_axpy(void *w, const void *V, uint64_t stride, int k, const double *coef_dev, double scale,
+                        uint64_t n, int type, void *stream);
+/* y = a x + b y  (b == 0: y is not read) */
+int glsb_vec_axpby(void *y, double a, const void *x, double b, uint64_t n, int type, void *stream);
+/* dst (dst_type) = src (src_type): the double <-> float copies of PreconditionMG::vmult / copy_to_mg /
+ * copy_from_mg and MGCoarseGridApplyPreconditioner (multigrid.cc:6-149) */
+int glsb_vec_convert(void *dst, int dst_type, const void *src, int src_type, uint64_t n, void *stream);
+/* v[idx[i]] = 0: AffineConstraints::set_zero (main.cc:856) */
+int glsb_vec_set_zero_indexed(void *v, const uint32_t *idx_dev, uint64_t n_idx, int type, void *stream);
+/* y (type) = A x with a dense row-major double matrix on the device: the coarse-grid "direct" solver of
+ * the V-cycle applied as the precomputed inverse (multigrid.cc:419-425, :512-529 use Trilinos on the host) */
+int glsb_dense_apply(void *y, const double *A_dev, const void *x, uint32_t m, uint32_t n, int type, void *stream);
+
 /* ---- ghost exchange helpers (update_ghost_values / compress(add)) ------- */
 
 /* buf[i] = vec[export_indices[i]] */

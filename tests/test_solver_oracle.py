@@ -1,0 +1,91 @@
+"""Known-answer tests of the CPU restatement of the solver stack (oracle/gls_solver.py): two-level
+transfer, V-cycle, GMRES, Newton, channel time loop.  No GPU."""
+import numpy as np
+import pytest
+
+from dealii_ns_gls_b200 import mesh as M
+from dealii_ns_gls_b200.driver import (ChannelParameters, channel_inhomogeneous_constraints,
+                                       channel_level_mesh)
+from oracle import gls_solver as gs
+
+
+def _pair(dim, degree, shape):
+    mc = M.structured_mesh(dim, shape, degree)
+    mf = M.structured_mesh(dim, tuple(2 * s for s in shape), degree)
+    return mc, mf, M.child_cells(mc, mf)
+
+
+@pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 2), (2, 3), (3, 1)])
+def test_prolongation_reproduces_polynomials(dim, degree):
+    """the FE_Q(p) embedding is exact for polynomials of degree <= p per direction"""
+    mc, mf, ch = _pair(dim, degree, (3, 2, 2)[:dim])
+    P = gs.prolongation_matrix(dim, degree, mf.cell_dofs.astype(np.int64), mc.cell_dofs.astype(np.int64), ch,
+                               mf.n_dofs, mc.n_dofs)
+    xc, xf = M.dof_coordinates(mc), M.dof_coordinates(mf)
+    cc, cf = M.dof_components(mc), M.dof_components(mf)
+
+    def f(x, c):
+        return (1 + c) * np.prod(1.0 + x ** degree - 0.3 * x, axis=1)
+
+    assert np.allclose(P @ f(xc, cc), f(xf, cf), atol=1e-12)
+    R = gs.interpolation_matrix(dim, degree, mf.cell_dofs, mc.cell_dofs, ch, mf.n_dofs, mc.n_dofs)
+    assert np.allclose(R @ f(xf, cf), f(xc, cc), atol=1e-12)
+    assert abs(R @ P - np.eye(mc.n_dofs)).max() < 1e-12
+
+
+def test_prolongation_constraints_and_weights():
+    """zero rows on constrained fine dofs, constrained coarse dofs read as their constraint row"""
+    p = ChannelParameters()
+    mc, mf = channel_level_mesh(p, 1), channel_level_mesh(p, 2)
+    ch = M.child_cells(mc, mf)
+    P = gs.prolongation_matrix(2, 1, mf.cell_dofs.astype(np.int64), mc.cell_dofs.astype(np.int64), ch, mf.n_dofs,
+                               mc.n_dofs, mf.constraints, mc.constraints)
+    fc = np.array(sorted(mf.constraints))
+    cc = np.array(sorted(mc.constraints))
+    assert abs(P[fc]).sum() == 0
+    assert abs(P[:, cc]).sum() == 0
+    free = np.setdiff1d(np.arange(mf.n_dofs), fc)
+    # a coarse vector that satisfies the (zero) constraints is prolongated like without constraints
+    P0 = gs.prolongation_matrix(2, 1, mf.cell_dofs.astype(np.int64), mc.cell_dofs.astype(np.int64), ch, mf.n_dofs,
+                                mc.n_dofs)
+    v = np.random.default_rng(0).standard_normal(mc.n_dofs)
+    v[cc] = 0
+    assert np.allclose((P @ v)[free], (P0 @ v)[free])
+
+
+def test_gmres_matches_dense_solve():
+    rng = np.random.default_rng(1)
+    n = 60
+    A = np.eye(n) * 4 + rng.standard_normal((n, n)) * 0.3
+    b = rng.standard_normal(n)
+    x, it, hist = gs.gmres(lambda v: A @ v, lambda v: v / 4, b, rel_tol=1e-10, basis=28)
+    assert np.allclose(x, np.linalg.solve(A, b), atol=1e-8)
+    assert hist[-1] <= 1e-10 * np.linalg.norm(b) and it == len(hist) - 1 - (it // 28)
+
+
+def _oracle_driver(p, **kw):
+    n_levels = 2 + p.n_global_refinements
+    meshes = {l: channel_level_mesh(p, l) for l in range(n_levels + 1)}
+    children = {l: M.child_cells(meshes[l - 1], meshes[l]) for l in range(1, n_levels + 1)}
+    ci = channel_inhomogeneous_constraints(p, meshes[n_levels])
+    return gs.OracleChannelDriver(dim=p.dim, degree=p.fe_degree, meshes=meshes, children=children,
+                                  constraints_inhomogeneous=ci.rows, inhomogeneities=ci.inhomogeneities,
+                                  min_dx=np.sqrt(p.dim) / 2 ** n_levels, nu=p.nu, c1=p.c_1, c2=p.c_2, cfl=p.cfl,
+                                  bdf_order=p.bdf_order, consider_time_derivative=p.consider_time_derivative,
+                                  cell_wise_stabilization=p.cell_wise_stabilization,
+                                  rel_tol=p.lin_relative_tolerance, abs_tol=p.lin_absolute_tolerance, **kw)
+
+
+def test_channel_time_steps_converge():
+    """input_channel.json at n_global_refinements = 0: Newton converges in a few steps, GMRES + GMG in a
+    handful of iterations, and the V-cycle is a contraction"""
+    p = ChannelParameters(n_global_refinements=0)
+    d = _oracle_driver(p)
+    for _ in range(2):
+        rec = d.step()
+        assert rec["newton_residuals"][-1] <= 1e-7
+        assert 1 <= rec["newton_iterations"] <= 8
+        assert all(1 <= k <= 15 for k in rec["linear_iterations"])
+    # inflow profile is kept, walls stay at rest
+    sol = d.history[0]
+    assert np.allclose(sol[d.cdofs], d.cvals)
