@@ -75,6 +75,7 @@ SYMBOLS = {
     "glsb_compute_inverse_diagonal": (_I, [_P, _P, _D, _P]),
     "glsb_diagonal_cells": (_I, [_P, _P, _D, _P]),
     "glsb_diagonal_finish": (_I, [_P, _P, _P]),
+    "glsb_get_system_matrix": (_I, [_P, _P, _D, _P]),
     "glsb_get_max_u": (_I, [_P, _P, C.POINTER(_D), _P]),
     "glsb_relaxation_vmult": (_I, [_P, _P, _P, _P, _D, _I, _D, _P]),
     "glsb_relaxation_step": (_I, [_P, _P, _P, _P, _D, _I, _D, _P]),

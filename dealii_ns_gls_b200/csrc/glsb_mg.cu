@@ -38,58 +38,90 @@ __device__ __forceinline__ T coarse_read(const TParams<T> &p, const T *__restric
   return s;
 }
 
-// fine += W P C_c coarse: one CTA per coarse cell
+// One 1-D sweep of the tensor-product embedding through shared memory.  A cell and its two children per
+// direction: x' = a * n + l is node l of child a (2n entries, the node the children share appears twice, as in
+// the cell-wise loop of deal.II).  expand: out[r][x'][i] = sum_j P[x'][j] in[r][j][i]; contract is the transpose.
+template <typename T>
+__device__ __forceinline__ void expand_axis(const T *__restrict__ in, T *__restrict__ out, const T *__restrict__ P,
+                                            int n, int outer, int inner)
+{
+  const int total = outer * 2 * n * inner;
+  for (int o = threadIdx.x; o < total; o += blockDim.x)
+    {
+      const int i = o % inner, x = (o / inner) % (2 * n), r = o / (inner * 2 * n);
+      const T  *src = in + (r * n) * inner + i, *pr = P + x * n;
+      T         s = 0;
+      for (int j = 0; j < n; ++j)
+        s += pr[j] * src[j * inner];
+      out[o] = s;
+    }
+}
+template <typename T>
+__device__ __forceinline__ void contract_axis(const T *__restrict__ in, T *__restrict__ out, const T *__restrict__ P,
+                                              int n, int outer, int inner)
+{
+  const int total = outer * n * inner;
+  for (int o = threadIdx.x; o < total; o += blockDim.x)
+    {
+      const int i = o % inner, j = (o / inner) % n, r = o / (inner * n);
+      const T  *src = in + (r * 2 * n) * inner + i;
+      T         s = 0;
+      for (int x = 0; x < 2 * n; ++x)
+        s += P[x * n + j] * src[x * inner];
+      out[o] = s;
+    }
+}
+
+// position of (child, local node l) of component c in the expanded [C][(2n)^dim] block
+template <int dim>
+__device__ __forceinline__ int expanded_pos(int child, int c, int l, int n)
+{
+  const int m = 2 * n;
+  const int x = (child & 1) * n + l % n, y = ((child >> 1) & 1) * n + (l / n) % n;
+  if (dim == 2)
+    return (c * m + y) * m + x;
+  const int z = ((child >> 2) & 1) * n + l / (n * n);
+  return ((c * m + z) * m + y) * m + x;
+}
+
+// fine += W P C_c coarse: one CTA per coarse cell, sum-factorised embedding (dim sweeps through shared memory)
 template <typename T, int dim>
 __global__ void __launch_bounds__(128) k_prolongate(const TParams<T> p, T *__restrict__ dst, const T *__restrict__ src)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T         *cv = reinterpret_cast<T *>(smem_raw); // [ndof] coarse local values, constraints resolved
-  T         *sP = cv + p.ndof;                     // [2][n][n]
-  const int  n = p.n, nloc = p.nloc, ndof = p.ndof;
+  const int  n = p.n, nloc = p.nloc, ndof = p.ndof, m = 2 * n, C = dim + 1;
+  const int  big = C * (dim == 3 ? m * m * m : m * m);
+  T         *X = reinterpret_cast<T *>(smem_raw), *Y = X + big, *sP = Y + big;
   const uint64_t cell = blockIdx.x;
   for (int d = threadIdx.x; d < ndof; d += blockDim.x)
-    cv[d] = coarse_read(p, src, p.cidx[cell * ndof + d]);
+    X[d] = coarse_read(p, src, p.cidx[cell * ndof + d]); // [C][n^dim], constraints resolved
   for (int k = threadIdx.x; k < 2 * n * n; k += blockDim.x)
     sP[k] = p.P[k];
   __syncthreads();
+  if (dim == 3)
+    {
+      expand_axis(X, Y, sP, n, C * n * n, 1); // [C][n][n][2n]
+      __syncthreads();
+      expand_axis(Y, X, sP, n, C * n, m);     // [C][n][2n][2n]
+      __syncthreads();
+      expand_axis(X, Y, sP, n, C, m * m);     // [C][2n][2n][2n]
+    }
+  else
+    {
+      expand_axis(X, Y, sP, n, C * n, 1); // [C][n][2n]
+      __syncthreads();
+      expand_axis(Y, X, sP, n, C, m);     // [C][2n][2n]
+    }
+  __syncthreads();
+  const T  *E     = dim == 3 ? Y : X;
   const int total = p.nch * ndof;
   for (int o = threadIdx.x; o < total; o += blockDim.x)
     {
-      const int child = o / ndof, d = o - child * ndof, c = d / nloc, l = d - c * nloc;
-      const int l0 = l % n, l1 = (l / n) % n, l2 = l / (n * n);
-      const T  *p0 = sP + ((child & 1) * n + l0) * n, *p1 = sP + (((child >> 1) & 1) * n + l1) * n;
-      const T  *p2 = sP + (((child >> 2) & 1) * n + l2) * n;
-      const T  *v  = cv + c * nloc;
-      T         s  = 0;
-      if (dim == 3)
-        {
-          for (int j2 = 0; j2 < n; ++j2)
-            {
-              T s2 = 0;
-              for (int j1 = 0; j1 < n; ++j1)
-                {
-                  T s1 = 0;
-                  for (int j0 = 0; j0 < n; ++j0)
-                    s1 += p0[j0] * v[(j2 * n + j1) * n + j0];
-                  s2 += p1[j1] * s1;
-                }
-              s += p2[j2] * s2;
-            }
-        }
-      else
-        {
-          for (int j1 = 0; j1 < n; ++j1)
-            {
-              T s1 = 0;
-              for (int j0 = 0; j0 < n; ++j0)
-                s1 += p0[j0] * v[j1 * n + j0];
-              s += p1[j1] * s1;
-            }
-        }
-      const uint32_t fi = p.fidx[(cell * p.nch + child) * ndof + d];
+      const int      child = o / ndof, d = o - child * ndof, c = d / nloc, l = d - c * nloc;
+      const uint32_t fi = p.fidx[cell * total + o];
       const T        wv = p.w ? p.w[fi] : T(1);
       if (wv != T(0))
-        atomicAdd(dst + fi, wv * s);
+        atomicAdd(dst + fi, wv * E[expanded_pos<dim>(child, c, l, n)]);
     }
 }
 
@@ -98,55 +130,39 @@ template <typename T, int dim>
 __global__ void __launch_bounds__(128) k_restrict(const TParams<T> p, T *__restrict__ dst, const T *__restrict__ src)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T         *fv = reinterpret_cast<T *>(smem_raw); // [nch][ndof] weighted fine values
-  T         *sP = fv + p.nch * p.ndof;
-  const int  n = p.n, nloc = p.nloc, ndof = p.ndof;
+  const int  n = p.n, nloc = p.nloc, ndof = p.ndof, m = 2 * n, C = dim + 1;
+  const int  big = C * (dim == 3 ? m * m * m : m * m);
+  T         *X = reinterpret_cast<T *>(smem_raw), *Y = X + big, *sP = Y + big;
   const uint64_t cell  = blockIdx.x;
   const int      total = p.nch * ndof;
   for (int o = threadIdx.x; o < total; o += blockDim.x)
     {
+      const int      child = o / ndof, d = o - child * ndof, c = d / nloc, l = d - c * nloc;
       const uint32_t fi = p.fidx[cell * total + o];
-      fv[o]             = (p.w ? p.w[fi] : T(1)) * src[fi];
+      X[expanded_pos<dim>(child, c, l, n)] = (p.w ? p.w[fi] : T(1)) * src[fi];
     }
   for (int k = threadIdx.x; k < 2 * n * n; k += blockDim.x)
     sP[k] = p.P[k];
   __syncthreads();
+  if (dim == 3)
+    {
+      contract_axis(X, Y, sP, n, C, m * m);     // [C][n][2n][2n]
+      __syncthreads();
+      contract_axis(Y, X, sP, n, C * n, m);     // [C][n][n][2n]
+      __syncthreads();
+      contract_axis(X, Y, sP, n, C * n * n, 1); // [C][n][n][n]
+    }
+  else
+    {
+      contract_axis(X, Y, sP, n, C, m);     // [C][n][2n]
+      __syncthreads();
+      contract_axis(Y, X, sP, n, C * n, 1); // [C][n][n]
+    }
+  __syncthreads();
+  const T *R = dim == 3 ? Y : X;
   for (int d = threadIdx.x; d < ndof; d += blockDim.x)
     {
-      const int c = d / nloc, j = d - c * nloc;
-      const int j0 = j % n, j1 = (j / n) % n, j2 = j / (n * n);
-      T         s = 0;
-      for (int child = 0; child < p.nch; ++child)
-        {
-          const T *p0 = sP + (child & 1) * n * n, *p1 = sP + ((child >> 1) & 1) * n * n;
-          const T *p2 = sP + ((child >> 2) & 1) * n * n;
-          const T *v  = fv + child * ndof + c * nloc;
-          if (dim == 3)
-            {
-              for (int l2 = 0; l2 < n; ++l2)
-                {
-                  T s2 = 0;
-                  for (int l1 = 0; l1 < n; ++l1)
-                    {
-                      T s1 = 0;
-                      for (int l0 = 0; l0 < n; ++l0)
-                        s1 += p0[l0 * n + j0] * v[(l2 * n + l1) * n + l0];
-                      s2 += p1[l1 * n + j1] * s1;
-                    }
-                  s += p2[l2 * n + j2] * s2;
-                }
-            }
-          else
-            {
-              for (int l1 = 0; l1 < n; ++l1)
-                {
-                  T s1 = 0;
-                  for (int l0 = 0; l0 < n; ++l0)
-                    s1 += p0[l0 * n + j0] * v[l1 * n + l0];
-                  s += p1[l1 * n + j1] * s1;
-                }
-            }
-        }
+      const T        s  = R[d];
       const uint32_t iv = p.cidx[cell * ndof + d];
       if (!(iv & GLSB_CONSTRAINED_BIT))
         atomicAdd(dst + iv, s);
@@ -404,12 +420,18 @@ int run_transfer(glsb_transfer *t, int which, void *dst, const void *src, cudaSt
     return 0;
   const TParams<T> p    = make_params<T>(t);
   const unsigned   grid = (unsigned)t->n_coarse_cells;
-  const size_t     pm   = sizeof(T) * 2 * t->n * t->n;
+  const int        m    = 2 * t->n;
+  const size_t     sm   = sizeof(T) * (2 * (size_t)(dim + 1) * (dim == 3 ? m * m * m : m * m) + 2 * t->n * t->n);
+  if (which != OP_INTERPOLATE && sm > 48 * 1024)
+    {
+      auto kern = which == OP_PROLONGATE ? k_prolongate<T, dim> : k_restrict<T, dim>;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
+        return 1;
+    }
   if (which == OP_PROLONGATE)
-    k_prolongate<T, dim><<<grid, 128, sizeof(T) * t->ndof + pm, s>>>(p, static_cast<T *>(dst), static_cast<const T *>(src));
+    k_prolongate<T, dim><<<grid, 128, sm, s>>>(p, static_cast<T *>(dst), static_cast<const T *>(src));
   else if (which == OP_RESTRICT)
-    k_restrict<T, dim><<<grid, 128, sizeof(T) * t->nch * t->ndof + pm, s>>>(p, static_cast<T *>(dst),
-                                                                            static_cast<const T *>(src));
+    k_restrict<T, dim><<<grid, 128, sm, s>>>(p, static_cast<T *>(dst), static_cast<const T *>(src));
   else
     k_interpolate<T, dim><<<grid, 128, 0, s>>>(p, static_cast<T *>(dst), static_cast<const T *>(src));
   return cudaGetLastError() != cudaSuccess;

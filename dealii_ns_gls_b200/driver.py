@@ -92,6 +92,7 @@ class Driver:
 
     def __init__(self, params: ChannelParameters, device=None, verbose=False):
         self.params, self.verbose = params, verbose
+        self.timers = None
         p = params
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         n_levels = 2 + p.n_global_refinements  # refine_global(2) + n (simulation.cc:166-169)
@@ -169,9 +170,27 @@ class Driver:
             self.linear_solver.solve(dst, src)
             self.ns_operator.get_constraints().distribute(dst)
 
-        nl.setup_jacobian, nl.setup_preconditioner = setup_jacobian, setup_preconditioner
-        nl.evaluate_rhs, nl.evaluate_residual = evaluate_rhs, evaluate_residual
-        nl.solve_with_jacobian = solve_with_jacobian
+        t = self._timed  # the reference wraps every hook in a MyScope timer (main.cc:806-857)
+        nl.setup_jacobian = t("setup_jacobian", setup_jacobian)
+        nl.setup_preconditioner = t("setup_preconditioner", setup_preconditioner)
+        nl.evaluate_rhs = t("evaluate_rhs", evaluate_rhs)
+        nl.evaluate_residual = t("evaluate_residual", evaluate_residual)
+        nl.solve_with_jacobian = t("solve_with_jacobian", solve_with_jacobian)
+
+    def _timed(self, name, fn):
+        """wall-clock scopes like the reference's TimerCollection; only when self.timers is a dict (each scope
+        then synchronises the device, so leave it None for throughput runs)"""
+        def wrapped(*a):
+            if self.timers is None:
+                return fn(*a)
+            import time
+            torch.cuda.synchronize(self.device)
+            t0 = time.perf_counter()
+            r = fn(*a)
+            torch.cuda.synchronize(self.device)
+            self.timers[name] = self.timers.get(name, 0.0) + time.perf_counter() - t0
+            return r
+        return wrapped
 
     def set_previous_solution(self, solution: SolutionHistory):
         """main.cc:772-803"""

@@ -220,24 +220,14 @@ class MGCoarseGridDirect:
     (multigrid.cc:419-425, :472-476: Trilinos SolverDirect on op[min_level]->get_system_matrix() behind the
     float <-> double shim MGCoarseGridApplyPreconditioner, :6-149).  The level-0 system matrix is obtained
     column by column from the level operator's own vmult on the device (what MatrixFreeTools::compute_matrix
-    does cell-wise, operator_ns.cc:1407-1430); it is inverted once on the host in double (LAPACK, the direct
-    solver's factorisation) and applied on the device as a dense matrix-vector product."""
+    does cell-wise, operator_ns.cc:1407-1430); (glsb_get_system_matrix); it is inverted once on the host in double (LAPACK, the
+    direct solver's factorisation) and applied on the device as a dense matrix-vector product."""
 
     def __init__(self, op, ops: DeviceVectorOps):
         self.op, self._ops = op, ops
-        n = op.n_local
-        e = op.initialize_dof_vector()
-        col = op.initialize_dof_vector()
-        A = torch.empty((n, n), dtype=torch.float64, device=op.device)
-        row = torch.empty(n, dtype=torch.float64, device=op.device)
-        for j in range(n):
-            e.zero_()
-            e[j] = 1
-            op.vmult(col, e)
-            self._ops.convert(row, col)
-            A[:, j] = row
-        self.matrix = A.cpu().numpy()
-        self.inverse = torch.from_numpy(np.ascontiguousarray(np.linalg.inv(self.matrix))).to(op.device)
+        self.matrix = op.get_system_matrix()
+        # the factorisation of the direct solver: LAPACK on the host, in double, once per initialize()
+        self.inverse = torch.from_numpy(np.ascontiguousarray(np.linalg.inv(self.matrix.cpu().numpy()))).to(op.device)
 
     def __call__(self, level, dst, src):
         self._ops.dense_apply(dst, self.inverse, src)

@@ -337,6 +337,16 @@ class NavierStokesOperator:
             self._chk(self._lib.glsb_diagonal_finish(self._op, self._vec(diagonal, "diagonal"), s),
                       "compute_inverse_diagonal")
 
+    def get_system_matrix(self) -> torch.Tensor:
+        """operator_ns.cc:1303-1434 for the coarse-grid solver: the dense matrix of vmult ([n, n] float64 on the
+        device), computed by the library from the operator's own cell loop."""
+        n = self.n_local
+        A = torch.empty((n, n), dtype=torch.float64, device=self.device)
+        w = self.time_integrator_data.get_primary_weight()
+        self._chk(self._lib.glsb_get_system_matrix(self._op, C.c_void_p(A.data_ptr()), w, self._stream()),
+                  "get_system_matrix")
+        return A
+
     def get_max_u(self, vec: torch.Tensor) -> float:
         """operator_ns.cc:530-568."""
         self._update_ghost_values(vec)

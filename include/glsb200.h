@@ -191,6 +191,12 @@ int glsb_compute_inverse_diagonal(glsb_op *op, void *diag, double weight, void *
 int glsb_diagonal_cells(glsb_op *op, void *diag, double weight, void *stream);
 int glsb_diagonal_finish(glsb_op *op, void *diag, void *stream);
 
+/* get_system_matrix (operator_ns.cc:1303-1434, used by the coarse-grid solvers, multigrid.cc:395-425): the
+ * matrix of vmult, dense, row-major n x n doubles on the device (A[i * n + j]), obtained column by column
+ * from the operator's own cell loop (MatrixFreeTools::compute_matrix does the same cell-wise): constrained
+ * rows carry 1 on the diagonal.  Meant for the coarsest multigrid level only; single-rank operators. */
+int glsb_get_system_matrix(glsb_op *op, double *A_dev, double weight, void *stream);
+
 /* get_max_u (operator_ns.cc:530-568): max over the local quadrature points of |u|;
  * synchronises the stream; the MPI::max over ranks stays with the caller. */
 int glsb_get_max_u(glsb_op *op, const void *vec, double *out_host, void *stream);
