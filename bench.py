@@ -366,9 +366,46 @@ def run_gpu(args):
         r = cpu_vmult_gdofs(args.cpu_cells, args.degree, 10, 2)
         line["cpu_baseline"] = {"value": r["value"], "unit": "GDoF/s", "cores": r["cores"], "kind": "port",
                                 "sample": r["sample"]}
+    if world == 1 and args.workload == "P" and args.time_step_refinements >= 0:
+        del op, src, dst, h_src, h_dst
+        torch.cuda.empty_cache()
+        line["time_step"] = time_step_wall(args.time_step_refinements, dev)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_step_wall(refinements, dev, n_steps=4):
+    """The second half of BASELINE.json's metric, "wall time per time step": the time loop of main.cc:908-990
+    (get_max_u, set_previous_solution on all levels, Newton with GMRES + geometric multigrid: relaxation
+    smoothers, device transfers, dense coarse solve) on the 3-D channel of input_channel.json at Q2, with the
+    fine operator in double and the level operators in float (config.h:6-7), everything resident on the device.
+    Wall clock around whole steps, device synchronised on both sides; the first two steps are warm-up."""
+    import torch
+
+    from dealii_ns_gls_b200.driver import ChannelParameters, Driver
+    t0 = time.perf_counter()
+    d = Driver(ChannelParameters(dim=3, fe_degree=2, n_global_refinements=refinements), device=dev)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+    walls, recs = [], []
+    for i in range(2 + n_steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rec = d.step()
+        torch.cuda.synchronize()
+        if i >= 2:
+            walls.append(time.perf_counter() - t0)
+            recs.append(rec)
+    fine = d.meshes[d.maxlevel]
+    return {"wall_s_per_step": float(np.mean(walls)), "unit": "s", "steps": n_steps, "warmup_steps": 2,
+            "n_dofs": int(fine.n_dofs), "n_cells": int(fine.n_cells), "levels": d.maxlevel + 1,
+            "newton_iterations": [r["newton_iterations"] for r in recs],
+            "gmres_iterations": [r["linear_iterations"] for r in recs],
+            "setup_s": setup_s,
+            "workload": f"3D channel (simulation.cc:143-189), Q2, {fine.n_cells} cells, BDF1, CFL 0.1, Newton + "
+                        "GMRES(rel 1e-2) + GMG V-cycle (5 relaxation sweeps, coarse direct), fine operator f64, "
+                        "level operators f32"}
 
 
 _REAL_STDOUT = None
@@ -404,6 +441,9 @@ def main():
                     help="P = performance.cc hypercube (the headline); C = curved O-grid with the Turek-3D flags")
     ap.add_argument("--number", default="double", choices=["double", "float"],
                     help="double = Krylov operator (headline); float = multigrid level operator (config.h:7)")
+    ap.add_argument("--time-step-refinements", type=int, default=3,
+                    help="n global refinements of the 3-D Q2 channel whose wall time per time step is reported "
+                         "next to the vmult metric (3 -> 4.3e6 DoFs, 4 -> 3.4e7); -1 = skip")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

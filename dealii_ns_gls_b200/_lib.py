@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libglsb200.so")
 
-GLSB_ABI_VERSION = 2
+GLSB_ABI_VERSION = 3
 GLSB_F64, GLSB_F32 = 0, 1
 GLSB_GEOM_CARTESIAN, GLSB_GEOM_GENERAL = 0, 2
 GLSB_CELLS_ALL, GLSB_CELLS_INTERIOR, GLSB_CELLS_BOUNDARY = 0, 1, 2
@@ -32,6 +32,10 @@ class GlsbDesc(C.Structure):
         ("n_export", C.c_uint64), ("export_indices", C.c_void_p),
         ("n_edge_constrained_indices", C.c_uint32), ("edge_constrained_indices", C.c_void_p),
         ("has_edge_constrained_indices", C.c_int32),
+        ("n_outflow_faces", C.c_uint32),
+        ("face_cell", C.c_void_p), ("face_no", C.c_void_p), ("face_kind", C.c_void_p),
+        ("face_normal", C.c_void_p), ("face_jxw", C.c_void_p), ("face_inv_jac", C.c_void_p),
+        ("face_target_velocity", C.c_void_p),
     ]
 
 

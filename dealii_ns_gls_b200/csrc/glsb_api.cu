@@ -2,6 +2,7 @@
 // transformations and dispatch to the kernels.  No CPU fallback anywhere.
 #include "../../include/glsb200.h"
 #include "glsb_common.h"
+#include "glsb_faces.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -330,6 +331,10 @@ struct glsb_op
 
   DevBuf   relax_t, pi_e, pi_v1, pi_v2, pi_sums; // smoother scratch vectors
   DevBuf   mat_e, mat_col;                        // glsb_get_system_matrix scratch vectors
+  // boundary faces with outflow terms (operator_ns.cc:1195-1301)
+  uint32_t n_faces = 0;
+  DevBuf   f_slot, f_no, f_kind, f_normal, f_jxw, f_inv_jac, f_target, f_beta, f_velocity;
+  double   Nf[2 * MAX_N] = {}, Gf[2 * MAX_N] = {};
   uint32_t n_edge = 0;
   int      has_edge = 0;
   DevBuf   edge_idx, edge_saved, edge_cpy;
@@ -483,10 +488,79 @@ void cell_range(const glsb_op *op, int which, KParams<T> &p)
     }                                                             \
   while (0)
 
+template <typename T>
+FaceParams<T> face_params(const glsb_op *op)
+{
+  FaceParams<T> f;
+  memset(&f, 0, sizeof f);
+  f.nf       = op->n_faces;
+  f.n        = op->n;
+  f.nloc     = op->n_loc;
+  f.dim      = op->dim;
+  f.nqf      = op->dim == 2 ? op->n : op->n * op->n;
+  f.slot     = op->f_slot.as<uint32_t>();
+  f.no       = op->f_no.as<uint32_t>();
+  f.kind     = op->f_kind.as<uint32_t>();
+  f.normal   = op->f_normal.as<T>();
+  f.jxw      = op->f_jxw.as<T>();
+  f.inv_jac  = op->f_inv_jac.as<T>();
+  f.target   = op->f_target.as<T>();
+  f.beta     = op->f_beta.as<T>();
+  f.velocity = op->f_velocity.as<T>();
+  f.nu       = (T)op->nu;
+  for (int i = 0; i < op->n * op->n; ++i)
+    {
+      f.S[i] = (T)op->shape.S[i];
+      f.G[i] = (T)op->shape.G[i];
+    }
+  for (int i = 0; i < 2 * op->n; ++i)
+    {
+      f.Nf[i] = (T)op->Nf[i];
+      f.Gf[i] = (T)op->Gf[i];
+    }
+  return f;
+}
+
+// the boundary lambda of MatrixFree::loop (operator_ns.cc:710-717): which = 0 apply, 1 residual, 2 face_velocity,
+// 3 diagonal
+template <int dim, typename T>
+int do_faces(glsb_op *op, const KParams<T> &p, int what, cudaStream_t s)
+{
+  if (op->n_faces == 0)
+    return 0;
+  const FaceParams<T> f  = face_params<T>(op);
+  const size_t        sm = sizeof(T) * face_smem_elems<dim>(op->n);
+  op->launches++;
+  if (what == 0)
+    k_faces_apply<T, dim, false><<<op->n_faces, FACE_THREADS, sm, s>>>(p, f);
+  else if (what == 1)
+    k_faces_apply<T, dim, true><<<op->n_faces, FACE_THREADS, sm, s>>>(p, f);
+  else if (what == 2)
+    k_faces_velocity<T, dim><<<op->n_faces, FACE_THREADS, sm, s>>>(p, f);
+  else
+    k_faces_diag<T, dim><<<op->n_faces, FACE_THREADS, 0, s>>>(p, f);
+  return cudaGetLastError() != cudaSuccess;
+}
+
 template <int dim, typename T>
 int do_cells(glsb_op *op, void *dst, const void *src, double weight, int which, int branch, cudaStream_t s,
              int part = 0, int n_parts = 1)
 {
+  // boundary faces ride with the last part of the launch that covers the cells next to the partition surface
+  // (their contributions to ghost dofs must be in dst before compress(add))
+  const bool with_faces = op->n_faces > 0 && which != GLSB_CELLS_INTERIOR && part == n_parts - 1 &&
+                          !(op->range_override[1] > op->range_override[0]);
+  if (with_faces)
+    {
+      KParams<T> pf = base_params<T>(op);
+      cell_range(op, GLSB_CELLS_ALL, pf);
+      pf.src           = static_cast<const T *>(src);
+      pf.dst           = static_cast<T *>(dst);
+      pf.weight        = (T)weight;
+      pf.sign_negative = (branch == BR_RESIDUAL);
+      if (do_faces<dim, T>(op, pf, branch == BR_RESIDUAL ? 1 : 0, s))
+        return 1;
+    }
   KParams<T> p = base_params<T>(op);
   cell_range(op, which, p);
   if (n_parts > 1)
@@ -526,6 +600,8 @@ int do_lin(glsb_op *op, const void *vec, double dt, cudaStream_t s)
   p.src  = static_cast<const T *>(vec);
   p.stau = (dt == 0.0) ? 0.0 : 1.0 / dt;
   op->launches++;
+  if (do_faces<dim, T>(op, p, 2, s)) // face_velocity (operator_ns.cc:460-476)
+    return 1;
   return Kernels<dim, T>::linearization(op->n, p, op->shape, s);
 }
 
@@ -569,6 +645,8 @@ int do_diag(glsb_op *op, void *diag, double weight, cudaStream_t s)
   dc.ent_val = op->dc_ent_val.as<double>();
   dc.n_list  = op->dc_n_list;
   op->launches += 1 + (dc.n_list > 0);
+  if (do_faces<dim, T>(op, p, 3, s))
+    return 1;
   return Kernels<dim, T>::diagonal(op->n, op->increment_form ? BR_NEWTON : BR_FIXED_POINT, p, op->shape,
                                    op->diag_skip.as<uint8_t>(), dc, s);
 }
@@ -971,6 +1049,54 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
         ms[i]            = d->cell_measure[k];
       }
     ok = ok && upload(op->h_min, hm.data(), hm.size() * 8) && upload(op->measure, ms.data(), ms.size() * 8);
+    // ---- boundary faces with outflow terms ----
+    if (ok && d->n_outflow_faces > 0)
+      {
+        const uint32_t nf = d->n_outflow_faces, nqf = (uint32_t)(op->dim == 2 ? op->n : op->n * op->n), dm = (uint32_t)op->dim;
+        std::vector<uint32_t> slot_of_cell(nc, 0xffffffffu), fslot(nf);
+        for (uint32_t i = 0; i < op->n_slots; ++i)
+          if (!(i >= op->n_interior && i < op->n_int_pad) && slot_of_cell[perm[i]] == 0xffffffffu)
+            slot_of_cell[perm[i]] = i;
+        std::vector<double> beta(nf);
+        for (uint32_t f = 0; f < nf && ok; ++f)
+          {
+            if (d->face_cell[f] >= nc || d->face_no[f] >= 2 * dm || (d->face_kind[f] != 1 && d->face_kind[f] != 2))
+              ok = false;
+            else
+              {
+                fslot[f] = slot_of_cell[d->face_cell[f]];
+                // effective_beta_face = beta / h^(p+1), beta = 1, h after Lethe (operator_ns.cc:427-458)
+                const double m = d->cell_measure[d->face_cell[f]];
+                const double h = (op->dim == 2 ? std::sqrt(4.0 * m / M_PI) : std::pow(6.0 * m / M_PI, 1.0 / 3.0)) / op->degree;
+                beta[f] = 1.0 / std::pow(h, (double)(op->degree + 1));
+              }
+          }
+        if (!ok)
+          {
+            delete op;
+            return fail(nullptr, "glsb_create: bad outflow face arrays");
+          }
+        op->n_faces = nf;
+        compute_face_basis_host(op->degree, op->Nf, op->Gf);
+        std::vector<double> zeros((size_t)nf * nqf * dm, 0.0);
+        const double *tgt = d->face_target_velocity ? d->face_target_velocity : zeros.data();
+        ok = upload(op->f_slot, fslot.data(), nf * 4) && upload(op->f_no, d->face_no, nf * 4) &&
+             upload(op->f_kind, d->face_kind, nf * 4);
+        if (op->number_type == GLSB_F64)
+          ok = ok && upload_converted<double>(op->f_normal, d->face_normal, (size_t)nf * nqf * dm) &&
+               upload_converted<double>(op->f_jxw, d->face_jxw, (size_t)nf * nqf) &&
+               upload_converted<double>(op->f_inv_jac, d->face_inv_jac, (size_t)nf * nqf * dm * dm) &&
+               upload_converted<double>(op->f_target, tgt, (size_t)nf * nqf * dm) &&
+               upload_converted<double>(op->f_beta, beta.data(), nf) &&
+               upload_converted<double>(op->f_velocity, zeros.data(), (size_t)nf * nqf * dm);
+        else
+          ok = ok && upload_converted<float>(op->f_normal, d->face_normal, (size_t)nf * nqf * dm) &&
+               upload_converted<float>(op->f_jxw, d->face_jxw, (size_t)nf * nqf) &&
+               upload_converted<float>(op->f_inv_jac, d->face_inv_jac, (size_t)nf * nqf * dm * dm) &&
+               upload_converted<float>(op->f_target, tgt, (size_t)nf * nqf * dm) &&
+               upload_converted<float>(op->f_beta, beta.data(), nf) &&
+               upload_converted<float>(op->f_velocity, zeros.data(), (size_t)nf * nqf * dm);
+      }
     if (op->geom == GLSB_GEOM_CARTESIAN)
       {
         std::vector<double> ij((size_t)dm * op->ncp), dj(op->ncp);
@@ -1393,6 +1519,8 @@ static int host_pipe_setup(glsb_op *op)
 
 int glsb_vmult_host(glsb_op *op, void *dst_host, const void *src_host, double weight, void *stream)
 {
+  if (op && op->n_faces > 0)
+    return fail(op, "glsb_vmult_host: operators with outflow faces use glsb_vmult on device vectors");
   if (!op || !dst_host || !src_host)
     return fail(op, "glsb_vmult_host: null argument");
   if (op->n_ghost != 0)

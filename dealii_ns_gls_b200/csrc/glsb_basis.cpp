@@ -176,4 +176,23 @@ void compute_transfer_host(int degree, double *P, double *R, int *rchild)
     }
 }
 
+// values Nf[side * n + i] and derivatives Gf[side * n + i] of the 1-D basis at the face positions xi = 0, 1
+void compute_face_basis_host(int degree, double *Nf, double *Gf)
+{
+  const int n = degree + 1;
+  ld        nodes[MAX_N], v[MAX_N], d[MAX_N];
+  gauss_lobatto(degree, nodes);
+  for (int i = 0; i < n; ++i)
+    nodes[i] = 0.5L * (nodes[i] + 1);
+  for (int side = 0; side < 2; ++side)
+    {
+      lagrange(n, nodes, (ld)side, v, d);
+      for (int i = 0; i < n; ++i)
+        {
+          Nf[side * n + i] = (fabsl(v[i]) < 1e-17L) ? 0.0 : (double)v[i];
+          Gf[side * n + i] = (double)d[i];
+        }
+    }
+}
+
 } // namespace glsb

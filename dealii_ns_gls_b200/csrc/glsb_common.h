@@ -36,6 +36,8 @@ struct ShapeHost
 void compute_shape_host(int degree, ShapeHost &out);
 // P[2][n][n], R[n][n], rchild[n]: two-level transfer matrices (glsb_basis.cpp)
 void compute_transfer_host(int degree, double *P, double *R, int *rchild);
+// Nf[2][n], Gf[2][n]: 1-D basis values / derivatives at xi = 0 and xi = 1 (boundary faces)
+void compute_face_basis_host(int degree, double *Nf, double *Gf);
 
 enum Branch : int
 {

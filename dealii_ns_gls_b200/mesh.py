@@ -89,6 +89,7 @@ class Mesh:
     canonical_ids: np.ndarray | None = None     # slab meshes: partition-independent id of each local dof
     cell_coords: np.ndarray | None = None       # structured blocks: integer cell coordinates [n_cells, dim]
     shape: tuple | None = None                  # structured blocks: cells per direction
+    outflow_faces: dict | None = None           # boundary_faces(...) result: faces with outflow terms
     extent: np.ndarray | None = None            # structured blocks: size of the block
     origin: np.ndarray | None = None
 
@@ -516,3 +517,77 @@ def general_geometry(mesh: Mesh, n_q_1d: int | None = None):
     for _ in range(dim - 1):
         w = np.kron(wg, w)
     return np.linalg.inv(J), np.linalg.det(J) * w[None, :]
+
+
+def _lagrange_1d(nodes, x):
+    """values and derivatives [len(x), len(nodes)] of the Lagrange basis on `nodes`"""
+    m = len(nodes)
+    V = np.ones((len(x), m))
+    D = np.zeros((len(x), m))
+    for i in range(m):
+        for a in range(m):
+            if a != i:
+                V[:, i] *= (x - nodes[a]) / (nodes[i] - nodes[a])
+        for l in range(m):
+            if l == i:
+                continue
+            t = np.ones(len(x)) / (nodes[i] - nodes[l])
+            for a in range(m):
+                if a != i and a != l:
+                    t *= (x - nodes[a]) / (nodes[i] - nodes[a])
+            D[:, i] += t
+    return V, D
+
+
+def boundary_faces(mesh: Mesh, kind_of_boundary_id, target_velocity=None):
+    """Boundary faces of a structured block that carry outflow terms (operator_ns.cc:1195-1301) and what
+    MatrixFree's face MappingInfo holds for them (mapping_update_flags_boundary_faces, operator_ns.cc:113-117).
+
+    kind_of_boundary_id: {boundary id: 1 (all_outflow_bcs_cut) | 2 (all_outflow_bcs_nitsche)}, boundary ids as
+    GridGenerator colorises a block: 2 * direction + side.  target_velocity: callable(points[..., dim]) ->
+    [..., dim] for the Nitsche residual.  Face quadrature points: QGauss(degree + 1) in the tangential
+    directions, ascending direction fastest.  Returns a dict of arrays:
+      face_cell[f], face_no[f], face_kind[f], normal[f, q, dim], jxw[f, q], inv_jac[f, q, e, j],
+      points[f, q, dim], target[f, q, dim] (zeros without target_velocity)"""
+    dim, kdeg, nq = mesh.dim, mesh.mapping_degree, mesh.degree + 1
+    xg, wg = np.polynomial.legendre.leggauss(nq)
+    xg, wg = 0.5 * (xg + 1.0), 0.5 * wg
+    nodes = gauss_lobatto_points(kdeg)
+    Vt, Dt = _lagrange_1d(nodes, xg)
+    cells, nos, kinds, normals, jxws, ijs, pts = [], [], [], [], [], [], []
+    for bid, kind in sorted(kind_of_boundary_id.items()):
+        e, side = bid // 2, bid % 2
+        sel = np.nonzero(mesh.cell_coords[:, e] == (mesh.shape[e] - 1 if side else 0))[0]
+        if len(sel) == 0:
+            continue
+        Vn, Dn = _lagrange_1d(nodes, np.array([float(side)]))
+        vals = [Vn if a == e else Vt for a in range(dim)]
+
+        def kron(mats):
+            T = mats[0]
+            for mtx in mats[1:]:
+                T = np.kron(mtx, T)
+            return T
+
+        Nm = kron(vals)
+        J = np.zeros((len(sel), Nm.shape[0], dim, dim))
+        for a in range(dim):
+            mats = list(vals)
+            mats[a] = Dn if a == e else Dt
+            J[:, :, :, a] = np.einsum("qm,kmi->kqi", kron(mats), mesh.cell_points[sel])
+        w = kron([np.ones((1, 1)) if a == e else wg.reshape(-1, 1) for a in range(dim)]).reshape(-1)
+        Jinv = np.linalg.inv(J)
+        nref = np.zeros(dim)
+        nref[e] = 1.0 if side else -1.0
+        nn = np.einsum("kqej,e->kqj", Jinv, nref)
+        ln = np.linalg.norm(nn, axis=2)
+        cells.append(sel), nos.append(np.full(len(sel), bid)), kinds.append(np.full(len(sel), kind))
+        normals.append(nn / ln[:, :, None]), jxws.append(np.abs(np.linalg.det(J)) * ln * w[None, :]), ijs.append(Jinv)
+        pts.append(np.einsum("qm,kmi->kqi", Nm, mesh.cell_points[sel]))
+    if not cells:
+        return None
+    out = dict(face_cell=np.concatenate(cells).astype(np.uint32), face_no=np.concatenate(nos).astype(np.uint32),
+               face_kind=np.concatenate(kinds).astype(np.uint32), normal=np.concatenate(normals),
+               jxw=np.concatenate(jxws), inv_jac=np.concatenate(ijs), points=np.concatenate(pts))
+    out["target"] = target_velocity(out["points"]) if target_velocity is not None else np.zeros_like(out["normal"])
+    return out

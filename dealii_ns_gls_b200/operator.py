@@ -153,6 +153,16 @@ def build_desc(mesh: Mesh, *, number, nu, c_1, c_2, theta, time_order, consider_
     d.n_edge_constrained_indices = len(edge)
     d.edge_constrained_indices = ptr(edge)
     d.has_edge_constrained_indices = int(getattr(mesh, "has_edge_constrained_indices", len(edge) > 0))
+    # boundary faces with outflow terms: mesh.outflow_faces = mesh.boundary_faces(...) (operator_ns.h:33-35)
+    faces = getattr(mesh, "outflow_faces", None)
+    if faces is not None and len(faces["face_cell"]):
+        for k_, dt_ in (("face_cell", np.uint32), ("face_no", np.uint32), ("face_kind", np.uint32),
+                        ("normal", np.float64), ("jxw", np.float64), ("inv_jac", np.float64), ("target", np.float64)):
+            keep["f_" + k_] = np.ascontiguousarray(faces[k_], dtype=dt_)
+        d.n_outflow_faces = len(keep["f_face_cell"])
+        d.face_cell, d.face_no, d.face_kind = ptr(keep["f_face_cell"]), ptr(keep["f_face_no"]), ptr(keep["f_face_kind"])
+        d.face_normal, d.face_jxw, d.face_inv_jac = ptr(keep["f_normal"]), ptr(keep["f_jxw"]), ptr(keep["f_inv_jac"])
+        d.face_target_velocity = ptr(keep["f_target"])
     return d, keep
 
 

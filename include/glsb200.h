@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GLSB_ABI_VERSION 2
+#define GLSB_ABI_VERSION 3
 
 typedef struct glsb_op glsb_op;
 
@@ -102,6 +102,21 @@ typedef struct glsb_desc
   uint32_t        n_edge_constrained_indices;
   const uint32_t *edge_constrained_indices;
   int32_t         has_edge_constrained_indices;
+
+  /* boundary faces with outflow terms (do_vmult_boundary, operator_ns.cc:1195-1301; the ctor arguments
+   * all_outflow_bcs_cut / all_outflow_bcs_nitsche, operator_ns.h:33-35, resolved to faces by the caller like
+   * MatrixFree::loop resolves boundary ids): kind 1 = "cut" (v, beta min(0, U.n) u), 2 = Nitsche.  Face
+   * quadrature: QGauss(degree + 1) in the tangential directions, ascending direction fastest; the arrays are
+   * what MatrixFree's face MappingInfo holds (mapping_update_flags_boundary_faces, operator_ns.cc:113-117).
+   * May be empty (all five BASELINE configs). */
+  uint32_t        n_outflow_faces;
+  const uint32_t *face_cell;            /* [n_faces] cell the face belongs to */
+  const uint32_t *face_no;              /* [n_faces] 2 * direction + side (GeometryInfo face number) */
+  const uint32_t *face_kind;            /* [n_faces] 1 or 2 */
+  const double   *face_normal;          /* [n_faces][n_qf][dim] unit outer normal */
+  const double   *face_jxw;             /* [n_faces][n_qf] */
+  const double   *face_inv_jac;         /* [n_faces][n_qf][dim][dim], [e][j] = (J^-1)_{e j} */
+  const double   *face_target_velocity; /* [n_faces][n_qf][dim] Nitsche target (operator_ns.cc:495-521) or NULL */
 } glsb_desc;
 
 /* ---- life cycle -------------------------------------------------------- */

@@ -26,6 +26,7 @@ Reference files restated (all relative to /root/reference):
   include/operator_ns.cc:622-682    evaluate_rhs / evaluate_residual
   include/operator_ns.cc:195-225    compute_inverse_diagonal (+ 1e-10 guard)
   include/operator_ns.cc:530-568    get_max_u
+  include/operator_ns.cc:1195-1301  do_vmult_boundary (outflow "cut" and Nitsche faces), :423-521 its tables
   include/time_integration.cc:61-91,100-107,141-178  BDF / theta / none weights
 
 Two independent evaluation paths are provided: ``path="naive"`` uses full
@@ -269,6 +270,9 @@ class OracleOperator:
         self.constraints = dict(constraints or {})
         self.constrained = np.array(sorted(self.constraints.keys()), dtype=np.int64)
 
+        self._cell_points = np.asarray(cell_points, dtype=np.float64)
+        self._mapping_degree = mapping_degree
+        self.faces = None  # boundary faces with outflow terms (set_outflow_faces)
         J = mapping_jacobians(np.asarray(cell_points, dtype=np.float64), mapping_degree, self.tb)
         self.Jinv = np.linalg.inv(J).astype(self.dtype)  # [k,q,e,j] = (J^-1)_{e j}
         self.JxW = (np.linalg.det(J) * self.tb.w[None, :]).astype(self.dtype)
@@ -405,6 +409,8 @@ class OracleOperator:
         self.H = grad[:, :d].copy()
         self.P = grad[:, d].copy()
         self._penalty(val[:, :d, :], dt)
+        if self.faces is not None:
+            self._set_face_velocity(vec)
 
     def _penalty(self, u, dt):
         d = self.dim
@@ -532,7 +538,103 @@ class OracleOperator:
             vout, gout = self._cell_fixed_point(val, grad, weight, residual)
         else:
             vout, gout = self._cell_newton(val, grad, weight)
-        return self._integrate(vout, gout)
+        out = self._integrate(vout, gout)
+        if self.faces is not None:
+            self._apply_faces(loc_in, out, residual)
+        return out
+
+    # ---------------- boundary faces with outflow terms ---------------- #
+
+    def _face_tables(self, face_no, degree, n_q):
+        """basis values / reference gradients at the quadrature points of face `face_no` = 2 * direction + side
+        (QGauss(n_q) in the tangential directions, ascending direction fastest): N[q, i], dN[e, q, i], w[q]"""
+        d = self.dim
+        direction, side = face_no // 2, face_no % 2
+        nodes = gauss_lobatto_points(degree)
+        xq, wq = gauss_points_weights(n_q)
+        St, Gt = lagrange_tables(nodes, xq)
+        Sn, Gn = lagrange_tables(nodes, np.array([float(side)]))
+        vals = [Sn if e == direction else St for e in range(d)]
+        N = _kron_all(vals)
+        dN = []
+        for e in range(d):
+            mats = list(vals)
+            mats[e] = Gn if e == direction else Gt
+            dN.append(_kron_all(mats))
+        w = _kron_all([np.ones((1, 1)) if e == direction else wq.reshape(-1, 1) for e in range(d)]).reshape(-1)
+        return N, np.stack(dN), w
+
+    def set_outflow_faces(self, face_cell, face_no, face_kind, target_velocity=None):
+        """Boundary faces carrying the outflow terms of do_vmult_boundary (operator_ns.cc:1195-1301):
+        face_kind 1 = all_outflow_bcs_cut, 2 = all_outflow_bcs_nitsche; target_velocity[f, q, dim] for the
+        Nitsche residual (:495-521).  Geometry from the mapping support points: n = J^-T n_ref / |.|,
+        JxW = |det J| |J^-T n_ref| w_q; beta = 1 / h^(p+1), h after Lethe (:423-458)."""
+        d, p = self.dim, self.degree
+        nq1 = self.tb.b.n_q
+        face_cell = np.asarray(face_cell, dtype=np.int64)
+        face_no = np.asarray(face_no, dtype=np.int64)
+        nf = len(face_cell)
+        nqf = nq1 ** (d - 1)
+        F = dict(cell=face_cell, no=face_no, kind=np.asarray(face_kind, dtype=np.int64),
+                 N=np.zeros((nf, nqf, self.n_loc)), dN=np.zeros((nf, d, nqf, self.n_loc)),
+                 normal=np.zeros((nf, nqf, d)), jxw=np.zeros((nf, nqf)), Jinv=np.zeros((nf, nqf, d, d)))
+        for fn in np.unique(face_no):
+            sel = np.nonzero(face_no == fn)[0]
+            N, dN, w = self._face_tables(int(fn), p, nq1)
+            _, dM, _ = self._face_tables(int(fn), self._mapping_degree, nq1)
+            J = np.einsum("eqm,kmi->kqie", dM, self._cell_points[face_cell[sel]])
+            Jinv = np.linalg.inv(J)  # [k, q, e, j]
+            nref = np.zeros(d)
+            nref[fn // 2] = 1.0 if fn % 2 else -1.0
+            nn = np.einsum("kqej,e->kqj", Jinv, nref)  # J^-T n_ref
+            ln = np.linalg.norm(nn, axis=2)
+            F["N"][sel], F["dN"][sel] = N, dN
+            F["normal"][sel] = nn / ln[:, :, None]
+            F["jxw"][sel] = np.abs(np.linalg.det(J)) * ln * w[None, :]
+            F["Jinv"][sel] = Jinv
+        if d == 2:
+            h = np.sqrt(4.0 * self.measure[face_cell] / math.pi) / p
+        else:
+            h = np.power(6.0 * self.measure[face_cell] / math.pi, 1.0 / 3.0) / p
+        F["beta"] = (1.0 / np.power(h.astype(self.dtype), self.dtype.type(p + 1))).astype(self.dtype)
+        F["target"] = None if target_velocity is None else np.asarray(target_velocity, dtype=self.dtype)
+        F["velocity"] = np.zeros((nf, nqf, d), dtype=self.dtype)
+        for k in ("N", "dN", "normal", "jxw", "Jinv"):
+            F[k] = F[k].astype(self.dtype)
+        self.faces = F
+
+    def _set_face_velocity(self, vec):
+        """face_velocity of compute_penalty_parameters (operator_ns.cc:460-476)"""
+        F = self.faces
+        u = self._gather(vec)[F["cell"]][:, : self.dim]  # [f, d, i]
+        F["velocity"] = np.einsum("fqi,fdi->fqd", F["N"], u).astype(self.dtype)
+
+    def _apply_faces(self, loc_in, out, residual):
+        F, d = self.faces, self.dim
+        T = self.dtype.type
+        u = loc_in[F["cell"]][:, :d]  # [f, d, i]
+        val = np.einsum("fqi,fci->fcq", F["N"], u)
+        rg = np.einsum("feqi,fci->fceq", F["dN"], u)
+        grad = np.einsum("fqej,fceq->fcjq", F["Jinv"], rg)
+        n = F["normal"]
+        beta = F["beta"][:, None, None]
+        vr = np.zeros_like(val)
+        gr = np.zeros_like(grad)
+        cut = F["kind"] == 1
+        nit = F["kind"] == 2
+        if cut.any():
+            sv = val if residual else np.moveaxis(F["velocity"], 2, 1)  # [f, d, q]
+            no = np.minimum(T(0), np.einsum("fdq,fqd->fq", sv, n))
+            vr[cut] = (beta * no[:, None, :] * val)[cut]
+        if nit.any():
+            v = val - np.moveaxis(F["target"], 2, 1) if (residual and F["target"] is not None) else val
+            gn = np.einsum("fcjq,fqj->fcq", grad, n)
+            vr[nit] = (beta * v - T(self.nu) * gn)[nit]
+            gr[nit] = (-T(self.nu) * v[:, :, None, :] * np.moveaxis(n, 2, 1)[:, None, :, :])[nit]
+        vq = vr * F["jxw"][:, None, :]
+        rgq = np.einsum("fqej,fcjq->fceq", F["Jinv"], gr) * F["jxw"][:, None, None, :]
+        loc = np.einsum("fqi,fcq->fci", F["N"], vq) + np.einsum("feqi,fceq->fci", F["dN"], rgq)
+        np.add.at(out, (F["cell"][:, None, None], np.arange(d)[None, :, None], np.arange(self.n_loc)[None, None, :]), loc)
 
     # ---------------- public API ---------------- #
 

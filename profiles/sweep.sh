@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 i=0
 for cfg in "$@"; do
   i=$((i+1))
-  env $cfg python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/sweep_$i.json 2> gpurun_out/sweep_$i.err
+  env $cfg python bench.py --steps 10 --warmup 3 --no-cpu-baseline --time-step-refinements -1 > gpurun_out/sweep_$i.json 2> gpurun_out/sweep_$i.err
   python - <<PY
 import json
 try:

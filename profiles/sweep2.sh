@@ -5,7 +5,7 @@ i=0
 for cfg in "$@"; do
   i=$((i+1))
   envs="${cfg%%--*}"; args="${cfg#*--}"
-  env $envs python bench.py --steps 10 --warmup 3 --no-cpu-baseline $args > gpurun_out/sweep2_$i.json 2> gpurun_out/sweep2_$i.err
+  env $envs python bench.py --steps 10 --warmup 3 --no-cpu-baseline --time-step-refinements -1 $args > gpurun_out/sweep2_$i.json 2> gpurun_out/sweep2_$i.err
   python - <<PY
 import json
 try:
