@@ -342,6 +342,7 @@ struct glsb_op
   DevBuf Q, d1c, d2c, max_bits;
   int    FT = 0, NL = 1, QG = 1, F_stage = 0;
   int    packed = 0; // float Q2 operators: two cells per lane in the vmult kernel
+  bool   regtile = false; // a register-tiled kernel exists for this (dim, degree, number)
   int    fU = -1, fH = -1, fP = -1, fO = -1, fd1q = -1, fd2q = -1, fJ = -1, fjxw = -1, fGold = -1, fgoldp = -1;
   DevBuf diag_skip, dc_cell, dc_col_ptr, dc_col_dof, dc_ent_ptr, dc_ent_loc, dc_ent_val;
   uint32_t dc_n_list = 0;
@@ -579,12 +580,12 @@ int do_cells(glsb_op *op, void *dst, const void *src, double weight, int which, 
   if (p.cell_end <= p.cell_begin)
     return 0;
   op->launches++;
-  if (dim == 3 && op->n == 3 && branch == BR_NEWTON && op->variant_forced != 1)
+  if (dim == 3 && op->regtile && branch == BR_NEWTON && op->variant_forced != 1)
     {
       const int rc = Kernels<dim, T>::vmult_q2(p, op->shape, op->F_stage, s);
       if (rc >= 0)
         {
-          op->variant = "q2_regtile_tma";
+          op->variant = op->n == 3 ? "q2_regtile_tma" : (op->n == 2 ? "q1_regtile_tma" : "q3_regtile_tma");
           return rc;
         }
     }
@@ -1009,7 +1010,20 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
         op->fgoldp = take(dm);
       }
     op->FT = f;
-    if (op->dim == 3 && op->n == 3)
+    // degrees with a register-tiled kernel (glsb_q2.cuh): Q2, Q1, and Q3 in float
+    op->regtile = op->dim == 3 && (op->n == 3 || op->n == 2 || (op->n == 4 && op->number_type == GLSB_F32));
+    if (op->regtile && op->n != 3)
+      {
+        // one stage = one quadrature layer (n^2 points) if 2-3 CTAs with a 2-deep ring fit, else one row
+        const size_t layer = (size_t)op->F_stage * op->n * op->n * 32 * op->tsize;
+        const size_t fixed = (size_t)4 * 2 * 180 * op->tsize + 2 * (4 * op->nq + 1) * 32 * 4 + 256;
+        const int    ctas  = (op->number_type == GLSB_F32 && op->n != 4) ? 3 : 2;
+        const bool   fits  = ctas * (2 * layer + fixed + 1024) <= 228 * 1024;
+        const char  *rows  = getenv("GLSB_Q2_ROWS");
+        op->QG             = rows ? (atoi(rows) == 1 ? op->n : op->n * op->n) : (fits ? op->n * op->n : op->n);
+        op->NL             = op->nq / op->QG;
+      }
+    else if (op->dim == 3 && op->n == 3)
       {
         // one block per ring stage of the Q2 kernel: a whole quadrature layer (9 points) if two CTAs with a
         // 2-deep ring of such stages fit into an SM's shared memory, else one (qz, qy) row of 3 points

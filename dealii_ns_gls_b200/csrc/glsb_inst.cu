@@ -220,6 +220,21 @@ template <>
 int Kernels<GLSB_DIM, GLSB_REAL>::vmult_q2(const KParams<GLSB_REAL> &p, const ShapeHost &sh, int F, cudaStream_t s)
 {
 #if GLSB_DIM == 3 && defined(GLSB_WITH_Q2)
+  if (sh.n == 2) // Q1: same kernel, 8 values per lane
+    {
+      const auto S = to_shape<GLSB_REAL, 2>(sh);
+      if (p.geom == GLSB_GEOM_GENERAL)
+        return q2::launch_flags<GLSB_REAL, GLSB_REAL, true, 2>(p, S, F, s);
+      return q2::launch_flags<GLSB_REAL, GLSB_REAL, false, 2>(p, S, F, s);
+    }
+  if (sh.n == 4) // Q3: 2 x 64 values per lane fit the register file in float only (the level operators)
+    {
+      if (sizeof(GLSB_REAL) != 4)
+        return -1;
+      return q2::launch_q3_float(p, to_shape<GLSB_REAL, 4>(sh), F, s);
+    }
+  if (sh.n != 3)
+    return -1;
   const auto S = to_shape<GLSB_REAL, 3>(sh);
   if (p.packed) // float only: two cells per lane, FFMA2 arithmetic
     {

@@ -205,17 +205,39 @@ __device__ __forceinline__ T sel3(int c, T a0, T a1, T a2)
   return vsel(c == 0, a0, vsel(c == 1, a1, a2));
 }
 
-// a ring stage holds ROWS rows (qz, qy) of 3 quadrature points: ROWS = 1 (9 stages per batch) or 3 (one
-// stage per quadrature layer); the q-point array is laid out accordingly (KParams::NL = 9 / ROWS, QG = 3 ROWS)
-template <typename T, int ROWS>
+// The kernel is templated on n = degree + 1 (n = 3: Q2, the tuned case; n = 2: Q1; n = 4: Q3 for the float
+// level operators -- FP64 Q3 needs 2 x 64 values per lane and does not fit the register file).
+// a ring stage holds ROWS rows (qz, qy) of n quadrature points: ROWS = 1 (n^2 stages per batch) or n (one
+// stage per quadrature layer); the q-point array is laid out accordingly (KParams::NL = n^2 / ROWS, QG = n ROWS)
+template <typename T, int ROWS, int n>
 __host__ __device__ constexpr size_t stage_elems(int F)
 {
-  return (size_t)F * 3 * ROWS * CELLS;
+  return (size_t)F * n * ROWS * CELLS;
 }
 
-constexpr int IDX_ROWS  = 109;              // 108 dof indices + one flag word per cell
-constexpr int IDX_ELEMS = IDX_ROWS * CELLS; // index block of one batch
-constexpr int MAX_NST   = 8;
+template <int n>
+__host__ __device__ constexpr int idx_elems() // index block of one batch: 4 n^3 dof indices + one flag word per cell
+{
+  return (4 * n * n * n + 1) * CELLS;
+}
+constexpr int MAX_NST = 8;
+// resident CTAs per SM a variant is compiled for: FP64 and the 64-bit packed type 2 (255 registers), float 3
+// (170 registers), float Q3 2 (2 x 64 values per lane)
+template <int value_bytes, int n>
+__host__ __device__ constexpr int target_ctas()
+{
+  return value_bytes == 4 ? (n == 4 ? 2 : GLSB_Q2_F32_CTAS) : GLSB_Q2_F64_CTAS;
+}
+// entry q of a strided constant-bank row, q a runtime (CTA-uniform) index: selects instead of indexing
+template <int n, typename V>
+__device__ __forceinline__ V selq(int q, const V *base, int off, int stride)
+{
+  V r = base[off];
+#pragma unroll
+  for (int a = 1; a < n; ++a)
+    r = vsel(q == a, base[off + a * stride], r);
+  return r;
+}
 // exchange scratch of a warp: rows value, d_0, d_1, d_2, y.  A row holds 16 pairs (components 0/1 or 2/3
 // of a cell, 16 bytes); lane (cell k, component c), h = c >> 1, owns element c & 1 of pair
 // ((k + 4 h) & 7) + 8 h.  With that (measured with ncu, shared-memory wavefronts per warp instruction):
@@ -249,12 +271,12 @@ struct alignas(16) Pair<F2>
 // last to release it (an arrival counter per slot), so no warp ever waits for another one's progress.
 // A CTA works on units of VW consecutive batches (VW = 2 for the packed float kernel): a stage / an index
 // slot then holds the VW blocks one after the other.
-template <typename T, int ROWS, int VW>
+template <typename T, int ROWS, int VW, int n>
 __device__ __forceinline__ void issue_stage(const KParams<T> &p, int F, T *tab, uint64_t *full, uint32_t j,
                                             uint32_t slot)
 {
-  constexpr uint32_t SPB   = 9 / ROWS; // stages per batch
-  const uint32_t     bytes = (uint32_t)(stage_elems<T, ROWS>(F) * sizeof(T));
+  constexpr uint32_t SPB   = n * n / ROWS; // stages per batch
+  const uint32_t     bytes = (uint32_t)(stage_elems<T, ROWS, n>(F) * sizeof(T));
   const uint32_t     unit = blockIdx.x + (j / SPB) * gridDim.x, row = j % SPB;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   mbar_expect_tx(&full[slot], VW * bytes);
@@ -262,22 +284,24 @@ __device__ __forceinline__ void issue_stage(const KParams<T> &p, int F, T *tab, 
   for (int v = 0; v < VW; ++v)
     {
       const uint64_t batch = (uint64_t)(p.cell_begin >> 5) + (uint64_t)unit * VW + v;
-      const T       *src   = p.Q + ((batch * SPB + row) * p.FT) * (3 * ROWS * CELLS);
-      bulk_g2s(tab + ((size_t)slot * VW + v) * stage_elems<T, ROWS>(F), src, bytes, &full[slot]);
+      const T       *src   = p.Q + ((batch * SPB + row) * p.FT) * (n * ROWS * CELLS);
+      bulk_g2s(tab + ((size_t)slot * VW + v) * stage_elems<T, ROWS, n>(F), src, bytes, &full[slot]);
     }
 }
 
-template <typename T, typename V, bool GENERAL, bool CTD, bool CELLWISE, int ROWS>
-__global__ void __launch_bounds__(TPB, (sizeof(V) == 4 ? GLSB_Q2_F32_CTAS : GLSB_Q2_F64_CTAS))
-  k_vmult_q2_newton(const KParams<T> p, const Shape<V, 3> sh, const int F, const int nst)
+template <typename T, typename V, bool GENERAL, bool CTD, bool CELLWISE, int ROWS, int n>
+__global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
+  k_vmult_q2_newton(const KParams<T> p, const Shape<V, n> sh, const int F, const int nst)
 {
   using VO          = VOps<V, T>;
   constexpr int VW  = VO::VW;
-  constexpr int ISL = VW * IDX_ELEMS;               // index ring slot: the blocks of the unit's VW batches
-  const int     SB  = (int)stage_elems<T, ROWS>(F); // table stage: offset of the second batch's block
+  constexpr int N2 = n * n, N3 = n * n * n;
+  constexpr int IDX_ELEMS = idx_elems<n>();
+  constexpr int ISL = VW * IDX_ELEMS;                  // index ring slot: the blocks of the unit's VW batches
+  const int     SB  = (int)stage_elems<T, ROWS, n>(F); // table stage: offset of the second batch's block
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T        *tab   = reinterpret_cast<T *>(smem_raw);
-  V        *xch   = reinterpret_cast<V *>(tab + nst * VW * stage_elems<T, ROWS>(F)); // [warp][2][XSLOT]
+  V        *xch   = reinterpret_cast<V *>(tab + nst * VW * stage_elems<T, ROWS, n>(F)); // [warp][2][XSLOT]
   uint32_t *ibuf  = reinterpret_cast<uint32_t *>(xch + (TPB / 32) * 2 * XSLOT);      // [2][VW][109][32] indices, flags
   uint64_t *full  = reinterpret_cast<uint64_t *>(ibuf + 2 * ISL);
   uint64_t *ifull = full + MAX_NST;
@@ -294,7 +318,7 @@ __global__ void __launch_bounds__(TPB, (sizeof(V) == 4 ? GLSB_Q2_F32_CTAS : GLSB
   // column of this lane's cell in a 32-cell table row, for fields of component row 0, 1, 2 and cv
   const int      colr[4] = {col, (col + 4) & 31, (col + 8) & 31, (col + 4 * cv) & 31};
   // this lane's entries of an index block: dof (c, j) at ixo + j * CELLS, the cell's flag word at flo
-  const int      ixo = (c * 27) * CELLS + ((col + 8 * c) & 31), flo = 108 * CELLS + col;
+  const int      ixo = (c * N3) * CELLS + ((col + 8 * c) & 31), flo = 4 * N3 * CELLS + col;
 
   if (threadIdx.x == 0)
     {
@@ -311,7 +335,7 @@ __global__ void __launch_bounds__(TPB, (sizeof(V) == 4 ? GLSB_Q2_F32_CTAS : GLSB
 
   const uint32_t n_batches = ((p.cell_end - p.cell_begin + CELLS - 1) / CELLS + VW - 1) / VW; // units
   const uint32_t my_n      = (blockIdx.x < n_batches) ? (n_batches - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const uint32_t n_stages  = my_n * (9 / ROWS);
+  const uint32_t n_stages  = my_n * (N2 / ROWS);
   if (my_n == 0)
     return;
 
@@ -330,7 +354,7 @@ __global__ void __launch_bounds__(TPB, (sizeof(V) == 4 ? GLSB_Q2_F32_CTAS : GLSB
       if (my_n > 1)
         issue_idx(1);
       for (uint32_t j = 0; j < (uint32_t)nst && j < n_stages; ++j)
-        issue_stage<T, ROWS, VW>(p, F, tab, full, j, j);
+        issue_stage<T, ROWS, VW, n>(p, F, tab, full, j, j);
     }
 
   const V  w = VO::bcast(p.weight), nu = VO::bcast(p.nu);
@@ -351,11 +375,11 @@ __global__ void __launch_bounds__(TPB, (sizeof(V) == 4 ? GLSB_Q2_F32_CTAS : GLSB
                                                   (VW == 2 && ibuf[(bi & 1) * ISL + IDX_ELEMS + flo] != 0));
 
       // ---- gather (read_dof_values) ------------------------------------------------------
-      V t[27];
+      V t[N3];
       if (!slow)
         {
 #pragma unroll
-          for (int j = 0; j < 27; ++j)
+          for (int j = 0; j < N3; ++j)
             {
               if (VW == 1)
                 t[j] = VO::load(p.src, ixs[j * CELLS], 0);
@@ -366,7 +390,7 @@ __global__ void __launch_bounds__(TPB, (sizeof(V) == 4 ? GLSB_Q2_F32_CTAS : GLSB
       else
         {
 #pragma unroll
-          for (int j = 0; j < 27; ++j)
+          for (int j = 0; j < N3; ++j)
             {
               const T a = gather_resolved(p, p.src, ixs[j * CELLS]);
               if (VW == 1)
@@ -396,75 +420,101 @@ __global__ void __launch_bounds__(TPB, (sizeof(V) == 4 ? GLSB_Q2_F32_CTAS : GLSB
 
       // ---- interpolate to the quadrature points in x and y (registers only) --------------
 #pragma unroll
-      for (int l = 0; l < 9; ++l)
+      for (int l = 0; l < N2; ++l)
         {
-          const V a = t[3 * l], b = t[3 * l + 1], d = t[3 * l + 2];
+          V in[n];
 #pragma unroll
-          for (int q = 0; q < 3; ++q)
-            t[3 * l + q] = sh.S[q * 3] * a + sh.S[q * 3 + 1] * b + sh.S[q * 3 + 2] * d;
+          for (int i = 0; i < n; ++i)
+            in[i] = t[n * l + i];
+#pragma unroll
+          for (int q = 0; q < n; ++q)
+            {
+              V s = sh.S[q * n] * in[0];
+#pragma unroll
+              for (int i = 1; i < n; ++i)
+                s += sh.S[q * n + i] * in[i];
+              t[n * l + q] = s;
+            }
         }
 #pragma unroll
-      for (int k = 0; k < 3; ++k)
+      for (int k = 0; k < n; ++k)
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < n; ++i)
           {
-            const V a = t[i + 9 * k], b = t[i + 3 + 9 * k], d = t[i + 6 + 9 * k];
+            V in[n];
 #pragma unroll
-            for (int q = 0; q < 3; ++q)
-              t[i + 3 * q + 9 * k] = sh.S[q * 3] * a + sh.S[q * 3 + 1] * b + sh.S[q * 3 + 2] * d;
+            for (int j = 0; j < n; ++j)
+              in[j] = t[i + n * j + N2 * k];
+#pragma unroll
+            for (int q = 0; q < n; ++q)
+              {
+                V s = sh.S[q * n] * in[0];
+#pragma unroll
+                for (int j = 1; j < n; ++j)
+                  s += sh.S[q * n + j] * in[j];
+                t[i + n * q + N2 * k] = s;
+              }
           }
 
-      V acc[27];
+      V acc[N3];
 #pragma unroll
-      for (int j = 0; j < 27; ++j)
+      for (int j = 0; j < N3; ++j)
         acc[j] = VO::zero();
 
       // ---- quadrature layers --------------------------------------------------------------
 #pragma unroll 1
-      for (int qz = 0; qz < 3; ++qz)
+      for (int qz = 0; qz < n; ++qz)
         {
           // runtime (CTA-uniform) layer index: select from the constant bank instead of indexing it
-          const V sz0 = sel3<V>(qz, sh.S[0], sh.S[3], sh.S[6]), sz1 = sel3<V>(qz, sh.S[1], sh.S[4], sh.S[7]),
-                  sz2 = sel3<V>(qz, sh.S[2], sh.S[5], sh.S[8]);
-          const V gz0 = sel3<V>(qz, sh.G[0], sh.G[3], sh.G[6]), gz1 = sel3<V>(qz, sh.G[1], sh.G[4], sh.G[7]),
-                  gz2 = sel3<V>(qz, sh.G[2], sh.G[5], sh.G[8]);
+          V sz[n], gz[n], tz[n], hz[n];
           // test side: Cartesian cells carry the quadrature weights in the sweep matrices (Shape::Sw/Gw/Dt),
           // general cells get them with JxW from the table
-          const V wz  = sel3<V>(qz, sh.w[0], sh.w[1], sh.w[2]);
-          V tz0 = sz0, tz1 = sz1, tz2 = sz2, hz0 = gz0, hz1 = gz1, hz2 = gz2;
-          if (!GENERAL)
-            {
-              tz0 = sz0 * wz, tz1 = sz1 * wz, tz2 = sz2 * wz;
-              hz0 = gz0 * wz, hz1 = gz1 * wz, hz2 = gz2 * wz;
-            }
-          V       vl[9], wl[9];
+          const V wz = selq<n, V>(qz, sh.w, 0, 1);
 #pragma unroll
-          for (int a = 0; a < 9; ++a)
+          for (int i = 0; i < n; ++i)
             {
-              vl[a] = sz0 * t[a] + sz1 * t[a + 9] + sz2 * t[a + 18];
+              sz[i] = selq<n, V>(qz, sh.S, i, n);
+              gz[i] = selq<n, V>(qz, sh.G, i, n);
+              tz[i] = GENERAL ? sz[i] : sz[i] * wz;
+              hz[i] = GENERAL ? gz[i] : gz[i] * wz;
+            }
+          V       vl[N2], wl[N2];
+#pragma unroll
+          for (int a = 0; a < N2; ++a)
+            {
+              V s = sz[0] * t[a];
+#pragma unroll
+              for (int i = 1; i < n; ++i)
+                s += sz[i] * t[a + N2 * i];
+              vl[a] = s;
               wl[a] = VO::zero();
             }
           const T *tb = nullptr; // first batch's block of the stage; the second one is SB elements further
 #pragma unroll
-          for (int qy = 0; qy < 3; ++qy)
+          for (int qy = 0; qy < n; ++qy)
             {
               if (qy % ROWS == 0)
                 {
                   mbar_wait(&full[slot], par);
                   tb = tab + (size_t)slot * VW * SB;
                 }
-              constexpr int QPS = 3 * ROWS;
-              const int     qlo = (qy % ROWS) * 3; // first point of this row inside the stage
+              constexpr int QPS = n * ROWS;
+              const int     qlo = (qy % ROWS) * n; // first point of this row inside the stage
 #define GLSB_TAB(f, x) VO::load(tb, ((f)*QPS + qlo + (x)) * CELLS + col, SB)          /* fields without a component row */
 #define GLSB_TABR(f, x, r) VO::load(tb, ((f)*QPS + qlo + (x)) * CELLS + colr[r], SB) /* rotated by 4 * row, see qoff() */
 #pragma unroll
-              for (int qx = 0; qx < 3; ++qx)
+              for (int qx = 0; qx < n; ++qx)
                 {
-                  const int a   = 3 * qy + qx;
+                  const int a   = n * qy + qx;
                   const V   val = vl[a];
-                  const V rx = sh.D[qx * 3] * vl[3 * qy] + sh.D[qx * 3 + 1] * vl[3 * qy + 1] + sh.D[qx * 3 + 2] * vl[3 * qy + 2];
-                  const V ry = sh.D[qy * 3] * vl[qx] + sh.D[qy * 3 + 1] * vl[qx + 3] + sh.D[qy * 3 + 2] * vl[qx + 6];
-                  const V rz = gz0 * t[a] + gz1 * t[a + 9] + gz2 * t[a + 18];
+                  V rx = sh.D[qx * n] * vl[n * qy], ry = sh.D[qy * n] * vl[qx], rz = gz[0] * t[a];
+#pragma unroll
+                  for (int i = 1; i < n; ++i)
+                    {
+                      rx += sh.D[qx * n + i] * vl[n * qy + i];
+                      ry += sh.D[qy * n + i] * vl[qx + n * i];
+                      rz += gz[i] * t[a + N2 * i];
+                    }
                   // geometry: physical gradient of this lane's component
                   V g0, g1, g2, jq = VO::zero();
                   V J00, J01, J02, J10, J11, J12, J20, J21, J22;
@@ -557,14 +607,14 @@ __global__ void __launch_bounds__(TPB, (sizeof(V) == 4 ? GLSB_Q2_F32_CTAS : GLSB
                   // integrate: collocation derivative transposed in x and y inside the layer, z into acc
                   wl[a] += vo;
 #pragma unroll
-                  for (int i = 0; i < 3; ++i)
+                  for (int i = 0; i < n; ++i)
                     {
-                      wl[i + 3 * qy] += (GENERAL ? sh.D[qx * 3 + i] : sh.Dt[qx * 3 + i]) * ox;
-                      wl[qx + 3 * i] += (GENERAL ? sh.D[qy * 3 + i] : sh.Dt[qy * 3 + i]) * oy;
+                      wl[i + n * qy] += (GENERAL ? sh.D[qx * n + i] : sh.Dt[qx * n + i]) * ox;
+                      wl[qx + n * i] += (GENERAL ? sh.D[qy * n + i] : sh.Dt[qy * n + i]) * oy;
                     }
-                  acc[a] += hz0 * oz;
-                  acc[a + 9] += hz1 * oz;
-                  acc[a + 18] += hz2 * oz;
+#pragma unroll
+                  for (int i = 0; i < n; ++i)
+                    acc[a + N2 * i] += hz[i] * oz;
                 }
 #undef GLSB_TAB
 #undef GLSB_TABR
@@ -578,7 +628,7 @@ __global__ void __launch_bounds__(TPB, (sizeof(V) == 4 ? GLSB_Q2_F32_CTAS : GLSB
                         {
                           cnt[slot] = 0;
                           if (it + nst < n_stages)
-                            issue_stage<T, ROWS, VW>(p, F, tab, full, it + nst, slot);
+                            issue_stage<T, ROWS, VW, n>(p, F, tab, full, it + nst, slot);
                         }
                     }
                   ++it;
@@ -590,39 +640,53 @@ __global__ void __launch_bounds__(TPB, (sizeof(V) == 4 ? GLSB_Q2_F32_CTAS : GLSB
                 }
             }
 #pragma unroll
-          for (int a = 0; a < 9; ++a)
-            {
-              acc[a] += tz0 * wl[a];
-              acc[a + 9] += tz1 * wl[a];
-              acc[a + 18] += tz2 * wl[a];
-            }
+          for (int a = 0; a < N2; ++a)
+#pragma unroll
+            for (int i = 0; i < n; ++i)
+              acc[a + N2 * i] += tz[i] * wl[a];
         }
 
       // ---- test with the basis in y and x (transposed sweeps) -----------------------------
 #pragma unroll
-      for (int k = 0; k < 3; ++k)
+      for (int k = 0; k < n; ++k)
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < n; ++i)
           {
-            const V a = acc[i + 9 * k], b = acc[i + 3 + 9 * k], d = acc[i + 6 + 9 * k];
+            V in[n];
 #pragma unroll
-            for (int q = 0; q < 3; ++q)
-              acc[i + 3 * q + 9 * k] = GENERAL ? sh.S[q] * a + sh.S[3 + q] * b + sh.S[6 + q] * d :
-                                                 sh.Sw[q] * a + sh.Sw[3 + q] * b + sh.Sw[6 + q] * d;
+            for (int j = 0; j < n; ++j)
+              in[j] = acc[i + n * j + N2 * k];
+#pragma unroll
+            for (int q = 0; q < n; ++q)
+              {
+                V s = (GENERAL ? sh.S[q] : sh.Sw[q]) * in[0];
+#pragma unroll
+                for (int j = 1; j < n; ++j)
+                  s += (GENERAL ? sh.S[n * j + q] : sh.Sw[n * j + q]) * in[j];
+                acc[i + n * q + N2 * k] = s;
+              }
           }
 #pragma unroll
-      for (int l = 0; l < 9; ++l)
+      for (int l = 0; l < N2; ++l)
         {
-          const V a = acc[3 * l], b = acc[3 * l + 1], d = acc[3 * l + 2];
+          V in[n];
 #pragma unroll
-          for (int q = 0; q < 3; ++q)
-            acc[3 * l + q] = GENERAL ? sh.S[q] * a + sh.S[3 + q] * b + sh.S[6 + q] * d :
-                                       sh.Sw[q] * a + sh.Sw[3 + q] * b + sh.Sw[6 + q] * d;
+          for (int i = 0; i < n; ++i)
+            in[i] = acc[n * l + i];
+#pragma unroll
+          for (int q = 0; q < n; ++q)
+            {
+              V s = (GENERAL ? sh.S[q] : sh.Sw[q]) * in[0];
+#pragma unroll
+              for (int i = 1; i < n; ++i)
+                s += (GENERAL ? sh.S[n * i + q] : sh.Sw[n * i + q]) * in[i];
+              acc[n * l + q] = s;
+            }
         }
       if (!GENERAL)
         {
 #pragma unroll
-          for (int j = 0; j < 27; ++j)
+          for (int j = 0; j < N3; ++j)
             acc[j] *= cdet;
         }
 
@@ -632,20 +696,20 @@ __global__ void __launch_bounds__(TPB, (sizeof(V) == 4 ? GLSB_Q2_F32_CTAS : GLSB
         if (v == 0 ? actA : actB)
           {
             const uint32_t *ix = ixs + v * IDX_ELEMS;
-            T               r[27];
+            T               r[N3];
 #pragma unroll
-            for (int j = 0; j < 27; ++j)
+            for (int j = 0; j < N3; ++j)
               r[j] = lane_value<T>(acc[j], v);
             if (!slow)
               {
 #pragma unroll
-                for (int j = 0; j < 27; ++j)
+                for (int j = 0; j < N3; ++j)
                   atomic_add(p.dst + ix[j * CELLS], r[j]);
               }
             else
               {
 #pragma unroll
-                for (int j = 0; j < 27; ++j)
+                for (int j = 0; j < N3; ++j)
                   scatter_resolved(p, p.dst, ix[j * CELLS], r[j]);
               }
           }
@@ -663,33 +727,33 @@ __global__ void __launch_bounds__(TPB, (sizeof(V) == 4 ? GLSB_Q2_F32_CTAS : GLSB
     }
 }
 
-template <typename T, int ROWS, int VW>
+template <typename T, int ROWS, int VW, int n>
 size_t smem_bytes(int F, int nst)
 {
-  return nst * VW * stage_elems<T, ROWS>(F) * sizeof(T) + (size_t)(TPB / 32) * 2 * XSLOT * (VW * sizeof(T)) +
-         2 * VW * IDX_ELEMS * 4 + (MAX_NST + 2) * (sizeof(uint64_t) + sizeof(uint32_t));
+  return nst * VW * stage_elems<T, ROWS, n>(F) * sizeof(T) + (size_t)(TPB / 32) * 2 * XSLOT * (VW * sizeof(T)) +
+         2 * VW * idx_elems<n>() * 4 + (MAX_NST + 2) * (sizeof(uint64_t) + sizeof(uint32_t));
 }
 
 // ring depth: 2 stages of a whole layer; with row stages as deep as the target occupancy allows (<= 4)
-template <typename T, int ROWS, int VW>
+template <typename T, int ROWS, int VW, int n>
 int ring_depth(int F)
 {
-  const int ctas = (VW * sizeof(T) == 4) ? GLSB_Q2_F32_CTAS : GLSB_Q2_F64_CTAS;
+  const int ctas = target_ctas<(int)(VW * sizeof(T)), n>();
   int       nst  = 2;
-  while (ROWS == 1 && nst < 4 && ctas * (smem_bytes<T, ROWS, VW>(F, nst + 1) + 1024) <= 228 * 1024)
+  while (ROWS == 1 && nst < 4 && ctas * (smem_bytes<T, ROWS, VW, n>(F, nst + 1) + 1024) <= 228 * 1024)
     ++nst;
   return nst;
 }
 
-template <typename T, typename V, bool GENERAL, bool CTD, bool CELLWISE, int ROWS>
-static int launch_rows(const KParams<T> &p, const Shape<V, 3> &S, int F, cudaStream_t s)
+template <typename T, typename V, bool GENERAL, bool CTD, bool CELLWISE, int ROWS, int n>
+static int launch_rows(const KParams<T> &p, const Shape<V, n> &S, int F, cudaStream_t s)
 {
   constexpr int VW = VOps<V, T>::VW;
   static int   n_sm = 0;
   static const int env_nst = getenv("GLSB_Q2_NST") ? atoi(getenv("GLSB_Q2_NST")) : 0;
-  const int    nst  = env_nst >= 2 && env_nst <= MAX_NST ? env_nst : ring_depth<T, ROWS, VW>(F);
-  const size_t smem = smem_bytes<T, ROWS, VW>(F, nst);
-  auto         kern = k_vmult_q2_newton<T, V, GENERAL, CTD, CELLWISE, ROWS>;
+  const int    nst  = env_nst >= 2 && env_nst <= MAX_NST ? env_nst : ring_depth<T, ROWS, VW, n>(F);
+  const size_t smem = smem_bytes<T, ROWS, VW, n>(F, nst);
+  auto         kern = k_vmult_q2_newton<T, V, GENERAL, CTD, CELLWISE, ROWS, n>;
   if (smem > 227 * 1024)
     return -1;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -710,21 +774,32 @@ static int launch_rows(const KParams<T> &p, const Shape<V, 3> &S, int F, cudaStr
   return cudaGetLastError() != cudaSuccess;
 }
 
-template <typename T, typename V, bool GENERAL, bool CTD, bool CELLWISE>
-static int launch(const KParams<T> &p, const Shape<V, 3> &S, int F, cudaStream_t s)
+template <typename T, typename V, bool GENERAL, bool CTD, bool CELLWISE, int n>
+static int launch(const KParams<T> &p, const Shape<V, n> &S, int F, cudaStream_t s)
 {
-  if (p.QG == 9)
-    return launch_rows<T, V, GENERAL, CTD, CELLWISE, 3>(p, S, F, s);
-  return launch_rows<T, V, GENERAL, CTD, CELLWISE, 1>(p, S, F, s);
+  if (p.QG == n * n)
+    return launch_rows<T, V, GENERAL, CTD, CELLWISE, n, n>(p, S, F, s);
+  return launch_rows<T, V, GENERAL, CTD, CELLWISE, 1, n>(p, S, F, s);
 }
 
-template <typename T, typename V, bool GENERAL>
-static int launch_flags(const KParams<T> &p, const Shape<V, 3> &S, int F, cudaStream_t s)
+template <typename T, typename V, bool GENERAL, int n = 3>
+static int launch_flags(const KParams<T> &p, const Shape<V, n> &S, int F, cudaStream_t s)
 {
   if (p.ctd)
-    return p.cell_wise ? launch<T, V, GENERAL, true, true>(p, S, F, s) : launch<T, V, GENERAL, true, false>(p, S, F, s);
-  return p.cell_wise ? launch<T, V, GENERAL, false, true>(p, S, F, s) : launch<T, V, GENERAL, false, false>(p, S, F, s);
+    return p.cell_wise ? launch<T, V, GENERAL, true, true, n>(p, S, F, s) :
+                         launch<T, V, GENERAL, true, false, n>(p, S, F, s);
+  return p.cell_wise ? launch<T, V, GENERAL, false, true, n>(p, S, F, s) :
+                       launch<T, V, GENERAL, false, false, n>(p, S, F, s);
 }
+
+// Q3 (n = 4) exists for float only; the double overload keeps the dispatch code of glsb_inst.cu compilable
+static int launch_q3_float(const KParams<float> &p, const Shape<float, 4> &S, int F, cudaStream_t s)
+{
+  if (p.geom == GLSB_GEOM_GENERAL)
+    return launch_flags<float, float, true, 4>(p, S, F, s);
+  return launch_flags<float, float, false, 4>(p, S, F, s);
+}
+static int launch_q3_float(const KParams<double> &, const Shape<double, 4> &, int, cudaStream_t) { return -1; }
 
 } // namespace q2
 } // namespace glsb
