@@ -68,8 +68,7 @@ public:
                    nu, c_1, c_2, all_outflow_bcs_cut, all_outflow_bcs_nitsche, time_integrator_data,
                    consider_time_derivative, increment_form, cell_wise_stabilization, mg_level)
   {
-    // boundary-face outflow terms are a "next" row of the scope table
-    AssertThrow(all_outflow_bcs_cut.empty() && all_outflow_bcs_nitsche.empty(), ExcNotImplemented());
+    // boundary-face outflow terms (operator_ns.cc:1195-1301): the faces are collected below (outflow_faces)
 
     typename MatrixFree<dim, Number>::AdditionalData ad;
     ad.mapping_update_flags = update_values | update_gradients; // operator_ns.cc:112
@@ -177,9 +176,83 @@ public:
         has_edge = Utilities::MPI::max(edge_constrained_indices.size(), dof_handler.get_communicator()) > 0;
       }
 
+    // ---- boundary faces with outflow terms: what MatrixFree::loop hands to do_vmult_boundary -------------
+    // Face quadrature in the library's order (QGauss(p+1) in the tangential directions, ascending direction
+    // fastest), geometry from FEValues on the cell at the projected points: n = J^-T n_ref / |.|,
+    // JxW = |det J| |J^-T n_ref| w_q (what update_normal_vectors | update_JxW_values give on the face).
+    std::vector<uint32_t> face_cell, face_no, face_kind;
+    std::vector<double>   face_normal, face_jxw, face_inv_jac, face_target;
+    if (!(all_outflow_bcs_cut.empty() && all_outflow_bcs_nitsche.empty()))
+      {
+        const QGauss<1>           q1(degree + 1);
+        const unsigned int        n1 = q1.size();
+        std::vector<unsigned int> cell_number; // position of (batch, lane) in the cell order used above
+        std::uint64_t             k = 0;
+        for (unsigned int b = 0; b < matrix_free.n_cell_batches(); ++b)
+          for (unsigned int v = 0; v < matrix_free.n_active_entries_per_cell_batch(b); ++v, ++k)
+            {
+              const auto cell = matrix_free.get_cell_iterator(b, v);
+              for (const unsigned int f : cell->face_indices())
+                {
+                  if (!cell->face(f)->at_boundary())
+                    continue;
+                  const auto id   = cell->face(f)->boundary_id();
+                  const bool cut  = all_outflow_bcs_cut.count(id) > 0;
+                  const auto nit  = all_outflow_bcs_nitsche.find(id);
+                  if (!cut && nit == all_outflow_bcs_nitsche.end())
+                    continue;
+                  const unsigned int dir = f / 2, side = f % 2;
+                  std::vector<Point<dim>> pts;
+                  std::vector<double>     wts;
+                  const unsigned int      nqf = Utilities::pow(n1, dim - 1);
+                  for (unsigned int q = 0; q < nqf; ++q)
+                    {
+                      Point<dim>   xi;
+                      double       w  = 1;
+                      unsigned int qq = q;
+                      for (unsigned int e = 0; e < dim; ++e)
+                        if (e == dir)
+                          xi[e] = side;
+                        else
+                          {
+                            xi[e] = q1.point(qq % n1)[0];
+                            w *= q1.weight(qq % n1);
+                            qq /= n1;
+                          }
+                      pts.push_back(xi);
+                      wts.push_back(w);
+                    }
+                  FEValues<dim> fev(mapping, dof_handler.get_fe(), Quadrature<dim>(pts, wts),
+                                    update_inverse_jacobians | update_jacobians | update_quadrature_points);
+                  fev.reinit(typename Triangulation<dim>::cell_iterator(cell));
+                  face_cell.push_back(k), face_no.push_back(f), face_kind.push_back(cut ? 1 : 2);
+                  for (unsigned int q = 0; q < nqf; ++q)
+                    {
+                      const auto    &Ji = fev.inverse_jacobian(q); // Ji[e][j] = (J^-1)_{e j}
+                      Tensor<1, dim> nn;
+                      for (unsigned int j = 0; j < dim; ++j)
+                        nn[j] = Ji[dir][j] * (side ? 1.0 : -1.0);
+                      const double ln = nn.norm();
+                      for (unsigned int j = 0; j < dim; ++j)
+                        face_normal.push_back(nn[j] / ln);
+                      face_jxw.push_back(std::abs(fev.jacobian(q).determinant()) * ln * wts[q]);
+                      for (unsigned int e = 0; e < dim; ++e)
+                        for (unsigned int j = 0; j < dim; ++j)
+                          face_inv_jac.push_back(Ji[e][j]);
+                      for (unsigned int c = 0; c < dim; ++c) // operator_ns.cc:495-521
+                        face_target.push_back(cut ? 0.0 : nit->second->value(fev.quadrature_point(q), c));
+                    }
+                }
+            }
+      }
+
     glsb_desc d{};
     d.abi_version = GLSB_ABI_VERSION;
     cudaGetDevice(&d.device);
+    d.n_outflow_faces = face_cell.size();
+    d.face_cell = face_cell.data(), d.face_no = face_no.data(), d.face_kind = face_kind.data();
+    d.face_normal = face_normal.data(), d.face_jxw = face_jxw.data(), d.face_inv_jac = face_inv_jac.data();
+    d.face_target_velocity = face_target.data();
     d.n_edge_constrained_indices   = edge_constrained_indices.size();
     d.edge_constrained_indices     = edge_constrained_indices.data();
     d.has_edge_constrained_indices = has_edge;
