@@ -585,7 +585,8 @@ int do_cells(glsb_op *op, void *dst, const void *src, double weight, int which, 
       const int rc = Kernels<dim, T>::vmult_q2(p, op->shape, op->F_stage, s);
       if (rc >= 0)
         {
-          op->variant = op->n == 3 ? "q2_regtile_tma" : (op->n == 2 ? "q1_regtile_tma" : "q3_regtile_tma");
+          static const char *names[] = {"", "", "q1_regtile_tma", "q2_regtile_tma", "q3_regtile_tma", "q4_regtile_tma"};
+          op->variant = names[op->n];
           return rc;
         }
     }
@@ -1011,14 +1012,16 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
       }
     op->FT = f;
     // degrees with a register-tiled kernel (glsb_q2.cuh): Q2, Q1, and Q3 in float
-    op->regtile = op->dim == 3 && (op->n == 3 || op->n == 2 || (op->n == 4 && op->number_type == GLSB_F32));
+    op->regtile = op->dim == 3 && (op->n <= 3 || ((op->n == 4 || op->n == 5) && op->number_type == GLSB_F32));
+    // Q4 float keeps the interpolated values in shared memory (glsb_q2.cuh, TSM): row stages only
+    const bool tsm = op->n == 5 && op->number_type == GLSB_F32;
     if (op->regtile && op->n != 3)
       {
         // one stage = one quadrature layer (n^2 points) if 2-3 CTAs with a 2-deep ring fit, else one row
         const size_t layer = (size_t)op->F_stage * op->n * op->n * 32 * op->tsize;
         const size_t fixed = (size_t)4 * 2 * 180 * op->tsize + 2 * (4 * op->nq + 1) * 32 * 4 + 256;
-        const int    ctas  = (op->number_type == GLSB_F32 && op->n != 4) ? 3 : 2;
-        const bool   fits  = ctas * (2 * layer + fixed + 1024) <= 228 * 1024;
+        const int    ctas  = (op->number_type == GLSB_F32 && op->n < 4) ? 3 : 2;
+        const bool   fits  = !tsm && ctas * (2 * layer + fixed + 1024) <= 228 * 1024;
         const char  *rows  = getenv("GLSB_Q2_ROWS");
         op->QG             = rows ? (atoi(rows) == 1 ? op->n : op->n * op->n) : (fits ? op->n * op->n : op->n);
         op->NL             = op->nq / op->QG;

@@ -233,6 +233,12 @@ int Kernels<GLSB_DIM, GLSB_REAL>::vmult_q2(const KParams<GLSB_REAL> &p, const Sh
         return -1;
       return q2::launch_q3_float(p, to_shape<GLSB_REAL, 4>(sh), F, s);
     }
+  if (sh.n == 5) // Q4: float only (TSM)
+    {
+      if (sizeof(GLSB_REAL) != 4)
+        return -1;
+      return q2::launch_q4_float(p, to_shape<GLSB_REAL, 5>(sh), F, s);
+    }
   if (sh.n != 3)
     return -1;
   const auto S = to_shape<GLSB_REAL, 3>(sh);
