@@ -60,6 +60,8 @@ SYMBOLS = {
     "glsb_invalidate_system": (_I, [_P]),
     "glsb_vmult": (_I, [_P, _P, _P, _D, _P]),
     "glsb_vmult_host": (_I, [_P, _P, _P, _D, _P]),
+    "glsb_vmult_host_begin": (_I, [_P, _P, _P, _P, _P, _D, _P]),
+    "glsb_vmult_host_finish": (_I, [_P, _P, _P, _P]),
     "glsb_host_register": (_I, [_P, _U64]),
     "glsb_host_unregister": (_I, [_P]),
     "glsb_edge_begin": (_I, [_P, _P, _P]),

@@ -249,6 +249,12 @@ __global__ void k_last_touch(const uint32_t *__restrict__ idx, const uint8_t *__
   else
     atomicMax(last + iv, c);
 }
+__global__ void k_mark_last(const uint32_t *__restrict__ idx, uint64_t n, uint32_t value, uint32_t *__restrict__ last)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n)
+    atomicMax(last + idx[t], value);
+}
 // flag[d] = entry d is touched again after the chunk whose completion triggers its download
 __global__ void k_late_flags(const uint32_t *__restrict__ last, const uint64_t *__restrict__ in_end, uint32_t nch,
                              uint8_t *__restrict__ flag, uint64_t n)
@@ -361,7 +367,7 @@ struct glsb_op
     std::vector<uint32_t>    cidx_end_spec; // ... below in_end[c] (speculative download)
     DevBuf                   src, dst, late_flag; // late_flag[d]: entry d changes after its speculative download
     uint64_t                 n_late = 0;
-  } hp;
+  } hp, hpp; // hpp: the pipeline of partitioned operators (interior cells only, glsb_vmult_host_begin / _finish)
   std::vector<uint32_t> cidx_sorted;
   std::vector<uint32_t> slot_lo, slot_hi; // per 32-slot batch: smallest / largest vector index touched
 
@@ -1196,6 +1202,21 @@ void glsb_destroy(glsb_op *op)
   if (op)
     {
       cudaSetDevice(op->device);
+      for (glsb_op::HostPipe *h : {&op->hpp})
+        {
+          for (cudaEvent_t e : h->e_in)
+            cudaEventDestroy(e);
+          for (cudaEvent_t e : h->e_cells)
+            cudaEventDestroy(e);
+          if (h->e_start)
+            cudaEventDestroy(h->e_start);
+          if (h->e_done)
+            cudaEventDestroy(h->e_done);
+          if (h->s_in)
+            cudaStreamDestroy(h->s_in);
+          if (h->s_out)
+            cudaStreamDestroy(h->s_out);
+        }
       for (cudaEvent_t e : op->hp.e_in)
         cudaEventDestroy(e);
       for (cudaEvent_t e : op->hp.e_cells)
@@ -1636,6 +1657,193 @@ int glsb_vmult_host(glsb_op *op, void *dst_host, const void *src_host, double we
     }
   if (cudaGetLastError() != cudaSuccess)
     return cuda_fail(op, "glsb_vmult_host");
+  return 0;
+}
+
+// ---- the same pipeline for partitioned operators (n_ghost > 0) -------------------------------------------
+// The interior cells (no ghost dofs) are chunked exactly like above; the cells at the partition surface and the
+// two halves of the ghost exchange stay with the host layer between _begin and _finish:
+//   glsb_vmult_host_begin : zero d_dst; per chunk: upload src, interior cells of the chunk, speculative download
+//   host layer            : update_ghost_values(d_src) -> glsb_vmult_cells(BOUNDARY) -> compress(add)(d_dst)
+//   glsb_vmult_host_finish: constrained rows, last download, re-send of the entries that changed after their
+//                           download (touched by a later chunk, by the boundary cells or by compress(add))
+static int host_pipe_setup_part(glsb_op *op)
+{
+  glsb_op::HostPipe &hp = op->hpp;
+  if (hp.ready)
+    return 0;
+  const uint64_t n_local = op->n_owned + op->n_ghost;
+  const uint32_t nb_all = (op->n_slots + 31) / 32, nb = op->n_int_pad / 32;
+  const char    *env = getenv("GLSB_HOST_CHUNKS");
+  uint32_t       nch = env ? (uint32_t)atoi(env) : 16;
+  nch                = std::max(1u, std::min(64u, nch));
+  if (nb < 8 * nch)
+    nch = 1;
+  hp.cell_begin.resize(nch + 1);
+  for (uint32_t c = 0; c <= nch; ++c)
+    hp.cell_begin[c] = (uint32_t)((uint64_t)nb * c / nch) * 32;
+  hp.cell_begin[nch] = op->n_interior;
+  std::vector<uint64_t> hi(nch, 0);
+  std::vector<uint8_t>  chunk_of_batch(nb_all, (uint8_t)nch); // batches of boundary cells: after every chunk
+  for (uint32_t c = 0; c < nch; ++c)
+    for (uint32_t b = hp.cell_begin[c] / 32; b < (hp.cell_begin[c + 1] + 31) / 32 && b < nb; ++b)
+      {
+        chunk_of_batch[b] = (uint8_t)c;
+        if (op->slot_lo[b] != 0xffffffffu)
+          hi[c] = std::max<uint64_t>(hi[c], (uint64_t)op->slot_hi[b] + 1);
+      }
+  hp.in_end.resize(nch);
+  hp.cidx_end_spec.resize(nch);
+  uint64_t run = 0;
+  for (uint32_t c = 0; c < nch; ++c)
+    {
+      run          = std::min<uint64_t>(std::max(run, hi[c]), op->n_owned);
+      hp.in_end[c] = (c + 1 == nch) ? op->n_owned : run;
+    }
+  for (uint32_t c = 0; c < nch; ++c)
+    hp.cidx_end_spec[c] = (uint32_t)(std::lower_bound(op->cidx_sorted.begin(), op->cidx_sorted.end(),
+                                                      (uint32_t)std::min<uint64_t>(hp.in_end[c], 0xffffffffull)) -
+                                     op->cidx_sorted.begin());
+  {
+    DevBuf last, cob, d_in_end;
+    if (!last.alloc(n_local * 4) || !hp.late_flag.alloc(n_local) || !upload(cob, chunk_of_batch.data(), nb_all) ||
+        !upload(d_in_end, hp.in_end.data(), nch * 8))
+      return 1;
+    cudaMemset(last.p, 0, n_local * 4);
+    const uint32_t ndof = (uint32_t)(op->C * op->n_loc);
+    const uint64_t tot  = (uint64_t)ndof * op->n_slots;
+    k_last_touch<<<(unsigned)((tot + 255) / 256), 256>>>(op->idx.as<uint32_t>(), cob.as<uint8_t>(),
+                                                         op->row_dof.as<uint32_t>(), op->row_ptr.as<uint32_t>(),
+                                                         op->ecol.as<uint32_t>(), last.as<uint32_t>(), op->n_slots,
+                                                         op->n_interior, op->n_int_pad, ndof);
+    if (op->n_export) // compress(add) changes the exported entries last
+      k_mark_last<<<(unsigned)((op->n_export + 255) / 256), 256>>>(op->export_idx.as<uint32_t>(), op->n_export, nch + 1,
+                                                                   last.as<uint32_t>());
+    k_late_flags<<<(unsigned)((op->n_owned + 255) / 256), 256>>>(last.as<uint32_t>(), d_in_end.as<uint64_t>(), nch,
+                                                                 hp.late_flag.as<uint8_t>(), op->n_owned);
+    if (cudaDeviceSynchronize() != cudaSuccess)
+      return 1;
+  }
+  if (cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking) != cudaSuccess)
+    return 1;
+  hp.e_in.resize(nch);
+  hp.e_cells.resize(nch);
+  for (uint32_t c = 0; c < nch; ++c)
+    if (cudaEventCreateWithFlags(&hp.e_in[c], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&hp.e_cells[c], cudaEventDisableTiming) != cudaSuccess)
+      return 1;
+  if (cudaEventCreateWithFlags(&hp.e_start, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&hp.e_done, cudaEventDisableTiming) != cudaSuccess)
+    return 1;
+  hp.ready = true;
+  return 0;
+}
+
+int glsb_vmult_host_begin(glsb_op *op, void *d_dst_v, void *d_src_v, void *dst_host, const void *src_host,
+                          double weight, void *stream)
+{
+  if (!op || !d_dst_v || !d_src_v || !dst_host || !src_host)
+    return fail(op, "glsb_vmult_host_begin: null argument");
+  if (op->n_faces > 0 || op->n_edge > 0)
+    return fail(op, "glsb_vmult_host_begin: operators with outflow faces or edge indices use the device-vector calls");
+  if (!op->lin_valid)
+    return fail(op, "glsb_vmult: set_linearization_point has not been called");
+  if (op->increment_form && op->ctd && !op->prev_valid)
+    return fail(op, "glsb_vmult: set_previous_solution has not been called");
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, dst_host) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer)
+    {
+      cudaGetLastError();
+      return fail(op, "glsb_vmult_host_begin: dst_host must be page-locked (glsb_host_register)");
+    }
+  if (host_pipe_setup_part(op))
+    return cuda_fail(op, "glsb_vmult_host_begin: setup");
+  glsb_op::HostPipe &hp     = op->hpp;
+  cudaStream_t       s      = (cudaStream_t)stream;
+  const uint32_t     nch    = (uint32_t)hp.in_end.size();
+  const size_t       ts     = op->tsize;
+  const int          branch = op->increment_form ? BR_NEWTON : BR_FIXED_POINT;
+  char              *d_src = (char *)d_src_v, *d_dst = (char *)d_dst_v;
+  cudaEventRecord(hp.e_start, s);
+  cudaStreamWaitEvent(hp.s_in, hp.e_start, 0);
+  cudaStreamWaitEvent(hp.s_out, hp.e_start, 0);
+  if (cudaMemsetAsync(d_dst, 0, (size_t)(op->n_owned + op->n_ghost) * ts, s) != cudaSuccess)
+    return cuda_fail(op, "glsb_vmult_host_begin: memset");
+  uint64_t in_done = 0, out_done = 0;
+  uint32_t c_done = 0;
+  for (uint32_t c = 0; c < nch; ++c)
+    {
+      if (hp.in_end[c] > in_done)
+        {
+          if (cudaMemcpyAsync(d_src + in_done * ts, (const char *)src_host + in_done * ts, (hp.in_end[c] - in_done) * ts,
+                              cudaMemcpyHostToDevice, hp.s_in) != cudaSuccess)
+            return cuda_fail(op, "glsb_vmult_host_begin: upload");
+          in_done = hp.in_end[c];
+        }
+      cudaEventRecord(hp.e_in[c], hp.s_in);
+      cudaStreamWaitEvent(s, hp.e_in[c], 0);
+      int rc = 0;
+      if (hp.cell_begin[c + 1] > hp.cell_begin[c])
+        {
+          op->range_override[0] = hp.cell_begin[c];
+          op->range_override[1] = hp.cell_begin[c + 1];
+#define CALL(D, T) do_cells<D, T>(op, d_dst, d_src, weight, GLSB_CELLS_ALL, branch, s)
+          GLSB_DISPATCH(op, CALL);
+#undef CALL
+          op->range_override[0] = op->range_override[1] = 0;
+        }
+      if (rc)
+        return cuda_fail(op, "glsb_vmult_host_begin: launch");
+      if (hp.cidx_end_spec[c] > c_done) // identity on the constrained rows inside the range sent now
+        {
+          const uint32_t m = hp.cidx_end_spec[c] - c_done;
+          if (op->number_type == GLSB_F64)
+            k_copy_indexed<double><<<(m + 255) / 256, 256, 0, s>>>((double *)d_dst, (const double *)d_src,
+                                                                 op->cidx.as<uint32_t>() + c_done, m);
+          else
+            k_copy_indexed<float><<<(m + 255) / 256, 256, 0, s>>>((float *)d_dst, (const float *)d_src,
+                                                                op->cidx.as<uint32_t>() + c_done, m);
+          op->launches++;
+          c_done = hp.cidx_end_spec[c];
+        }
+      cudaEventRecord(hp.e_cells[c], s);
+      if (hp.in_end[c] > out_done)
+        {
+          cudaStreamWaitEvent(hp.s_out, hp.e_cells[c], 0);
+          if (cudaMemcpyAsync((char *)dst_host + out_done * ts, d_dst + out_done * ts, (hp.in_end[c] - out_done) * ts,
+                              cudaMemcpyDeviceToHost, hp.s_out) != cudaSuccess)
+            return cuda_fail(op, "glsb_vmult_host_begin: download");
+          out_done = hp.in_end[c];
+        }
+    }
+  if (cudaGetLastError() != cudaSuccess)
+    return cuda_fail(op, "glsb_vmult_host_begin");
+  return 0;
+}
+
+int glsb_vmult_host_finish(glsb_op *op, void *d_dst_v, void *dst_host, void *stream)
+{
+  if (!op || !d_dst_v || !dst_host || !op->hpp.ready)
+    return fail(op, "glsb_vmult_host_finish: call glsb_vmult_host_begin first");
+  glsb_op::HostPipe &hp = op->hpp;
+  cudaStream_t       s  = (cudaStream_t)stream;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, dst_host) != cudaSuccess || !at.devicePointer)
+    return fail(op, "glsb_vmult_host_finish: dst_host must be page-locked");
+  // the downloads of _begin have to land before the late entries are re-sent
+  cudaEventRecord(hp.e_done, hp.s_out);
+  cudaStreamWaitEvent(s, hp.e_done, 0);
+  const uint64_t n = op->n_owned;
+  if (op->number_type == GLSB_F64)
+    k_flush_flagged<double><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((double *)at.devicePointer, (const double *)d_dst_v,
+                                                                      hp.late_flag.as<uint8_t>(), n);
+  else
+    k_flush_flagged<float><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((float *)at.devicePointer, (const float *)d_dst_v,
+                                                                     hp.late_flag.as<uint8_t>(), n);
+  op->launches++;
+  if (cudaGetLastError() != cudaSuccess)
+    return cuda_fail(op, "glsb_vmult_host_finish");
   return 0;
 }
 

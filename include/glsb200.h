@@ -143,6 +143,15 @@ int glsb_vmult(glsb_op *op, void *dst, const void *src, double weight, void *str
  * chunked pipeline over PCIe.  Ordered after the work on `stream`; `stream` waits for the last download.
  * Single-rank operators only (n_ghost == 0). */
 int glsb_vmult_host(glsb_op *op, void *dst_host, const void *src_host, double weight, void *stream);
+/* The same pipeline for partitioned operators (n_ghost > 0), split around the ghost exchange the host layer
+ * drives: _begin zeroes d_dst and pipelines upload / interior cells / speculative download in chunks (d_src,
+ * d_dst: device vectors of n_owned + n_ghost values owned by the caller; dst_host page-locked); the caller then
+ * imports the ghosts of d_src, runs glsb_vmult_cells(GLSB_CELLS_BOUNDARY) and compress(add)s d_dst; _finish
+ * re-sends the entries that changed after their download (later chunks, boundary cells, compress).  The
+ * identity on constrained rows (operator_ns.cc:719-721) is applied chunk by chunk inside _begin. */
+int glsb_vmult_host_begin(glsb_op *op, void *d_dst, void *d_src, void *dst_host, const void *src_host, double weight,
+                          void *stream);
+int glsb_vmult_host_finish(glsb_op *op, void *d_dst, void *dst_host, void *stream);
 /* cudaHostRegister / cudaHostUnregister for a caller-owned host vector */
 int glsb_host_register(void *ptr, uint64_t bytes);
 int glsb_host_unregister(void *ptr);
