@@ -596,7 +596,7 @@ int do_cells(glsb_op *op, void *dst, const void *src, double weight, int which, 
           return rc;
         }
     }
-  op->variant = "generic";
+  op->variant = (dim == 3 && op->n >= 4 && getenv("GLSB_NO_COL") == nullptr) ? "column" : "generic";
   return Kernels<dim, T>::vmult(op->n, branch, p, op->shape, s);
 }
 
@@ -699,6 +699,37 @@ __global__ void k_unit_vector(T *__restrict__ e, uint64_t n, uint64_t j)
   if (i < n)
     e[i] = (i == j) ? T(1) : T(0);
 }
+// A (row-major double) = transpose of the column-major T matrix M; 1 on the diagonal of constrained rows
+template <typename T>
+__global__ void k_matrix_finish(double *__restrict__ A, const T *__restrict__ M, uint64_t n)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n * n)
+    {
+      const uint64_t i = t / n, j = t - i * n;
+      A[t]             = (double)M[j * n + i];
+    }
+}
+__global__ void k_matrix_identity_rows(double *__restrict__ A, const uint32_t *__restrict__ idx, uint32_t m, uint64_t n)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < m)
+    A[(uint64_t)idx[t] * n + idx[t]] = 1.0;
+}
+
+template <int dim, typename T>
+int do_matrix(glsb_op *op, void *M, double weight, cudaStream_t s)
+{
+  KParams<T> p = base_params<T>(op);
+  cell_range(op, GLSB_CELLS_ALL, p);
+  p.dst         = static_cast<T *>(M);
+  p.weight      = (T)weight;
+  p.unit_stride = op->n_owned;
+  op->launches++;
+  return Kernels<dim, T>::matrix_columns(op->n, op->increment_form ? BR_NEWTON : BR_FIXED_POINT, (uint32_t)op->n_owned, p,
+                                         op->shape, s);
+}
+
 template <typename T>
 __global__ void k_store_column(double *__restrict__ A, const T *__restrict__ col, uint64_t n, uint64_t j)
 {
@@ -1426,12 +1457,36 @@ int glsb_get_system_matrix(glsb_op *op, double *A_dev, double weight, void *stre
       return 1;
     }
   const uint64_t n = op->n_owned;
-  if (!op->mat_e.p || op->mat_e.bytes < n * op->tsize)
-    if (!op->mat_e.alloc(n * op->tsize) || !op->mat_col.alloc(n * op->tsize))
-      {
-        op->err = "glsb_get_system_matrix: out of device memory";
-        return 1;
-      }
+  if (!op->lin_valid)
+    return fail(op, "glsb_get_system_matrix: set_linearization_point has not been called");
+  if (op->n_faces == 0 && op->n_edge == 0 && n <= 65535)
+    {
+      // all columns in one launch: blockIdx.y = column, the unit vectors are never materialised
+      cudaStream_t s0 = static_cast<cudaStream_t>(stream);
+      if (op->mat_col.bytes < n * n * op->tsize && !op->mat_col.alloc(n * n * op->tsize))
+        return fail(op, "glsb_get_system_matrix: out of device memory");
+      cudaMemsetAsync(op->mat_col.p, 0, n * n * op->tsize, s0);
+      int rc = 0;
+#define CALL(D, T) do_matrix<D, T>(op, op->mat_col.p, weight, s0)
+      GLSB_DISPATCH(op, CALL);
+#undef CALL
+      if (rc)
+        return cuda_fail(op, "glsb_get_system_matrix: launch");
+      const unsigned g = (unsigned)((n * n + 255) / 256);
+      if (op->number_type == GLSB_F64)
+        k_matrix_finish<double><<<g, 256, 0, s0>>>(A_dev, op->mat_col.as<double>(), n);
+      else
+        k_matrix_finish<float><<<g, 256, 0, s0>>>(A_dev, op->mat_col.as<float>(), n);
+      if (op->n_constrained)
+        k_matrix_identity_rows<<<(op->n_constrained + 255) / 256, 256, 0, s0>>>(A_dev, op->cidx.as<uint32_t>(),
+                                                                               op->n_constrained, n);
+      op->launches += 2;
+      return cudaGetLastError() != cudaSuccess ? cuda_fail(op, "glsb_get_system_matrix") : 0;
+    }
+  // operators with outflow faces or edge indices: column by column through glsb_vmult
+  if ((op->mat_e.bytes < n * op->tsize && !op->mat_e.alloc(n * op->tsize)) ||
+      (op->mat_col.bytes < n * op->tsize && !op->mat_col.alloc(n * op->tsize)))
+    return fail(op, "glsb_get_system_matrix: out of device memory");
   cudaStream_t   s      = static_cast<cudaStream_t>(stream);
   const unsigned blocks = (unsigned)((n + 255) / 256);
   for (uint64_t j = 0; j < n; ++j)

@@ -94,6 +94,7 @@ struct KParams
   const T *src;
   T       *dst;
   unsigned long long *max_bits; // get_max_u
+  uint64_t unit_stride;         // get_system_matrix: elements between the columns of the output matrix
 };
 
 // dof index of local dof `dof` of cell `cell`: rows of 32 consecutive cells are contiguous (coalesced
@@ -163,6 +164,9 @@ struct Kernels
   static int diagonal(int n, int branch, const KParams<T> &p, const ShapeHost &sh, const uint8_t *skip_cell,
                       const DiagColumns &dc, cudaStream_t s);
   static int max_u(int n, const KParams<T> &p, const ShapeHost &sh, cudaStream_t s);
+  // all columns of the system matrix in one launch (unit vectors as src, column-major T matrix at p.dst)
+  static int matrix_columns(int n, int branch, uint32_t n_columns, const KParams<T> &p, const ShapeHost &sh,
+                            cudaStream_t s);
   // register-tiled Q2 (dim 3, degree 2) Newton-branch vmult; returns -1 if not applicable
   static int vmult_q2(const KParams<T> &p, const ShapeHost &sh, int n_stage_fields, cudaStream_t s);
 };

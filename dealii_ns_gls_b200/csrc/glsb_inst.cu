@@ -4,6 +4,9 @@
 #ifdef GLSB_WITH_Q2
 #include "glsb_q2.cuh"
 #endif
+#if GLSB_DIM == 3
+#include "glsb_col.cuh"
+#endif
 
 #ifndef GLSB_DIM
 #error "define GLSB_DIM"
@@ -71,6 +74,30 @@ static int launch_vmult(int branch, const KParams<T> &p, const ShapeHost &sh, cu
         if (ensure_smem(k_vmult_generic<dim, n, T, BR_RESIDUAL>, sm))
           return 1;
         k_vmult_generic<dim, n, T, BR_RESIDUAL><<<GLSB_GRID(G, p), G::THREADS, sm, s>>>(p, S);
+    }
+  return cudaGetLastError() != cudaSuccess;
+}
+
+template <int dim, int n, typename T>
+static int launch_matrix(int branch, uint32_t n_columns, const KParams<T> &p, const ShapeHost &sh, cudaStream_t s)
+{
+  using G = Geo<dim, n>;
+  if (p.cell_end <= p.cell_begin || n_columns == 0)
+    return 0;
+  const size_t sm = generic_smem_bytes<dim, n, T>();
+  const auto   S  = to_shape<T, n>(sh);
+  const dim3   grid(GLSB_GRID(G, p), n_columns);
+  if (branch == BR_NEWTON)
+    {
+      if (ensure_smem(k_vmult_generic<dim, n, T, BR_NEWTON, true>, sm))
+        return 1;
+      k_vmult_generic<dim, n, T, BR_NEWTON, true><<<grid, G::THREADS, sm, s>>>(p, S);
+    }
+  else
+    {
+      if (ensure_smem(k_vmult_generic<dim, n, T, BR_FIXED_POINT, true>, sm))
+        return 1;
+      k_vmult_generic<dim, n, T, BR_FIXED_POINT, true><<<grid, G::THREADS, sm, s>>>(p, S);
     }
   return cudaGetLastError() != cudaSuccess;
 }
@@ -184,6 +211,14 @@ template <>
 int Kernels<GLSB_DIM, GLSB_REAL>::vmult(int n, int branch, const KParams<GLSB_REAL> &p, const ShapeHost &sh,
                                         cudaStream_t s)
 {
+#if GLSB_DIM == 3
+  // degrees 3 and 4: the column kernel (glsb_col.cuh); GLSB_NO_COL=1 keeps the generic kernel (cross-checks)
+  static const bool no_col = getenv("GLSB_NO_COL") != nullptr;
+  if (!no_col && n == 4)
+    return col::launch<4, GLSB_REAL>(branch, p, to_shape<GLSB_REAL, 4>(sh), s);
+  if (!no_col && n == 5)
+    return col::launch<5, GLSB_REAL>(branch, p, to_shape<GLSB_REAL, 5>(sh), s);
+#endif
 #define CALL(N) launch_vmult<GLSB_DIM, N, GLSB_REAL>(branch, p, sh, s)
   GLSB_SWITCH_N(CALL)
 #undef CALL
@@ -256,6 +291,15 @@ int Kernels<GLSB_DIM, GLSB_REAL>::vmult_q2(const KParams<GLSB_REAL> &p, const Sh
   (void)p, (void)sh, (void)F, (void)s;
   return -1;
 #endif
+}
+
+template <>
+int Kernels<GLSB_DIM, GLSB_REAL>::matrix_columns(int n, int branch, uint32_t n_columns, const KParams<GLSB_REAL> &p,
+                                                 const ShapeHost &sh, cudaStream_t s)
+{
+#define CALL(N) launch_matrix<GLSB_DIM, N, GLSB_REAL>(branch, n_columns, p, sh, s)
+  GLSB_SWITCH_N(CALL)
+#undef CALL
 }
 
 template <>

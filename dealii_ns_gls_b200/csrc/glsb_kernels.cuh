@@ -519,7 +519,23 @@ __device__ __forceinline__ void cell_apply(Ctx<dim, n, T> &ctx, const KParams<T>
   ctx.integrate(vout, rgq);
 }
 
-template <int dim, int n, typename T, int BR>
+// value of the unit vector e_col at (possibly constrained) index iv, resolved like read_dof_values
+template <typename T>
+__device__ __forceinline__ T unit_resolved(const KParams<T> &p, uint32_t iv, uint32_t col)
+{
+  if (!(iv & GLSB_CONSTRAINED_BIT))
+    return iv == col ? T(1) : T(0);
+  const uint32_t r = iv & ~GLSB_CONSTRAINED_BIT;
+  T              s = 0;
+  for (uint32_t e = p.row_ptr[r]; e < p.row_ptr[r + 1]; ++e)
+    if (p.ecol[e] == col)
+      s += p.eval[e];
+  return s;
+}
+
+// UNIT: get_system_matrix -- blockIdx.y is a column j: src is the unit vector e_j (never materialised), dst the
+// j-th column of a column-major n x n matrix (p.dst + j * p.unit_stride): all columns in ONE launch
+template <int dim, int n, typename T, int BR, bool UNIT = false>
 __global__ void __launch_bounds__(Geo<dim, n>::THREADS, GLSB_GEN_CTAS) k_vmult_generic(const KParams<T> p, const Shape<T, n> sh)
 {
   using G = Geo<dim, n>;
@@ -529,6 +545,7 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS, GLSB_GEN_CTAS) k_vmult_g
   const uint32_t cell0  = p.cell_begin + blockIdx.x * G::CPB + ctx.cb;
   const bool     active = cell_active(p, cell0);
   const uint32_t cell   = cell0 < p.cell_end ? cell0 : p.cell_end - 1;
+  T             *dst    = UNIT ? p.dst + (uint64_t)blockIdx.y * p.unit_stride : p.dst;
   uint32_t       iv[G::C];
 #pragma unroll
   for (int c = 0; c < G::C; ++c)
@@ -540,8 +557,8 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS, GLSB_GEN_CTAS) k_vmult_g
   load_tables<dim, T, BR>(p, qpos(p, (uint32_t)ctx.l, cell), cell, tb);
 #pragma unroll
   for (int c = 0; c < G::C; ++c)
-    ctx.v[ctx.at(c, ctx.l)] =
-      (BR == BR_RESIDUAL) ? p.src[plain_index(p, iv[c])] : gather_resolved(p, p.src, iv[c]);
+    ctx.v[ctx.at(c, ctx.l)] = UNIT ? unit_resolved(p, iv[c], blockIdx.y) :
+                              (BR == BR_RESIDUAL) ? p.src[plain_index(p, iv[c])] : gather_resolved(p, p.src, iv[c]);
   __syncthreads();
   cell_apply<dim, n, T, BR>(ctx, p, geo, tb);
   if (active)
@@ -552,7 +569,8 @@ __global__ void __launch_bounds__(Geo<dim, n>::THREADS, GLSB_GEN_CTAS) k_vmult_g
           T r = ctx.v[ctx.at(c, ctx.l)];
           if (p.sign_negative)
             r = -r;
-          scatter_resolved(p, p.dst, iv[c], r);
+          if (!UNIT || r != T(0))
+            scatter_resolved(p, dst, iv[c], r);
         }
     }
 }
