@@ -267,6 +267,26 @@ __global__ void k_late_flags(const uint32_t *__restrict__ last, const uint64_t *
     ++c;
   flag[d] = last[d] > c;
 }
+// compact the flags into an index list (order irrelevant); count may exceed capacity: the caller then keeps the scan
+__global__ void k_compact_flags(const uint8_t *__restrict__ flag, uint64_t n, uint32_t *__restrict__ list,
+                                uint32_t capacity, unsigned long long *__restrict__ count)
+{
+  const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < n && flag[d])
+    {
+      const unsigned long long k = atomicAdd(count, 1ull);
+      if (k < capacity)
+        list[k] = (uint32_t)d;
+    }
+}
+template <typename T>
+__global__ void k_flush_listed(T *__restrict__ host_dst, const T *__restrict__ dev_dst, const uint32_t *__restrict__ list,
+                               uint32_t m)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < m)
+    host_dst[list[t]] = dev_dst[list[t]];
+}
 // re-send the flagged entries with stores to the (mapped, page-locked) host vector
 template <typename T>
 __global__ void k_flush_flagged(T *__restrict__ host_dst, const T *__restrict__ dev_dst,
@@ -366,6 +386,7 @@ struct glsb_op
     std::vector<uint32_t>    cidx_end;   // [n_chunks] constrained indices (sorted) below out_end[c]
     std::vector<uint32_t>    cidx_end_spec; // ... below in_end[c] (speculative download)
     DevBuf                   src, dst, late_flag; // late_flag[d]: entry d changes after its speculative download
+    DevBuf                   late_list;           // the same as a compact index list (n_late entries), if it fits
     uint64_t                 n_late = 0;
   } hp, hpp; // hpp: the pipeline of partitioned operators (interior cells only, glsb_vmult_host_begin / _finish)
   std::vector<uint32_t> cidx_sorted;
@@ -1516,6 +1537,28 @@ int glsb_get_system_matrix(glsb_op *op, double *A_dev, double weight, void *stre
 //     the Morton curve, where low-numbered surface nodes are touched by cells far down the cell order;
 //   * conservative mode (pageable dst_host): dst[0, out_end[c]) is sent once no later chunk touches it.
 // PCIe is full duplex, so the total is ~ max(upload, download) instead of upload + kernels + download.
+// late_flag -> late_list (n_late entries); leaves late_list empty when more than 1/8 of the entries are late
+static void compact_late(glsb_op::HostPipe &hp, uint64_t n)
+{
+  const uint32_t cap = (uint32_t)std::min<uint64_t>(n / 8 + 1024, 0x7fffffffull);
+  DevBuf         cnt;
+  if (!hp.late_list.alloc((size_t)cap * 4) || !cnt.alloc(8))
+    {
+      hp.late_list.release();
+      return;
+    }
+  cudaMemset(cnt.p, 0, 8);
+  k_compact_flags<<<(unsigned)((n + 255) / 256), 256>>>(hp.late_flag.as<uint8_t>(), n, hp.late_list.as<uint32_t>(), cap,
+                                                        cnt.as<unsigned long long>());
+  unsigned long long m = 0;
+  if (cudaMemcpy(&m, cnt.p, 8, cudaMemcpyDeviceToHost) != cudaSuccess || m > cap)
+    {
+      hp.late_list.release();
+      return;
+    }
+  hp.n_late = m;
+}
+
 static int host_pipe_setup(glsb_op *op)
 {
   glsb_op::HostPipe &hp = op->hp;
@@ -1593,6 +1636,7 @@ static int host_pipe_setup(glsb_op *op)
                                                              hp.late_flag.as<uint8_t>(), n_local);
     if (cudaDeviceSynchronize() != cudaSuccess)
       return 1;
+    compact_late(hp, n_local);
   }
   if (cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking) != cudaSuccess)
@@ -1702,7 +1746,17 @@ int glsb_vmult_host(glsb_op *op, void *dst_host, const void *src_host, double we
   if (dst_mapped)
     {
       // after the last range has landed: re-send what later chunks changed
-      if (op->number_type == GLSB_F64)
+      if (hp.late_list.p)
+        {
+          const uint32_t m = (uint32_t)hp.n_late;
+          if (m && op->number_type == GLSB_F64)
+            k_flush_listed<double><<<(m + 255) / 256, 256, 0, s>>>((double *)dst_mapped, (const double *)d_dst,
+                                                                 hp.late_list.as<uint32_t>(), m);
+          else if (m)
+            k_flush_listed<float><<<(m + 255) / 256, 256, 0, s>>>((float *)dst_mapped, (const float *)d_dst,
+                                                                hp.late_list.as<uint32_t>(), m);
+        }
+      else if (op->number_type == GLSB_F64)
         k_flush_flagged<double><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((double *)dst_mapped, (const double *)d_dst,
                                                                           hp.late_flag.as<uint8_t>(), n);
       else
@@ -1778,6 +1832,7 @@ static int host_pipe_setup_part(glsb_op *op)
                                                                  hp.late_flag.as<uint8_t>(), op->n_owned);
     if (cudaDeviceSynchronize() != cudaSuccess)
       return 1;
+    compact_late(hp, op->n_owned);
   }
   if (cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking) != cudaSuccess)
@@ -1890,7 +1945,17 @@ int glsb_vmult_host_finish(glsb_op *op, void *d_dst_v, void *dst_host, void *str
   cudaEventRecord(hp.e_done, hp.s_out);
   cudaStreamWaitEvent(s, hp.e_done, 0);
   const uint64_t n = op->n_owned;
-  if (op->number_type == GLSB_F64)
+  if (hp.late_list.p)
+    {
+      const uint32_t m = (uint32_t)hp.n_late;
+      if (m && op->number_type == GLSB_F64)
+        k_flush_listed<double><<<(m + 255) / 256, 256, 0, s>>>((double *)at.devicePointer, (const double *)d_dst_v,
+                                                             hp.late_list.as<uint32_t>(), m);
+      else if (m)
+        k_flush_listed<float><<<(m + 255) / 256, 256, 0, s>>>((float *)at.devicePointer, (const float *)d_dst_v,
+                                                            hp.late_list.as<uint32_t>(), m);
+    }
+  else if (op->number_type == GLSB_F64)
     k_flush_flagged<double><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((double *)at.devicePointer, (const double *)d_dst_v,
                                                                       hp.late_flag.as<uint8_t>(), n);
   else

@@ -171,4 +171,47 @@ struct Kernels
   static int vmult_q2(const KParams<T> &p, const ShapeHost &sh, int n_stage_fields, cudaStream_t s);
 };
 
+template <typename T, int n>
+inline Shape<T, n> to_shape(const ShapeHost &h)
+{
+  Shape<T, n> s;
+  for (int i = 0; i < n * n; ++i)
+    {
+      s.S[i] = (T)h.S[i];
+      s.D[i] = (T)h.D[i];
+      s.G[i] = (T)h.G[i];
+    }
+  for (int i = 0; i < n; ++i)
+    s.w[i] = (T)h.w[i];
+  for (int q = 0; q < n; ++q)
+    for (int j = 0; j < n; ++j)
+      {
+        s.Sw[q * n + j] = (T)(h.w[q] * h.S[q * n + j]);
+        s.Gw[q * n + j] = (T)(h.w[q] * h.G[q * n + j]);
+        s.Dt[q * n + j] = (T)(h.D[q * n + j] * h.w[q] / h.w[j]);
+      }
+  return s;
+}
+
+// register-tiled vmult kernel (glsb_q2.cuh), one translation unit per (Number, n): glsb_inst_q2.cu.
+// Return -1 if the variant does not apply (the caller falls back to the generic / column kernel).
+namespace q2
+{
+template <typename T, int n>
+int launch_degree(const KParams<T> &p, const ShapeHost &sh, int F, cudaStream_t s);
+int launch_packed_q2(const KParams<float> &p, const ShapeHost &sh, int F, cudaStream_t s); // float, FFMA2
+inline int launch_packed_q2(const KParams<double> &, const ShapeHost &, int, cudaStream_t) { return -1; }
+// Q3 / Q4: 2 n^3 values per lane fit in float only
+template <int n>
+inline int launch_float_only(const KParams<float> &p, const ShapeHost &sh, int F, cudaStream_t s)
+{
+  return launch_degree<float, n>(p, sh, F, s);
+}
+template <int n>
+inline int launch_float_only(const KParams<double> &, const ShapeHost &, int, cudaStream_t)
+{
+  return -1;
+}
+} // namespace q2
+
 } // namespace glsb

@@ -1,9 +1,6 @@
 // One translation unit per (dim, Number): compile with -DGLSB_DIM=2|3 -DGLSB_REAL=double|float.
 #include "glsb_kernels.cuh"
 #include <cstdlib>
-#ifdef GLSB_WITH_Q2
-#include "glsb_q2.cuh"
-#endif
 #if GLSB_DIM == 3
 #include "glsb_col.cuh"
 #endif
@@ -17,27 +14,6 @@
 
 namespace glsb
 {
-template <typename T, int n>
-static Shape<T, n> to_shape(const ShapeHost &h)
-{
-  Shape<T, n> s;
-  for (int i = 0; i < n * n; ++i)
-    {
-      s.S[i] = (T)h.S[i];
-      s.D[i] = (T)h.D[i];
-      s.G[i] = (T)h.G[i];
-    }
-  for (int i = 0; i < n; ++i)
-    s.w[i] = (T)h.w[i];
-  for (int q = 0; q < n; ++q)
-    for (int j = 0; j < n; ++j)
-      {
-        s.Sw[q * n + j] = (T)(h.w[q] * h.S[q * n + j]);
-        s.Gw[q * n + j] = (T)(h.w[q] * h.G[q * n + j]);
-        s.Dt[q * n + j] = (T)(h.D[q * n + j] * h.w[q] / h.w[j]);
-      }
-  return s;
-}
 
 template <typename K>
 static int ensure_smem(K kernel, size_t bytes)
@@ -255,38 +231,20 @@ template <>
 int Kernels<GLSB_DIM, GLSB_REAL>::vmult_q2(const KParams<GLSB_REAL> &p, const ShapeHost &sh, int F, cudaStream_t s)
 {
 #if GLSB_DIM == 3 && defined(GLSB_WITH_Q2)
-  if (sh.n == 2) // Q1: same kernel, 8 values per lane
+  // one translation unit per (Number, degree) of the register-tiled kernel: glsb_inst_q2.cu
+  switch (sh.n)
     {
-      const auto S = to_shape<GLSB_REAL, 2>(sh);
-      if (p.geom == GLSB_GEOM_GENERAL)
-        return q2::launch_flags<GLSB_REAL, GLSB_REAL, true, 2>(p, S, F, s);
-      return q2::launch_flags<GLSB_REAL, GLSB_REAL, false, 2>(p, S, F, s);
-    }
-  if (sh.n == 4) // Q3: 2 x 64 values per lane fit the register file in float only (the level operators)
-    {
-      if (sizeof(GLSB_REAL) != 4)
+      case 2:
+        return q2::launch_degree<GLSB_REAL, 2>(p, sh, F, s);
+      case 3:
+        return p.packed ? q2::launch_packed_q2(p, sh, F, s) : q2::launch_degree<GLSB_REAL, 3>(p, sh, F, s);
+      case 4:
+        return q2::launch_float_only<4>(p, sh, F, s);
+      case 5:
+        return q2::launch_float_only<5>(p, sh, F, s);
+      default:
         return -1;
-      return q2::launch_q3_float(p, to_shape<GLSB_REAL, 4>(sh), F, s);
     }
-  if (sh.n == 5) // Q4: float only (TSM)
-    {
-      if (sizeof(GLSB_REAL) != 4)
-        return -1;
-      return q2::launch_q4_float(p, to_shape<GLSB_REAL, 5>(sh), F, s);
-    }
-  if (sh.n != 3)
-    return -1;
-  const auto S = to_shape<GLSB_REAL, 3>(sh);
-  if (p.packed) // float only: two cells per lane, FFMA2 arithmetic
-    {
-      const auto S2 = q2::to_packed_shape(S);
-      if (p.geom == GLSB_GEOM_GENERAL)
-        return q2::launch_flags<GLSB_REAL, q2::PackedOf<GLSB_REAL>::type, true>(p, S2, F, s);
-      return q2::launch_flags<GLSB_REAL, q2::PackedOf<GLSB_REAL>::type, false>(p, S2, F, s);
-    }
-  if (p.geom == GLSB_GEOM_GENERAL)
-    return q2::launch_flags<GLSB_REAL, GLSB_REAL, true>(p, S, F, s);
-  return q2::launch_flags<GLSB_REAL, GLSB_REAL, false>(p, S, F, s);
 #else
   (void)p, (void)sh, (void)F, (void)s;
   return -1;

@@ -821,21 +821,5 @@ static int launch_flags(const KParams<T> &p, const Shape<V, n> &S, int F, cudaSt
                        launch<T, V, GENERAL, false, false, n>(p, S, F, s);
 }
 
-// Q3 / Q4 (n = 4, 5) exist for float only; the double overloads keep the dispatch code of glsb_inst.cu compilable
-static int launch_q3_float(const KParams<float> &p, const Shape<float, 4> &S, int F, cudaStream_t s)
-{
-  if (p.geom == GLSB_GEOM_GENERAL)
-    return launch_flags<float, float, true, 4>(p, S, F, s);
-  return launch_flags<float, float, false, 4>(p, S, F, s);
-}
-static int launch_q3_float(const KParams<double> &, const Shape<double, 4> &, int, cudaStream_t) { return -1; }
-static int launch_q4_float(const KParams<float> &p, const Shape<float, 5> &S, int F, cudaStream_t s)
-{
-  if (p.geom == GLSB_GEOM_GENERAL)
-    return launch_flags<float, float, true, 5>(p, S, F, s);
-  return launch_flags<float, float, false, 5>(p, S, F, s);
-}
-static int launch_q4_float(const KParams<double> &, const Shape<double, 5> &, int, cudaStream_t) { return -1; }
-
 } // namespace q2
 } // namespace glsb

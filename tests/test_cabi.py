@@ -105,3 +105,31 @@ def test_bench_reference_arm_prints_one_json_line():
         assert key in d
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_transfer_and_vector_entry_points_fail_loudly():
+    """the multigrid-transfer and Krylov entry points reject bad descriptors / null pointers with a non-zero
+    status and never fall back to the CPU"""
+    lib = L.load()
+    d = L.GlsbTransferDesc()
+    d.abi_version = 99
+    h = C.c_void_p()
+    assert lib.glsb_transfer_create(C.byref(d), C.byref(h)) != 0
+    assert b"abi" in lib.glsb_transfer_last_error(None).lower()
+    d.abi_version = L.GLSB_ABI_VERSION
+    d.dim, d.degree, d.number_type = 4, 2, L.GLSB_F32
+    assert lib.glsb_transfer_create(C.byref(d), C.byref(h)) != 0
+    assert b"dim" in lib.glsb_transfer_last_error(None)
+    d.dim = 3
+    import torch
+    if not torch.cuda.is_available():
+        assert lib.glsb_transfer_create(C.byref(d), C.byref(h)) != 0
+        assert b"no usable CUDA device" in lib.glsb_transfer_last_error(None)
+    assert lib.glsb_transfer_prolongate_and_add(None, None, None, None) != 0
+    assert lib.glsb_vec_multi_dot(None, None, 0, 1, None, 0, L.GLSB_F64, None) != 0
+    assert lib.glsb_vec_multi_axpy(None, None, 0, 1, None, 1.0, 0, L.GLSB_F64, None) != 0
+    assert lib.glsb_vec_axpby(None, 1.0, None, 0.0, 0, L.GLSB_F64, None) != 0
+    assert lib.glsb_vec_convert(None, L.GLSB_F64, None, L.GLSB_F32, 0, None) != 0
+    assert lib.glsb_dense_apply(None, None, None, 1, 1, L.GLSB_F64, None) != 0
+    assert lib.glsb_get_system_matrix(None, None, 0.0, None) != 0
+    assert lib.glsb_vmult_host_begin(None, None, None, None, None, 0.0, None) != 0
