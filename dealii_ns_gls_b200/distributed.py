@@ -101,6 +101,12 @@ class GhostExchange:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return float(t[0])
 
+    def allreduce_sum(self, vals) -> list:
+        """MPI::sum of a few scalars (norms / inner products of distributed vectors)"""
+        t = torch.tensor(list(vals), dtype=torch.float64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return [float(x) for x in t]
+
     # ---- vmult ----
     SM_RESERVE = 8  # multiprocessors left to the NCCL send/recv kernels next to the persistent cell kernel
     # exchanged bytes per vmult above which the exchanges are hidden behind the interior cells.  Below it

@@ -387,7 +387,9 @@ def hypercube_slab(n_per_dir, degree, *, n_ranks=1, rank=0, dim=3, order="morton
     ln = local_of_node[cell_nodes]
     cell_dofs = np.concatenate([ln * C + c for c in range(C)], axis=1)
 
-    part = RankPartition(rank=rank, n_ranks=n_ranks, n_owned=n_owned, n_ghost=n_ghost, owned_offset=0,
+    # rank 0 owns all its node planes, every other rank all but its bottom plane
+    first_owned = 0 if rank == 0 else C * plane * (p * n_per_dir * rank + 1)
+    part = RankPartition(rank=rank, n_ranks=n_ranks, n_owned=n_owned, n_ghost=n_ghost, owned_offset=first_owned,
                          ghost_global=np.zeros(0, dtype=np.int64), ghost_owner=np.full(n_ghost, rank - 1))
     if rank > 0:
         part.recv.append((rank - 1, 0, n_ghost))

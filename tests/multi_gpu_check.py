@@ -70,6 +70,43 @@ def main():
     print(f"rank {rank}/{world}: vmult rel_l2 {e1:.2e}  inv_diag rel_l2 {e2:.2e}  max_u err {e3:.1e}  "
           f"interior/boundary cells {m.n_cells - int(m.cell_is_boundary.sum())}/{int(m.cell_is_boundary.sum())} "
           f"variant {op.vmult_variant()}  {'OK' if ok else 'FAIL'}", flush=True)
+    # relaxation smoother on the partitioned operator: omega from the distributed power iteration and 5 sweeps,
+    # against the CPU restatement on the union of the slabs in the SAME global numbering (owner offset + local)
+    from dealii_ns_gls_b200.smoother import PreconditionRelaxation
+    from oracle import gls_oracle as go
+    from oracle.gls_smoother import OracleRelaxation
+    sm = PreconditionRelaxation(op, diag)
+    sm.estimate_eigenvalues()
+    bvec = torch.tensor(field(m.canonical_ids, 3), device=dev)
+    bvec[m.n_owned:] = 0
+    xs = op.initialize_dof_vector()
+    sm.vmult(xs, bvec)
+    canon_to_global = np.zeros(ng, dtype=np.int64)
+    for mm in meshes:
+        canon_to_global[mm.canonical_ids[: mm.n_owned]] = mm.partition.owned_offset + np.arange(mm.n_owned)
+    gl = [canon_to_global[mm.canonical_ids] for mm in meshes]
+    union_dofs = np.concatenate([g[mm.cell_dofs.astype(np.int64)] for g, mm in zip(gl, meshes)])
+    union_pts = np.concatenate([mm.cell_points for mm in meshes])
+    ou = go.OracleOperator(dim=3, degree=degree, cell_dofs=union_dofs, n_dofs=ng, cell_points=union_pts,
+                           mapping_degree=1, constraints={}, nu=0.1, c1=4.0, c2=2.0, theta=1.0, order=2,
+                           consider_time_derivative=False, increment_form=True, cell_wise_stabilization=True,
+                           path="sumfac")
+    to_global = np.zeros(ng)
+    for g, mm in zip(gl, meshes):
+        to_global[g] = field(mm.canonical_ids, 1)
+    ou.set_linearization_point(to_global, 0.1)
+    osm = OracleRelaxation(ou, w, ou.compute_inverse_diagonal(w))
+    osm.estimate_eigenvalues()
+    bg = np.zeros(ng)
+    for g, mm in zip(gl, meshes):
+        bg[g] = field(mm.canonical_ids, 3)
+    xref = osm.vmult(bg)
+    e5 = abs(sm.get_relaxation() / osm.get_relaxation() - 1.0)
+    e6 = np.linalg.norm(xs[: m.n_owned].cpu().numpy() - xref[gl[rank][: m.n_owned]]) / np.linalg.norm(xref)
+    ok56 = e5 < 1e-10 and e6 < 1e-10
+    print(f"rank {rank}/{world}: relaxation omega rel err {e5:.1e}  5 sweeps rel_l2 {e6:.1e}  {'OK' if ok56 else 'FAIL'}",
+          flush=True)
+    ok = ok and ok56
     # host-vector entry of a partitioned operator: chunked pipeline + exchange in between (glsb_vmult_host_begin /
     # _finish) against the device-vector vmult, on a mesh large enough for several chunks and with Dirichlet rows
     n2 = int(os.environ.get("GLSB_CHECK_CELLS", "48"))
