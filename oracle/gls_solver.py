@@ -199,6 +199,14 @@ def gmres(A, M, b, *, rel_tol=1e-2, abs_tol=1e-12, max_iter=10000, basis=28):
             return x, it, hist
 
 
+class _TimeNone:
+    """TimeIntegratorDataNone (include/time_integration.cc:141-178): order 0, weight 0, dt = 1"""
+    weights = [0.0]
+
+    def update_dt(self, dt):
+        pass
+
+
 class OracleChannelDriver:
     """Driver<dim>::run for the channel (main.cc:220-1000), all on the CPU oracle."""
 
@@ -207,7 +215,7 @@ class OracleChannelDriver:
                  rel_tol=1e-2, abs_tol=1e-12, newton_inexact=False, level_dtype=np.float64):
         self.dim, self.cfl, self.min_dx = dim, cfl, min_dx
         self.lo, self.hi = min(meshes), max(meshes)
-        self.bdf = go.OracleBDF(bdf_order)
+        self.bdf = go.OracleBDF(bdf_order) if bdf_order > 0 else _TimeNone()
         self.rel_tol, self.abs_tol, self.inexact = rel_tol, abs_tol, newton_inexact
 
         def make(mesh, dtype):
@@ -259,6 +267,9 @@ class OracleChannelDriver:
         dt = self.min_dx * self.cfl / max(u_max, 1.0)
         self.bdf.update_dt(dt)
         w = self.bdf.weights
+        dt_loop = dt
+        if isinstance(self.bdf, _TimeNone):
+            dt = 1.0  # get_current_dt() of the "none" scheme; the loop body runs once (main.cc:982-987)
         for i in range(len(self.history) - 2, -1, -1):
             self.history[i + 1] = self.history[i].copy()
         order = len(self.history) - 1
@@ -289,7 +300,7 @@ class OracleChannelDriver:
             if it > 30:
                 raise RuntimeError("Newton iteration did not converge")
         self._distribute(sol)
-        self.t += dt
-        rec = dict(t=self.t, dt=dt, u_max=u_max, newton_iterations=it, newton_residuals=res, linear_iterations=lin)
+        self.t += dt_loop
+        rec = dict(t=self.t, dt=dt_loop, u_max=u_max, newton_iterations=it, newton_residuals=res, linear_iterations=lin)
         self.log.append(rec)
         return rec

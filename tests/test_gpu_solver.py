@@ -128,8 +128,10 @@ def test_vcycle_matches_oracle(mg_number, tol):
                                 dict(n_global_refinements=0, fe_degree=2),
                                 dict(dim=3, n_global_refinements=0, fe_degree=1),
                                 dict(n_global_refinements=0, bdf_order=2),
-                                dict(n_global_refinements=0, cell_wise_stabilization=False, nu=0.01)],
-                         ids=["q1", "q1_r1", "q2", "3d_q1", "bdf2", "qwise"])
+                                dict(n_global_refinements=0, cell_wise_stabilization=False, nu=0.01),
+                                dict(n_global_refinements=0, time_integration="none", fe_degree=2,
+                                     cell_wise_stabilization=False, nu=0.05)],
+                         ids=["q1", "q1_r1", "q2", "3d_q1", "bdf2", "qwise", "stationary_q2"])
 @pytest.mark.parametrize("mg_number", ["double", "float"])
 def test_channel_time_steps_identical_iteration_counts(kw, mg_number):
     """the north-star's solver-level criterion, as far as it can be checked without deal.II: the Newton and

@@ -71,7 +71,8 @@ def _oracle_driver(p, **kw):
     return gs.OracleChannelDriver(dim=p.dim, degree=p.fe_degree, meshes=meshes, children=children,
                                   constraints_inhomogeneous=ci.rows, inhomogeneities=ci.inhomogeneities,
                                   min_dx=np.sqrt(p.dim) / 2 ** n_levels, nu=p.nu, c1=p.c_1, c2=p.c_2, cfl=p.cfl,
-                                  bdf_order=p.bdf_order, consider_time_derivative=p.consider_time_derivative,
+                                  bdf_order=p.bdf_order if p.time_integration == "bdf" else 0,
+                                  consider_time_derivative=p.consider_time_derivative,
                                   cell_wise_stabilization=p.cell_wise_stabilization,
                                   rel_tol=p.lin_relative_tolerance, abs_tol=p.lin_absolute_tolerance, **kw)
 
