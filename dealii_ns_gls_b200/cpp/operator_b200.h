@@ -21,6 +21,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/glsb200.h"
@@ -375,6 +376,110 @@ private:
   glsb_op                  *op = nullptr;
   std::uint64_t             n_local, n_global;
   cudaStream_t              stream;
+};
+
+// ---------------------------------------------------------------------------------------------
+// the device pieces of the callers, C++ side
+// ---------------------------------------------------------------------------------------------
+template <typename Number>
+constexpr int number_type_of()
+{
+  return std::is_same<Number, double>::value ? GLSB_F64 : GLSB_F32;
+}
+
+// deal.II's MGTwoLevelTransfer<dim, VectorType> between a level and the next coarser one (main.cc:540-563):
+// reinit() takes what the two DoFHandlers give -- the coarse cells' dof indices (GLSB_CONSTRAINED_BIT | row for
+// constrained ones), their children's fine dof indices, the coarse constraint rows and deal.II's weights.
+template <int dim, typename Number>
+class MGTwoLevelTransfer
+{
+public:
+  MGTwoLevelTransfer() = default;
+  MGTwoLevelTransfer(const MGTwoLevelTransfer &) = delete;
+  ~MGTwoLevelTransfer() { glsb_transfer_destroy(t_); }
+
+  void reinit(int degree, std::uint64_t n_fine_dofs, std::uint64_t n_coarse_dofs,
+              const std::vector<std::uint32_t> &coarse_dof_indices, const std::vector<std::uint32_t> &fine_dof_indices,
+              const std::vector<double> &weights, const std::vector<std::uint32_t> &row_ptr = {},
+              const std::vector<std::uint32_t> &entry_col = {}, const std::vector<double> &entry_val = {})
+  {
+    glsb_transfer_destroy(t_);
+    t_ = nullptr;
+    const std::uint64_t ndof = (dim + 1) * (dim == 2 ? (degree + 1) * (degree + 1) : (degree + 1) * (degree + 1) * (degree + 1));
+    glsb_transfer_desc  d{};
+    d.abi_version = GLSB_ABI_VERSION;
+    cuda_check(cudaGetDevice(&d.device), "cudaGetDevice");
+    d.dim = dim, d.degree = degree, d.number_type = number_type_of<Number>();
+    d.n_coarse_cells = coarse_dof_indices.size() / ndof;
+    d.n_fine_dofs = n_fine_dofs, d.n_coarse_dofs = n_coarse_dofs;
+    d.coarse_dof_indices = coarse_dof_indices.data(), d.fine_dof_indices = fine_dof_indices.data();
+    d.n_constraint_rows = row_ptr.empty() ? 0 : (std::uint32_t)row_ptr.size() - 1;
+    d.row_ptr = row_ptr.data(), d.entry_col = entry_col.data(), d.entry_val = entry_val.data();
+    d.weights = weights.empty() ? nullptr : weights.data();
+    if (glsb_transfer_create(&d, &t_) != 0)
+      throw Error(std::string("glsb_transfer_create: ") + glsb_transfer_last_error(nullptr));
+  }
+  void prolongate_and_add(DeviceVector<Number> &dst_fine, const DeviceVector<Number> &src_coarse) const
+  {
+    check(glsb_transfer_prolongate_and_add(t_, dst_fine.data(), src_coarse.data(), nullptr));
+  }
+  void restrict_and_add(DeviceVector<Number> &dst_coarse, const DeviceVector<Number> &src_fine) const
+  {
+    check(glsb_transfer_restrict_and_add(t_, dst_coarse.data(), src_fine.data(), nullptr));
+  }
+  void interpolate(DeviceVector<Number> &dst_coarse, const DeviceVector<Number> &src_fine) const
+  {
+    check(glsb_transfer_interpolate(t_, dst_coarse.data(), src_fine.data(), nullptr));
+  }
+
+private:
+  void check(int rc) const
+  {
+    if (rc != 0)
+      throw Error(std::string("glsb_transfer: ") + glsb_transfer_last_error(t_));
+  }
+  glsb_transfer *t_ = nullptr;
+};
+
+// the vector operations deal.II's SolverGMRES / Multigrid do on LinearAlgebra::distributed::Vector
+// (solver_l.cc:46-74), on device vectors
+template <typename Number>
+struct DeviceVectorOps
+{
+  static void chk(int rc, const char *what)
+  {
+    if (rc != 0)
+      throw Error(std::string(what) + " failed");
+  }
+  // y = a x + b y
+  static void axpby(DeviceVector<Number> &y, double a, const DeviceVector<Number> &x, double b)
+  {
+    chk(glsb_vec_axpby(y.data(), a, x.data(), b, y.size(), number_type_of<Number>(), nullptr), "glsb_vec_axpby");
+  }
+  // out[j] = V_j . w, j < k, V = k vectors of length w.size() stored back to back
+  static std::vector<double> multi_dot(const DeviceVector<Number> &V, int k, const DeviceVector<Number> &w)
+  {
+    DeviceVector<double> out(k);
+    chk(glsb_vec_multi_dot(out.data(), V.data(), w.size(), k, w.data(), w.size(), number_type_of<Number>(), nullptr),
+        "glsb_vec_multi_dot");
+    return out.to_host();
+  }
+  // w += scale * sum_j coef[j] V_j
+  static void multi_axpy(DeviceVector<Number> &w, const DeviceVector<Number> &V, const std::vector<double> &coef,
+                         double scale)
+  {
+    DeviceVector<double> c;
+    c.copy_from_host(coef);
+    chk(glsb_vec_multi_axpy(w.data(), V.data(), w.size(), (int)coef.size(), c.data(), scale, w.size(),
+                            number_type_of<Number>(), nullptr),
+        "glsb_vec_multi_axpy");
+  }
+  template <typename Other>
+  static void convert(DeviceVector<Number> &dst, const DeviceVector<Other> &src)
+  {
+    chk(glsb_vec_convert(dst.data(), number_type_of<Number>(), src.data(), number_type_of<Other>(), dst.size(), nullptr),
+        "glsb_vec_convert");
+  }
 };
 
 } // namespace glsb

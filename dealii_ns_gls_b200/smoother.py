@@ -14,7 +14,6 @@ import ctypes as C
 
 import torch
 
-from . import _lib as L
 
 
 class EigenvalueInformation:

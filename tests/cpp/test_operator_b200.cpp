@@ -34,6 +34,93 @@ static double rel_l2(const std::vector<double> &a, const std::vector<double> &b)
   return std::sqrt(d / n);
 }
 
+// two levels of a structured 2-D Q1 block (nx x ny coarse cells, refined once), lexicographic node numbering,
+// the dim + 1 components of a node consecutive: what MGTwoLevelTransfer::reinit receives
+static bool check_transfer_and_vector_ops()
+{
+  const int nx = 3, ny = 2, C = 3;
+  auto      node = [](int i, int j, int npx) { return j * npx + i; };
+  const int cpx = nx + 1, fpx = 2 * nx + 1, n_coarse = cpx * (ny + 1) * C, n_fine = fpx * (2 * ny + 1) * C;
+  std::vector<std::uint32_t> cidx, fidx;
+  std::vector<double>        touch(n_fine, 0.0);
+  auto cell_dofs = [&](int i, int j, int npx, std::vector<std::uint32_t> &out) {
+    for (int c = 0; c < C; ++c)
+      for (int l = 0; l < 4; ++l)
+        out.push_back((std::uint32_t)(node(i + (l & 1), j + (l >> 1), npx) * C + c));
+  };
+  for (int j = 0; j < ny; ++j)
+    for (int i = 0; i < nx; ++i)
+      {
+        cell_dofs(i, j, cpx, cidx);
+        for (int ch = 0; ch < 4; ++ch)
+          cell_dofs(2 * i + (ch & 1), 2 * j + (ch >> 1), fpx, fidx);
+      }
+  for (auto g : fidx)
+    touch[g] += 1.0;
+  std::vector<double> w(n_fine);
+  for (int g = 0; g < n_fine; ++g)
+    w[g] = 1.0 / touch[g];
+  glsb::MGTwoLevelTransfer<2, double> transfer;
+  transfer.reinit(1, n_fine, n_coarse, cidx, fidx, w);
+  // a (bi)linear function per component is prolongated exactly and interpolated back exactly
+  auto f = [](double x, double y, int c) { return (1 + c) * (0.3 + 2 * x - y + 0.5 * x * y); };
+  std::vector<double> hc(n_coarse), hf(n_fine);
+  for (int j = 0; j <= ny; ++j)
+    for (int i = 0; i <= nx; ++i)
+      for (int c = 0; c < C; ++c)
+        hc[node(i, j, cpx) * C + c] = f(i, j, c);
+  for (int j = 0; j <= 2 * ny; ++j)
+    for (int i = 0; i <= 2 * nx; ++i)
+      for (int c = 0; c < C; ++c)
+        hf[node(i, j, fpx) * C + c] = f(0.5 * i, 0.5 * j, c);
+  glsb::DeviceVector<double> dc, df(n_fine), back(n_coarse);
+  dc.copy_from_host(hc);
+  transfer.prolongate_and_add(df, dc);
+  const double e1 = rel_l2(df.to_host(), hf);
+  transfer.interpolate(back, df);
+  const double e2 = rel_l2(back.to_host(), hc);
+  // restriction is the transpose: (P c) . g == c . (P^T g)
+  std::vector<double> hg(n_fine);
+  for (int g = 0; g < n_fine; ++g)
+    hg[g] = std::sin(0.37 * g) + 0.1;
+  glsb::DeviceVector<double> dg, rc(n_coarse);
+  dg.copy_from_host(hg);
+  transfer.restrict_and_add(rc, dg);
+  using Ops = glsb::DeviceVectorOps<double>;
+  const double lhs = Ops::multi_dot(df, 1, dg)[0], rhs = Ops::multi_dot(dc, 1, rc)[0];
+  const double e3  = std::abs(lhs - rhs) / std::abs(lhs);
+  // batched inner products and the k-term update against host loops
+  const int k = 5, n = 1001;
+  std::vector<double> hV((size_t)k * n), hw(n), coef(k);
+  for (size_t i = 0; i < hV.size(); ++i)
+    hV[i] = std::cos(0.11 * i);
+  for (int i = 0; i < n; ++i)
+    hw[i] = std::sin(0.07 * i) - 0.2;
+  glsb::DeviceVector<double> V, wv;
+  V.copy_from_host(hV), wv.copy_from_host(hw);
+  const auto dots = Ops::multi_dot(V, k, wv);
+  double     e4   = 0;
+  for (int j = 0; j < k; ++j)
+    {
+      double s = 0;
+      for (int i = 0; i < n; ++i)
+        s += hV[(size_t)j * n + i] * hw[i];
+      e4      = std::max(e4, std::abs(s - dots[j]) / (1 + std::abs(s)));
+      coef[j] = 0.5 - 0.1 * j;
+    }
+  Ops::multi_axpy(wv, V, coef, -1.0);
+  std::vector<double> ref(hw);
+  for (int j = 0; j < k; ++j)
+    for (int i = 0; i < n; ++i)
+      ref[i] -= coef[j] * hV[(size_t)j * n + i];
+  const double e5 = rel_l2(wv.to_host(), ref);
+  glsb::DeviceVector<float> wf(n);
+  glsb::DeviceVectorOps<float>::convert(wf, wv);
+  std::printf("transfer: prolongation %.1e interpolation %.1e transpose %.1e; multi_dot %.1e multi_axpy %.1e\n", e1, e2, e3, e4,
+              e5);
+  return e1 < 1e-14 && e2 < 1e-14 && e3 < 1e-13 && e4 < 1e-13 && e5 < 1e-14 && std::abs(wf.to_host()[7] - (float)ref[7]) < 1e-6;
+}
+
 int main(int argc, char **argv)
 {
   if (argc < 2)
@@ -112,6 +199,7 @@ int main(int argc, char **argv)
           threw = true;
         }
       ok = ok && threw;
+      ok = check_transfer_and_vector_ops() && ok;
       std::printf(ok ? "PASS\n" : "FAIL\n");
       return ok ? 0 : 1;
     }

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from dealii_ns_gls_b200 import mesh as M
-from dealii_ns_gls_b200.driver import ChannelParameters, Driver, channel_level_mesh
+from dealii_ns_gls_b200.driver import ChannelParameters, Driver
 from oracle import gls_solver as gs
 from tests.test_solver_oracle import _oracle_driver
 from tests.util import rel_l2
