@@ -444,7 +444,7 @@ def main():
                     help="P = performance.cc hypercube (the headline); C = curved O-grid with the Turek-3D flags")
     ap.add_argument("--number", default="double", choices=["double", "float"],
                     help="double = Krylov operator (headline); float = multigrid level operator (config.h:7)")
-    ap.add_argument("--time-step-refinements", type=int, default=3,
+    ap.add_argument("--time-step-refinements", type=int, default=4,
                     help="n global refinements of the 3-D Q2 channel whose wall time per time step is reported "
                          "next to the vmult metric (3 -> 4.3e6 DoFs, 4 -> 3.4e7); -1 = skip")
     args = ap.parse_args()

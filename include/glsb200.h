@@ -301,7 +301,8 @@ int glsb_transfer_interpolate(glsb_transfer *t, void *dst_coarse, const void *sr
  * These are the same vector operations on device vectors, batched: one pass over the data for all k inner
  * products, one for the k-term update.  type = GLSB_F64 / GLSB_F32; results of reductions are double. */
 /* out_dev[j] = sum_i V[j * stride + i] * w[i], j < k  (out_dev: k doubles on the device, overwritten;
- * deterministic two-stage reduction) */
+ * deterministic two-stage reduction through one scratch buffer per device: calls on different streams of
+ * the same device must not overlap) */
 int glsb_vec_multi_dot(double *out_dev, const void *V, uint64_t stride, int k, const void *w, uint64_t n, int type,
                        void *stream);
 /* w[i] += scale * sum_j coef_dev[j] * V[j * stride + i]  (coef_dev: k doubles on the device) */
