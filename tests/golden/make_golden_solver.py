@@ -1,0 +1,50 @@
+"""Golden record of the solver-level behaviour of the CPU restatement (oracle/gls_solver.py):
+
+  python tests/golden/make_golden_solver.py     ->  tests/golden/solver_channel.json
+
+For each channel configuration of tests/test_gpu_solver.py: Newton and GMRES iteration counts, time-step
+sizes, first Newton residuals and the l2 norm of the solution after each of three time steps.  The reference
+has no recorded iteration counts, so this pins the ORACLE's solver stack (a later change
+that alters a count fails tests/test_solver_oracle.py) and gives the device path a file-based target."""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from dealii_ns_gls_b200.driver import ChannelParameters  # noqa: E402
+from tests.test_solver_oracle import _oracle_driver  # noqa: E402
+
+CASES = {
+    "q1": dict(n_global_refinements=0),
+    "q1_r1": dict(n_global_refinements=1),
+    "q2": dict(n_global_refinements=0, fe_degree=2),
+    "3d_q1": dict(dim=3, n_global_refinements=0, fe_degree=1),
+    "bdf2": dict(n_global_refinements=0, bdf_order=2),
+    "qwise": dict(n_global_refinements=0, cell_wise_stabilization=False, nu=0.01),
+    "stationary_q2": dict(n_global_refinements=0, time_integration="none", fe_degree=2, cell_wise_stabilization=False,
+                          nu=0.05),
+}
+
+
+def run(kw, n_steps=3):
+    d = _oracle_driver(ChannelParameters(**kw))
+    out = []
+    for _ in range(n_steps):
+        r = d.step()
+        out.append(dict(newton_iterations=r["newton_iterations"], linear_iterations=r["linear_iterations"],
+                        dt=r["dt"], first_residuals=[float(x) for x in r["newton_residuals"][:2]],
+                        solution_l2=float(np.linalg.norm(d.history[0]))))
+    return out
+
+
+if __name__ == "__main__":
+    rec = {name: dict(parameters=kw, steps=run(kw)) for name, kw in CASES.items()}
+    with open(os.path.join(HERE, "solver_channel.json"), "w") as f:
+        json.dump(rec, f, indent=1)
+    for name, r in rec.items():
+        print(name, [(s["newton_iterations"], s["linear_iterations"]) for s in r["steps"]])

@@ -147,3 +147,20 @@ def test_channel_time_steps_identical_iteration_counts(kw, mg_number):
         assert abs(rd["dt"] / ro["dt"] - 1) < tol
         assert np.allclose(rd["newton_residuals"][:2], ro["newton_residuals"][:2], rtol=tol)
         assert rel_l2(dev.solution.get_current_solution().cpu().numpy(), ora.history[0]) < tol
+
+
+@pytest.mark.parametrize("name", ["q1", "q1_r1", "q2", "3d_q1", "bdf2", "qwise", "stationary_q2"])
+def test_channel_time_steps_match_golden_record(name):
+    """the device time loop (float level operators, config.h:7) against the committed record of the oracle's
+    solver stack, tests/golden/solver_channel.json: iteration counts identical, norms to the float-level tolerance"""
+    from tests.test_solver_oracle import _golden
+    g = _golden()[name]
+    dev = Driver(ChannelParameters(mg_number="float", **g["parameters"]))
+    for ref in g["steps"]:
+        r = dev.step()
+        assert r["newton_iterations"] == ref["newton_iterations"]
+        assert r["linear_iterations"] == ref["linear_iterations"]
+        assert abs(r["dt"] / ref["dt"] - 1) < 1e-3
+        assert np.allclose(r["newton_residuals"][:2], ref["first_residuals"], rtol=1e-3)
+        l2 = float(torch.linalg.vector_norm(dev.solution.get_current_solution()))
+        assert abs(l2 / ref["solution_l2"] - 1) < 1e-3

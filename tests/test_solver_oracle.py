@@ -90,3 +90,25 @@ def test_channel_time_steps_converge():
     # inflow profile is kept, walls stay at rest
     sol = d.history[0]
     assert np.allclose(sol[d.cdofs], d.cvals)
+
+
+def _golden():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "solver_channel.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", ["q1", "qwise", "stationary_q2"])
+def test_solver_stack_matches_golden_record(name):
+    """tests/golden/solver_channel.json pins the oracle's Newton / GMRES iteration counts, time-step sizes and
+    solution norms (a cheap subset here; the GPU suite checks the device path against every case)"""
+    g = _golden()[name]
+    d = _oracle_driver(ChannelParameters(**g["parameters"]))
+    for ref in g["steps"]:
+        r = d.step()
+        assert r["newton_iterations"] == ref["newton_iterations"]
+        assert r["linear_iterations"] == ref["linear_iterations"]
+        assert abs(r["dt"] / ref["dt"] - 1) < 1e-10
+        assert np.allclose(r["newton_residuals"][:2], ref["first_residuals"], rtol=1e-8)
+        assert abs(np.linalg.norm(d.history[0]) / ref["solution_l2"] - 1) < 1e-8
