@@ -1,5 +1,6 @@
 """Wall time per time step of the channel driver (main.cc:908-990 mirror) with everything on the device:
-usage  python profiles/step_probe.py <dim> <degree> <n_global_refinements> [n_steps] [mg_number]"""
+usage  python profiles/step_probe.py <dim> <degree> <n_global_refinements> [n_steps] [mg_number] [graph|eager]
+       [inexact|exact]"""
 import json
 import sys
 import time
@@ -13,8 +14,12 @@ from dealii_ns_gls_b200.driver import ChannelParameters, Driver
 dim, degree, r = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 n_steps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 mg_number = sys.argv[5] if len(sys.argv) > 5 else "float"
+use_graph = len(sys.argv) > 6 and sys.argv[6] == "graph"
+inexact = len(sys.argv) > 7 and sys.argv[7] == "inexact"
 t0 = time.perf_counter()
-d = Driver(ChannelParameters(dim=dim, fe_degree=degree, n_global_refinements=r, mg_number=mg_number))
+from dealii_ns_gls_b200.multigrid import PreconditionerGMGAdditionalData
+d = Driver(ChannelParameters(dim=dim, fe_degree=degree, n_global_refinements=r, mg_number=mg_number,
+                             newton_inexact=inexact, gmg=PreconditionerGMGAdditionalData(use_cuda_graph=use_graph)))
 torch.cuda.synchronize()
 print(f"setup {time.perf_counter() - t0:.1f} s; fine level: {d.meshes[d.maxlevel].n_cells} cells, "
       f"{d.meshes[d.maxlevel].n_dofs} dofs, {d.maxlevel + 1} levels", flush=True)
