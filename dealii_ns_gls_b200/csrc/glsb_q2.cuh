@@ -76,6 +76,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                : "memory");
 }
 
+// per-thread asynchronous copy global -> shared (LDGSTS), 4 or 8 bytes
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *dst, const void *src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst)), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- register value types -------------------------------------------------------------------------------
 // V = T (double or float): one cell per lane.  V = F2 with T = float: TWO cells per lane (the same position
 // of two consecutive 32-cell batches) in one 64-bit register, arithmetic with the packed FP32 instructions of
@@ -304,7 +313,7 @@ __host__ __device__ constexpr bool use_tsm()
 
 template <typename T, typename V, bool GENERAL, bool CTD, bool CELLWISE, int ROWS, int n>
 __global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
-  k_vmult_q2_newton(const KParams<T> p, const Shape<V, n> sh, const int F, const int nst)
+  k_vmult_q2_newton(const KParams<T> p, const Shape<V, n> sh, const int F, const int nst, const int gah)
 {
   constexpr bool TSM = use_tsm<T, n>();
   using VO          = VOps<V, T>;
@@ -316,7 +325,9 @@ __global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T        *tab   = reinterpret_cast<T *>(smem_raw);
   V        *xch   = reinterpret_cast<V *>(tab + nst * VW * stage_elems<T, ROWS, n>(F)); // [warp][2][XSLOT]
-  uint32_t *ibuf  = reinterpret_cast<uint32_t *>(xch + (TPB / 32) * 2 * XSLOT);      // [2][VW][4 n^3 + 1][32] indices, flags
+  // gather-ahead staging (gah): [n^3][TPB] source values of this CTA's NEXT batch, one private column per lane
+  V        *gsm   = xch + (TPB / 32) * 2 * XSLOT + threadIdx.x;
+  uint32_t *ibuf  = reinterpret_cast<uint32_t *>(xch + (TPB / 32) * 2 * XSLOT + (gah ? N3 * TPB : 0)); // [2][VW][4 n^3 + 1][32]
   V        *tsm   = reinterpret_cast<V *>(ibuf) + threadIdx.x;                        // TSM: [n^3][TPB] instead of ibuf
   uint64_t *full  = TSM ? reinterpret_cast<uint64_t *>(reinterpret_cast<V *>(ibuf) + N3 * TPB) :
                           reinterpret_cast<uint64_t *>(ibuf + 2 * ISL);
@@ -376,6 +387,33 @@ __global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
         issue_stage<T, ROWS, VW, n>(p, F, tab, full, j, j);
     }
 
+  // gather-ahead: the source values of batch bi of this CTA go global -> shared with per-thread cp.async
+  // (LDGSTS, no registers held while they are in flight) during the arithmetic of batch bi - 1; every lane
+  // copies and later reads only its own column, so no barrier is involved.  Batches with constrained dofs
+  // (warp-uniform flag) are gathered directly as before.
+  auto gather_ahead = [&](uint32_t bi) -> void {
+    const uint32_t *ib = ibuf + (bi & 1) * ISL;
+    mbar_wait(&ifull[bi & 1], (bi >> 1) & 1);
+    if (__any_sync(0xffffffffu, ib[flo] != 0 || (VW == 2 && ib[IDX_ELEMS + flo] != 0)))
+      return;
+    const uint32_t *ix = ib + ixo;
+#pragma unroll
+    for (int j = 0; j < N3; ++j)
+      {
+        if (VW == 1)
+          cp_async<(int)sizeof(T)>(gsm + j * TPB, p.src + ix[j * CELLS]);
+        else
+          {
+            T *g2 = reinterpret_cast<T *>(gsm + j * TPB);
+            cp_async<(int)sizeof(T)>(g2, p.src + ix[j * CELLS]);
+            cp_async<(int)sizeof(T)>(g2 + 1, p.src + ix[j * CELLS + IDX_ELEMS]);
+          }
+      }
+    cp_async_commit();
+  };
+  if (!TSM && gah)
+    gather_ahead(0);
+
   const V  w = VO::bcast(p.weight), nu = VO::bcast(p.nu);
   uint32_t it = 0, slot = 0, par = 0; // stage counter, its ring slot and phase parity
   for (uint32_t bi = 0; bi < my_n; ++bi)
@@ -396,7 +434,14 @@ __global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
 
       // ---- gather (read_dof_values) ------------------------------------------------------
       V t[N3];
-      if (!slow)
+      if (!slow && !TSM && gah)
+        {
+          cp_async_wait_all();
+#pragma unroll
+          for (int j = 0; j < N3; ++j)
+            t[j] = gsm[j * TPB];
+        }
+      else if (!slow)
         {
 #pragma unroll
           for (int j = 0; j < N3; ++j)
@@ -671,6 +716,10 @@ __global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
 #pragma unroll
             for (int i = 0; i < n; ++i)
               acc[a + N2 * i] += tz[i] * wl[a];
+          // the next batch's index block (requested at the end of the previous batch) has had a layer's time
+          // to arrive: start its gather now, it completes behind the remaining layers
+          if (!TSM && gah && qz == 0 && bi + 1 < my_n)
+            gather_ahead(bi + 1);
         }
 
       // ---- test with the basis in y and x (transposed sweeps) -----------------------------
@@ -755,11 +804,22 @@ __global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
     }
 }
 
+// gather-ahead staging of the source values (GLSB_Q2_GAHEAD=0/1 overrides the default)
+template <typename T, int n>
+inline bool use_gather_ahead()
+{
+  static const int env = getenv("GLSB_Q2_GAHEAD") ? atoi(getenv("GLSB_Q2_GAHEAD")) : -1;
+  if (use_tsm<T, n>())
+    return false;
+  return env >= 0 ? env != 0 : false;
+}
+
 template <typename T, int ROWS, int VW, int n>
 size_t smem_bytes(int F, int nst)
 {
   const size_t idx_or_t = use_tsm<T, n>() ? (size_t)n * n * n * TPB * sizeof(T) : (size_t)2 * VW * idx_elems<n>() * 4;
-  return nst * VW * stage_elems<T, ROWS, n>(F) * sizeof(T) + (size_t)(TPB / 32) * 2 * XSLOT * (VW * sizeof(T)) +
+  const size_t gsm      = use_gather_ahead<T, n>() ? (size_t)n * n * n * TPB * (VW * sizeof(T)) : 0;
+  return nst * VW * stage_elems<T, ROWS, n>(F) * sizeof(T) + (size_t)(TPB / 32) * 2 * XSLOT * (VW * sizeof(T)) + gsm +
          idx_or_t + (MAX_NST + 2) * (sizeof(uint64_t) + sizeof(uint32_t));
 }
 
@@ -799,7 +859,7 @@ static int launch_rows(const KParams<T> &p, const Shape<V, n> &S, int F, cudaStr
   const uint32_t n_units = ((p.cell_end - p.cell_begin + CELLS - 1) / CELLS + VW - 1) / VW;
   const int      use_sm  = (p.sm_reserve > 0 && p.sm_reserve < n_sm) ? n_sm - p.sm_reserve : n_sm;
   const uint32_t grid    = n_units < (uint32_t)(use_sm * bps) ? n_units : (uint32_t)(use_sm * bps);
-  kern<<<grid, TPB, smem, s>>>(p, S, F, nst);
+  kern<<<grid, TPB, smem, s>>>(p, S, F, nst, use_gather_ahead<T, n>() ? 1 : 0);
   return cudaGetLastError() != cudaSuccess;
 }
 
