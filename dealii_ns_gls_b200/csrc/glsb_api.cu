@@ -197,7 +197,7 @@ __global__ void k_pi_normalise(T *__restrict__ e, const T *__restrict__ v1, uint
 __global__ void k_pi_record(double *__restrict__ sums, double *__restrict__ hist, int k)
 {
   if (k >= 0)
-    hist[k] = sums[1];
+    hist[k] = fabs(sums[1]); // deal.II's power_iteration returns std::abs(eigenvalue_estimate)
   sums[0] = sums[1] = sums[2] = 0;
 }
 
@@ -2215,6 +2215,10 @@ int glsb_diagonal_finish(glsb_op *op, void *diag, void *stream)
       if (op->n_constrained)
         k_set_indexed<double><<<(op->n_constrained + 255) / 256, 256, 0, s>>>(
           (double *)diag, op->cidx.as<uint32_t>(), op->n_constrained, 1.0);
+      // refinement-edge dofs of a GMG-LS level: diagonal = 0, which the guard turns into 1 (operator_ns.cc:219-224)
+      if (op->n_edge)
+        k_set_indexed<double><<<(op->n_edge + 255) / 256, 256, 0, s>>>((double *)diag, op->edge_idx.as<uint32_t>(),
+                                                                       op->n_edge, 0.0);
       k_invert_guarded<double><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((double *)diag, n);
     }
   else
@@ -2222,9 +2226,12 @@ int glsb_diagonal_finish(glsb_op *op, void *diag, void *stream)
       if (op->n_constrained)
         k_set_indexed<float><<<(op->n_constrained + 255) / 256, 256, 0, s>>>(
           (float *)diag, op->cidx.as<uint32_t>(), op->n_constrained, 1.0f);
+      if (op->n_edge)
+        k_set_indexed<float><<<(op->n_edge + 255) / 256, 256, 0, s>>>((float *)diag, op->edge_idx.as<uint32_t>(),
+                                                                      op->n_edge, 0.0f);
       k_invert_guarded<float><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((float *)diag, n);
     }
-  op->launches += 1 + (op->n_constrained > 0);
+  op->launches += 1 + (op->n_constrained > 0) + (op->n_edge > 0);
   if (cudaGetLastError() != cudaSuccess)
     return cuda_fail(op, "glsb_diagonal_finish");
   return 0;

@@ -34,6 +34,9 @@ namespace q2
 #ifndef GLSB_Q2_F64_CTAS
 #define GLSB_Q2_F64_CTAS 2
 #endif
+#ifndef GLSB_Q2_GAH
+#define GLSB_Q2_GAH 0 // gather-ahead staging of the next batch's source values (measured: no gain)
+#endif
 #ifndef GLSB_Q2_F32_CTAS
 #define GLSB_Q2_F32_CTAS 3 // resident CTAs per SM the float instantiation is compiled for
 #endif
@@ -313,8 +316,9 @@ __host__ __device__ constexpr bool use_tsm()
 
 template <typename T, typename V, bool GENERAL, bool CTD, bool CELLWISE, int ROWS, int n>
 __global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
-  k_vmult_q2_newton(const KParams<T> p, const Shape<V, n> sh, const int F, const int nst, const int gah)
+  k_vmult_q2_newton(const KParams<T> p, const Shape<V, n> sh, const int F, const int nst, const int gah_rt)
 {
+  const bool gah = GLSB_Q2_GAH && gah_rt;
   constexpr bool TSM = use_tsm<T, n>();
   using VO          = VOps<V, T>;
   constexpr int VW  = VO::VW;
@@ -326,7 +330,7 @@ __global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
   T        *tab   = reinterpret_cast<T *>(smem_raw);
   V        *xch   = reinterpret_cast<V *>(tab + nst * VW * stage_elems<T, ROWS, n>(F)); // [warp][2][XSLOT]
   // gather-ahead staging (gah): [n^3][TPB] source values of this CTA's NEXT batch, one private column per lane
-  V        *gsm   = xch + (TPB / 32) * 2 * XSLOT + threadIdx.x;
+  V        *gsm   = xch + (TPB / 32) * 2 * XSLOT + (GLSB_Q2_GAH ? threadIdx.x : 0);
   uint32_t *ibuf  = reinterpret_cast<uint32_t *>(xch + (TPB / 32) * 2 * XSLOT + (gah ? N3 * TPB : 0)); // [2][VW][4 n^3 + 1][32]
   V        *tsm   = reinterpret_cast<V *>(ibuf) + threadIdx.x;                        // TSM: [n^3][TPB] instead of ibuf
   uint64_t *full  = TSM ? reinterpret_cast<uint64_t *>(reinterpret_cast<V *>(ibuf) + N3 * TPB) :
@@ -809,7 +813,7 @@ template <typename T, int n>
 inline bool use_gather_ahead()
 {
   static const int env = getenv("GLSB_Q2_GAHEAD") ? atoi(getenv("GLSB_Q2_GAHEAD")) : -1;
-  if (use_tsm<T, n>())
+  if (use_tsm<T, n>() || !GLSB_Q2_GAH)
     return false;
   return env >= 0 ? env != 0 : false;
 }

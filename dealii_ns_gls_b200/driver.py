@@ -107,6 +107,9 @@ class Driver:
             raise NotImplementedError(p.time_integration)
         tid = self.time_integrator_data
         self.constraints_inhomogeneous = channel_inhomogeneous_constraints(p, fine)
+        # `constraints` of main.cc:268-306: everything but the rows of the inhomogeneous boundary ids
+        self.constraints = AffineConstraints({d: r for d, r in self.constraints_inhomogeneous.rows.items()
+                                              if d not in self.constraints_inhomogeneous.inhomogeneities})
         increment_form = True  # Newton (main.cc:331)
         # main.cc:333-348
         self.ns_operator = NavierStokesOperator(fine, self.constraints_inhomogeneous, p.nu, p.c_1, p.c_2, tid,
@@ -225,6 +228,7 @@ class Driver:
         n_lin_before = len(self.linear_solver.n_iterations)
         n_newton = self.nonlinear_solver.solve(cur)
         self.constraints_inhomogeneous.distribute(cur)
+        self.constraints.distribute(cur)  # main.cc:963
         self.t += dt
         rec = dict(cycle=self.counter, t=self.t, dt=dt, u_max=u_max, newton_iterations=n_newton,
                    newton_residuals=list(self.nonlinear_solver.residuals),

@@ -424,6 +424,216 @@ def hypercube_slab(n_per_dir, degree, *, n_ranks=1, rank=0, dim=3, order="morton
     return mesh
 
 
+def morton_rank_grid(n_ranks, dim=3):
+    """Boxes per direction when the Morton curve of a uniformly refined hypercube is cut into n_ranks equal
+    contiguous pieces (p4est's partition, performance.cc:29-31): the leading bits of the key belong to
+    z, y, x in turn, so 2 ranks are z-halves, 4 ranks (z, y)-quarters, 8 ranks octants, 16 ranks octants
+    halved in z again, ...  Returns (grid, coords_of_rank) with rank = position along the curve."""
+    k = int(n_ranks).bit_length() - 1
+    assert 1 << k == n_ranks, "power-of-two rank counts only"
+    bits = [0] * dim                              # key bits per direction, assigned from the top: z, y, x, z, ...
+    for b in range(k):
+        bits[dim - 1 - (b % dim)] += 1
+    grid = tuple(1 << b for b in bits)
+    coords = np.zeros((n_ranks, dim), dtype=np.int64)
+    for r in range(n_ranks):
+        used = [0] * dim
+        for b in range(k):                        # b-th bit from the top of the k-bit rank
+            e = dim - 1 - (b % dim)
+            bit = (r >> (k - 1 - b)) & 1
+            used[e] += 1
+            coords[r, e] |= bit << (bits[e] - used[e])
+    return grid, coords
+
+
+def hypercube_box(n_per_dir, degree, *, n_ranks=1, rank=0, dim=3, order="morton", with_points=True,
+                  index_dtype=np.uint32):
+    """Rank `rank`'s box of n^dim cells of a hypercube partitioned the way deal.II / p4est partition it: equal
+    pieces of the Morton curve (morton_rank_grid: halves, quarters, octants), generated in O(local cells).
+
+    Ownership follows deal.II (lowest touching rank): a box owns its nodes except those on a low face behind
+    which another box lies; those are ghosts owned by the box diagonally below through every such face the node
+    lies on, so a box imports from up to 2^dim - 1 neighbours (faces, edges, corner) and exports its high
+    faces to as many.  Ghosts are grouped by owner; both sides order a neighbour's nodes lexicographically,
+    which is all the Partitioner-style send / receive lists need."""
+    p, C = degree, dim + 1
+    shape = (n_per_dir,) * dim
+    grid, box_of = morton_rank_grid(n_ranks, dim)
+    b = box_of[rank]
+    rank_of_box = {tuple(box_of[r]): r for r in range(n_ranks)}
+    cc, loc, cell_nodes, node_rank, first_cell, npts = _number_nodes(dim, shape, p, (False,) * dim, order)
+    nnode, ncell = int(np.prod(npts)), cc.shape[0]
+    node_ids = np.arange(nnode)
+    ijk = np.stack([(node_ids // int(np.prod(npts[:e]))) % npts[e] for e in range(dim)], axis=1)  # x fastest
+    low = (ijk == 0) & (b[None, :] > 0)           # on a low face with a neighbour behind it
+    is_ghost_node = low.any(axis=1)
+    owner_box = b[None, :] - low.astype(np.int64)
+    owner_rank = np.array([rank_of_box[tuple(o)] for o in owner_box[is_ghost_node]], dtype=np.int64) \
+        if is_ghost_node.any() else np.zeros(0, dtype=np.int64)
+    owned_nodes = np.nonzero(~is_ghost_node)[0]
+    owned_sorted = owned_nodes[np.argsort(node_rank[owned_nodes], kind="stable")]   # first-touch order
+    n_owned_nodes = len(owned_sorted)
+    local_of_node = np.empty(nnode, dtype=np.int64)
+    local_of_node[owned_sorted] = np.arange(n_owned_nodes)
+    ghost_nodes = np.nonzero(is_ghost_node)[0]
+    gorder = np.lexsort((ghost_nodes, owner_rank))                                  # by owner, then lexicographic
+    ghost_nodes, owner_rank = ghost_nodes[gorder], owner_rank[gorder]
+    local_of_node[ghost_nodes] = n_owned_nodes + np.arange(len(ghost_nodes))
+    n_owned, n_ghost = n_owned_nodes * C, len(ghost_nodes) * C
+    cell_dofs = np.concatenate([local_of_node[cell_nodes] * C + c for c in range(C)], axis=1)
+
+    def owned_count(bb):
+        return int(np.prod([p * n_per_dir + (1 if bb[e] == 0 else 0) for e in range(dim)])) * C
+
+    first_owned = sum(owned_count(box_of[r]) for r in range(rank))
+    part = RankPartition(rank=rank, n_ranks=n_ranks, n_owned=n_owned, n_ghost=n_ghost, owned_offset=first_owned,
+                         ghost_global=np.zeros(0, dtype=np.int64), ghost_owner=np.repeat(owner_rank, C))
+    for r in np.unique(owner_rank):
+        sel = np.nonzero(owner_rank == r)[0]
+        part.recv.append((int(r), int(sel[0]) * C, int(len(sel)) * C))
+    # exports: neighbour b + delta imports from me the nodes on my high faces in supp(delta) that I own
+    top = np.asarray(npts) - 1
+    for r in range(n_ranks):
+        delta = box_of[r] - b
+        if r == rank or (delta < 0).any() or (delta > 1).any():
+            continue
+        sel = ~is_ghost_node
+        for e in range(dim):
+            sel &= (ijk[:, e] == top[e]) if delta[e] == 1 else np.ones(nnode, dtype=bool)
+            # the neighbour keeps for itself what lies on its own low faces towards OTHER boxes only if it owns
+            # them: nodes of mine with i_e == 0, b_e > 0 are not mine (already excluded by ~is_ghost_node)
+        exp_nodes = node_ids[sel]                                                    # lexicographic
+        exp = (local_of_node[exp_nodes][:, None] * C + np.arange(C)[None, :]).reshape(-1)
+        part.send.append((int(r), exp.astype(np.int64)))
+
+    hcell = 1.0 / n_per_dir
+    gn = [p * n_per_dir * grid[e] + 1 for e in range(dim)]
+    mesh = Mesh(dim=dim, degree=p, n_cells=ncell, n_dofs=n_owned + n_ghost, n_owned=n_owned,
+                cell_dofs=cell_dofs.astype(index_dtype), geometry_type=0, cell_points=None, mapping_degree=1,
+                constraints={}, cell_h_min=np.full(ncell, hcell), cell_measure=np.full(ncell, hcell ** dim),
+                partition=part, node_compact=True, n_global_dofs=int(np.prod(gn)) * C)
+    mesh.cart_inv_jac = np.full((ncell, dim), 1.0 / hcell)
+    mesh.cart_det = np.full(ncell, hcell ** dim)
+    mesh.cell_is_boundary = (cell_dofs >= n_owned).any(axis=1)
+    gijk = ijk + (b * p * n_per_dir)[None, :]
+    gnode = np.zeros(nnode, dtype=np.int64)
+    mul = 1
+    for e in range(dim):
+        gnode += gijk[:, e] * mul
+        mul *= gn[e]
+    canon = np.empty(n_owned + n_ghost, dtype=np.int64)
+    for c in range(C):
+        canon[local_of_node * C + c] = gnode * C + c
+    mesh.canonical_ids = canon
+    mesh.shape, mesh.cell_coords = shape, np.ascontiguousarray(cc)
+    mesh.extent, mesh.origin = np.ones(dim), b.astype(np.float64)
+    if with_points:
+        mloc = np.stack(np.meshgrid(*[np.arange(2)] * dim, indexing="ij"), axis=-1).reshape(-1, dim)[:, ::-1]
+        mesh.cell_points = mesh.origin[None, None, :] + (cc[:, None, :] + mloc[None, :, :].astype(np.float64)) * hcell
+    return mesh
+
+
+def hypercube_hanging(dim, n_coarse, degree, *, refine=None, dirichlet=None, index_dtype=np.uint32):
+    """Unit hypercube of n_coarse^dim cells in which the cells selected by `refine(cell_coords) -> bool mask`
+    (default: the block with all coordinates >= n_coarse / 2) are refined once: a true 2:1 mesh with hanging
+    nodes on faces (and, in 3-D, on edges where the refined block has a re-entrant edge), as
+    DoFTools::make_hanging_node_constraints sees it in the reference (main.cc:293, simulation.cc:803-809,
+    input/rotation.json).
+
+    Active cells are walked along the Morton curve of the fine level (p4est order); every node is numbered by the
+    first active cell touching it, components of a node consecutive.  A node of a refined cell that lies on an
+    unrefined cell K without being one of K's nodes is a hanging node: it is constrained to the value of K's
+    finite element function there, x_h = sum_j phi_j^K(x_h) x_j -- deal.II's FE_Q face/line interpolation
+    constraints (Q1: 1/2, 1/2 and 1/4 x 4; Q2 on a line at 1/4: 3/8, 3/4, -1/8); weights below 1e-14 dropped.
+    Masters are never constrained themselves (one level of difference)."""
+    p, C, n = degree, dim + 1, degree + 1
+    n_loc = n ** dim
+    gp = gauss_lobatto_points(p)
+    cc0 = np.stack(np.meshgrid(*[np.arange(n_coarse)] * dim, indexing="ij"), axis=-1).reshape(-1, dim)
+    ref_mask = (cc0 >= n_coarse // 2).all(axis=1) if refine is None else np.asarray(refine(cc0), dtype=bool)
+    # active cells: (fine-level integer origin, size in fine units)
+    cells = []
+    for k in range(len(cc0)):
+        if ref_mask[k]:
+            for ch in range(2 ** dim):
+                cells.append((2 * cc0[k] + np.array([(ch >> e) & 1 for e in range(dim)]), 1))
+        else:
+            cells.append((2 * cc0[k], 2))
+    org = np.array([c[0] for c in cells], dtype=np.int64)
+    size = np.array([c[1] for c in cells], dtype=np.int64)
+    perm = np.argsort(_morton_key(org), kind="stable")
+    org, size = org[perm], size[perm]
+    ncell = len(org)
+    hf = 1.0 / (2 * n_coarse)
+    loc = np.stack(np.meshgrid(*[np.arange(n)] * dim, indexing="ij"), axis=-1).reshape(-1, dim)[:, ::-1]
+    # local numbering order inside a cell: vertices, lines, quads, hexes (like DoFHandler::distribute_dofs)
+    ent_dim = ((loc > 0) & (loc < p)).sum(axis=1)
+    colorder = np.lexsort((np.arange(n_loc), ent_dim))
+    pts = (org[:, None, :] + size[:, None, None] * gp[loc][None, :, :]) * hf       # [ncell, n_loc, dim]
+    keys = np.round(pts * 2 ** 40).astype(np.int64)
+    node_of = {}
+    cell_nodes = np.zeros((ncell, n_loc), dtype=np.int64)
+    for k in range(ncell):
+        for l in colorder:
+            cell_nodes[k, l] = node_of.setdefault(tuple(keys[k, l]), len(node_of))
+    nnode = len(node_of)
+    node_xyz = np.zeros((nnode, dim))
+    node_xyz[cell_nodes.reshape(-1)] = pts.reshape(-1, dim)
+    cell_dofs = np.concatenate([cell_nodes * C + c for c in range(C)], axis=1)
+
+    # ---- hanging-node constraints ------------------------------------------------------------
+    def lagrange(x):
+        v = np.ones(n)
+        for i in range(n):
+            for j in range(n):
+                if j != i:
+                    v[i] *= (x - gp[j]) / (gp[i] - gp[j])
+        return v
+
+    fine_nodes = np.unique(cell_nodes[size == 1]) if (size == 1).any() else np.zeros(0, dtype=np.int64)
+    node_rows = {}
+    tol = 1e-12
+    for k in np.nonzero(size == 2)[0]:
+        lo, hi = org[k] * hf, (org[k] + 2) * hf
+        inside = fine_nodes[((node_xyz[fine_nodes] >= lo - tol) & (node_xyz[fine_nodes] <= hi + tol)).all(axis=1)]
+        mine = set(cell_nodes[k].tolist())
+        for nd in inside:
+            if int(nd) in mine or int(nd) in node_rows:
+                continue
+            xi = (node_xyz[nd] - lo) / (hi - lo)
+            w1 = [lagrange(xi[e]) for e in range(dim)]
+            row = []
+            for l in range(n_loc):
+                w = float(np.prod([w1[e][loc[l, e]] for e in range(dim)]))
+                if abs(w) > 1e-14:
+                    row.append((int(cell_nodes[k, l]), w))
+            node_rows[int(nd)] = row
+    constraints = {}
+    for nd, row in node_rows.items():
+        for c in range(C):
+            constraints[nd * C + c] = [(m * C + c, w) for m, w in row]
+
+    hcell = size.astype(np.float64) * hf
+    mloc = np.stack(np.meshgrid(*[np.arange(2)] * dim, indexing="ij"), axis=-1).reshape(-1, dim)[:, ::-1]
+    cpts = (org[:, None, :] + size[:, None, None] * mloc[None, :, :]) * hf
+    mesh = Mesh(dim=dim, degree=p, n_cells=ncell, n_dofs=nnode * C, n_owned=nnode * C,
+                cell_dofs=cell_dofs.astype(index_dtype), geometry_type=0, cell_points=cpts, mapping_degree=1,
+                constraints=constraints, cell_h_min=hcell.copy(), cell_measure=hcell ** dim, node_compact=True,
+                n_global_dofs=nnode * C)
+    mesh.cart_inv_jac = np.repeat((1.0 / hcell)[:, None], dim, axis=1)
+    mesh.cart_det = hcell ** dim
+    mesh.cell_is_boundary = np.zeros(ncell, dtype=bool)
+    mesh.node_xyz = node_xyz
+    mesh.hanging_nodes = np.array(sorted(node_rows.keys()), dtype=np.int64)
+    if dirichlet is not None:
+        for c in range(C):
+            for nd in np.nonzero(dirichlet(node_xyz, c))[0]:
+                if int(nd) not in node_rows:
+                    constraints[int(nd) * C + c] = []
+        # a hanging node whose masters are all zero-constrained stays a (consistent) weighted row
+    return mesh
+
+
 def cylinder_shell(shape, degree, *, r_inner=0.05, r_outer=0.5, length=0.41,
                    mapping_degree=None, no_slip=True, **kw):
     """O-grid around a cylinder (r, theta periodic[, z]) -- curved cells, like the

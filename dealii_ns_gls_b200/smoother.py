@@ -84,7 +84,7 @@ class PreconditionRelaxation:
             lam, nrm2 = ex.allreduce_sum([float(torch.dot(e[:no].double(), v[:no].double())),
                                           float(torch.dot(v[:no].double(), v[:no].double()))])
             e[:no] = v[:no] / nrm2 ** 0.5
-        ev_max = 1.2 * lam
+        ev_max = 1.2 * abs(lam)  # deal.II's power_iteration returns std::abs(eigenvalue_estimate)
         alpha = ev_max / self.smoothing_range if self.smoothing_range > 1.0 else 0.9 * ev_max
         self._eigenvalues = EigenvalueInformation(ev_max / self.smoothing_range, ev_max, self.eig_cg_n_iterations)
         if self.relaxation == 0.0:

@@ -710,9 +710,9 @@ class OracleOperator:
             A[:, j] = self.vmult(e, weight)
         return A
 
-    def compute_inverse_diagonal(self, weight):
-        """operator_ns.cc:195-225: diag(C^T A C), 1 on constrained rows, then
-        x -> |x| > 1e-10 ? 1/x : 1."""
+    def compute_inverse_diagonal(self, weight, edge_constrained_indices=None):
+        """operator_ns.cc:195-225: diag(C^T A C), 1 on constrained rows, 0 on the refinement-edge dofs of a
+        GMG-LS level (:219-220), then x -> |x| > 1e-10 ? 1/x : 1."""
         A = self.cell_matrices(weight)
         nl = self.C * self.n_loc
         diag = np.zeros(self.n_dofs, dtype=self.dtype)
@@ -727,5 +727,8 @@ class OracleOperator:
                 Cc = Ck[:, cols]
                 diag[cols] += np.einsum("ig,ij,jg->g", Cc, A[k], Cc)
             diag[self.constrained] = 1
+        if edge_constrained_indices is not None and len(edge_constrained_indices):
+            diag[np.asarray(edge_constrained_indices, dtype=np.int64)] = 0
         T = self.dtype.type
-        return np.where(np.abs(diag) > T(1e-10), T(1.0) / diag, T(1.0)).astype(self.dtype)
+        with np.errstate(divide="ignore"):
+            return np.where(np.abs(diag) > T(1e-10), T(1.0) / diag, T(1.0)).astype(self.dtype)

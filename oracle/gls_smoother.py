@@ -39,7 +39,7 @@ class OracleRelaxation:
             v = (self.d * self.A(e)).astype(self.dtype)
             lam = float(np.dot(e.astype(np.float64), v.astype(np.float64)))
             e = (v / np.linalg.norm(v.astype(np.float64))).astype(self.dtype)
-        self.max_eigenvalue_estimate = 1.2 * lam
+        self.max_eigenvalue_estimate = 1.2 * abs(lam)
         alpha = self.max_eigenvalue_estimate / self.smoothing_range if self.smoothing_range > 1 \
             else 0.9 * self.max_eigenvalue_estimate
         if self.relaxation == 0.0:

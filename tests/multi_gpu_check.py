@@ -3,7 +3,7 @@
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
       --master-port 29511 tests/multi_gpu_check.py
 
-Every rank builds its slab of a small hypercube, applies the CUDA operator with the NCCL ghost
+Every rank builds its part (Morton box by default, GLSB_CHECK_PARTITION=slab for z-slabs) of a small hypercube, applies the CUDA operator with the NCCL ghost
 exchange (interior cells overlapped with the import, compress(add) afterwards) and the result is
 compared with the CPU oracle evaluated on the union of the slabs."""
 import os
@@ -22,6 +22,13 @@ from dealii_ns_gls_b200.operator import NavierStokesOperator  # noqa: E402
 from tests.util import TI, make_oracle  # noqa: E402
 
 
+def make_part(*a, **kw):
+    """GLSB_CHECK_PARTITION = box (default: Morton halves / quarters / octants, the reference's p4est owner
+    ranks, up to 7 neighbours) or slab (z-slabs, the round-1 partition)"""
+    fn = gm.hypercube_slab if os.environ.get("GLSB_CHECK_PARTITION", "box") == "slab" else gm.hypercube_box
+    return fn(*a, **kw)
+
+
 def field(ids, seed):
     x = (ids.astype(np.float64) * 0.6180339887498949 + seed * 0.137) % 1.0
     return 2.0 * x - 1.0
@@ -33,7 +40,7 @@ def main():
     dev = torch.device("cuda", lr)
     dist.init_process_group("nccl", device_id=dev)
     n, degree, w = 7, 2, 10.0
-    m = gm.hypercube_slab(n, degree, n_ranks=world, rank=rank)
+    m = make_part(n, degree, n_ranks=world, rank=rank)
     ex = GhostExchange(m.partition, dev)
     ti = TI(2, [w, -w, 0.0], 0.1)
     op = NavierStokesOperator(m, None, 0.1, 4.0, 2.0, ti, False, True, True, number="double", device=dev, exchange=ex)
@@ -49,7 +56,7 @@ def main():
     umax = op.get_max_u(src)
     torch.cuda.synchronize()
     # reference on the union of the slabs (every rank computes it; sizes are tiny)
-    meshes = [gm.hypercube_slab(n, degree, n_ranks=world, rank=r) for r in range(world)]
+    meshes = [make_part(n, degree, n_ranks=world, rank=r) for r in range(world)]
     ng = meshes[0].n_global_dofs
     acc, dacc, um = np.zeros(ng), np.zeros(ng), 0.0
     for mm in meshes:
@@ -69,6 +76,7 @@ def main():
     ok = e1 < 1e-12 and e2 < 1e-11 and e3 < 1e-12 and op.vmult_variant() == "q2_regtile_tma"
     print(f"rank {rank}/{world}: vmult rel_l2 {e1:.2e}  inv_diag rel_l2 {e2:.2e}  max_u err {e3:.1e}  "
           f"interior/boundary cells {m.n_cells - int(m.cell_is_boundary.sum())}/{int(m.cell_is_boundary.sum())} "
+          f"neighbours recv {[r for r, _, _ in m.partition.recv]} send {[r for r, _ in m.partition.send]} "
           f"variant {op.vmult_variant()}  {'OK' if ok else 'FAIL'}", flush=True)
     # relaxation smoother on the partitioned operator: omega from the distributed power iteration and 5 sweeps,
     # against the CPU restatement on the union of the slabs in the SAME global numbering (owner offset + local)
@@ -111,7 +119,7 @@ def main():
     # _finish) against the device-vector vmult, on a mesh large enough for several chunks and with Dirichlet rows
     n2 = int(os.environ.get("GLSB_CHECK_CELLS", "48"))
     eps = 1e-12
-    m2 = gm.hypercube_slab(n2, degree, n_ranks=world, rank=rank, with_points=False)
+    m2 = make_part(n2, degree, n_ranks=world, rank=rank, with_points=False)
     ex2 = GhostExchange(m2.partition, dev)
     op2 = NavierStokesOperator(m2, None, 0.1, 4.0, 2.0, ti, False, True, True, number="double", device=dev, exchange=ex2)
     g = torch.Generator(device=dev).manual_seed(7 + rank)

@@ -12,12 +12,12 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _slab_reference(n, degree, R, lin_fn, src_fn, weight):
+def _slab_reference(n, degree, R, lin_fn, src_fn, weight, kind="slab"):
     from dealii_ns_gls_b200 import mesh as gm
     from tests.util import TI, make_oracle
     full = gm.hypercube_slab(n, degree, n_ranks=1, rank=0)
     # one rank holding the whole R-slab domain: stack the slabs by canonical ids
-    meshes = [gm.hypercube_slab(n, degree, n_ranks=R, rank=r) for r in range(R)]
+    meshes = [_make(gm, kind, n, degree, R, r) for r in range(R)]
     ng = meshes[0].n_global_dofs
     ti = TI(2, [weight, -weight, 0.0], 0.1)
     acc = np.zeros(ng)
@@ -36,7 +36,11 @@ def _field(ids, seed):
     return 2.0 * x - 1.0
 
 
-def _worker(rank, world, port, n, degree, out):
+def _make(gm, kind, n, degree, world, rank):
+    return (gm.hypercube_box if kind == "box" else gm.hypercube_slab)(n, degree, n_ranks=world, rank=rank)
+
+
+def _worker(rank, world, port, n, degree, out, kind="slab"):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -44,7 +48,7 @@ def _worker(rank, world, port, n, degree, out):
     from dealii_ns_gls_b200 import mesh as gm
     from dealii_ns_gls_b200.distributed import GhostExchange
     from tests.util import TI, make_oracle
-    m = gm.hypercube_slab(n, degree, n_ranks=world, rank=rank)
+    m = _make(gm, kind, n, degree, world, rank)
     ex = GhostExchange(m.partition, "cpu")
     ti = TI(2, [10.0, -10.0, 0.0], 0.1)
     o = make_oracle(m, ti)
@@ -94,3 +98,51 @@ def test_slab_partition_lists_are_consistent():
         # the sender's export order equals the receiver's ghost order (same canonical ids)
         assert np.array_equal(ms[r].canonical_ids[exp], ms[r + 1].canonical_ids[ms[r + 1].n_owned:])
     assert not ms[0].partition.recv and not ms[-1].partition.send
+
+
+@pytest.mark.parametrize("R", [2, 4, 8])
+def test_morton_box_partition_lists_are_consistent(R):
+    """p4est-style partition (halves / quarters / octants of the Morton curve, performance.cc:29-31): every
+    dof owned once by the lowest touching rank, contiguous owned ranges, and the sender's export order equal
+    to the receiver's ghost order for every pair, including edge- and corner-neighbours."""
+    from dealii_ns_gls_b200 import mesh as gm
+    n, p = 2, 2
+    ms = [gm.hypercube_box(n, p, n_ranks=R, rank=r) for r in range(R)]
+    ng = ms[0].n_global_dofs
+    assert sum(m.n_owned for m in ms) == ng
+    owner = np.full(ng, -1)
+    off = 0
+    for r, m in enumerate(ms):
+        assert m.partition.owned_offset == off
+        off += m.n_owned
+        assert (owner[m.canonical_ids[:m.n_owned]] == -1).all()
+        owner[m.canonical_ids[:m.n_owned]] = r
+    assert (owner >= 0).all()
+    for r, m in enumerate(ms):
+        # lowest touching rank owns
+        touch = m.canonical_ids
+        assert (owner[touch] <= r).all()
+        assert (m.partition.ghost_owner == owner[m.canonical_ids[m.n_owned:]]).all()
+        for frm, o, cnt in m.partition.recv:
+            (exp,) = [idx for to, idx in ms[frm].partition.send if to == r]
+            assert cnt == len(exp)
+            assert np.array_equal(ms[frm].canonical_ids[exp], m.canonical_ids[m.n_owned + o:m.n_owned + o + cnt])
+        assert sum(c for _, _, c in m.partition.recv) == m.n_dofs - m.n_owned
+    if R == 8:
+        assert len(ms[7].partition.recv) == 7 and len(ms[0].partition.send) == 7  # faces, edges and the corner
+
+
+def test_four_rank_quarters_ghost_exchange_matches_single_domain(tmp_path):
+    """(z, y)-quarters: ranks with 1 and 3 neighbours, edge-shared dofs contributed to by all four ranks."""
+    n, world, degree = 2, 4, 2
+    port = 31500 + (os.getpid() % 2000)
+    out = str(tmp_path / "res")
+    mp.spawn(_worker, args=(world, port, n, degree, out, "box"), nprocs=world, join=True)
+    ref = _slab_reference(n, degree, world, lambda ids: _field(ids, 1), lambda ids: _field(ids, 2), 10.0, kind="box")
+    seen = np.zeros(len(ref), dtype=bool)
+    for r in range(world):
+        d = torch.load(out + f".{r}", weights_only=False)
+        assert d["ghost_zero"] and d["mx"] == float(world)
+        assert np.linalg.norm(d["dst"] - ref[d["ids"]]) <= 1e-13 * np.linalg.norm(ref)
+        seen[d["ids"]] = True
+    assert seen.all()

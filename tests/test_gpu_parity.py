@@ -23,6 +23,10 @@ def _to_dev(a, number):
     return torch.tensor(np.asarray(a), dtype=torch.float64 if number == "double" else torch.float32, device="cuda")
 
 
+def torch_idx(a):
+    return _torch().tensor(np.asarray(a, dtype=np.int64), device="cuda")
+
+
 def _mesh(kind, dim, degree, **kw):
     if kind == "cube":
         return gm.hypercube(dim, 4 if dim == 2 else 3, degree, **kw)
@@ -301,6 +305,11 @@ def test_gmg_ls_edge_indices_and_interface_operators(dim, degree, kind, number):
     assert rel_l2(dst.cpu().numpy(), ora.vmult_interface_down(src, 15.0), mesh=mesh) < TOL[number]
     gpu.vmult_interface_up(dst, x)
     assert rel_l2(dst.cpu().numpy(), ora.vmult_interface_up(src, 15.0, edge), mesh=mesh) < TOL[number]
+    # inverse diagonal: exactly 1 on the refinement-edge dofs (operator_ns.cc:219-224)
+    gpu.compute_inverse_diagonal(dst)
+    ref_d = ora.compute_inverse_diagonal(15.0, edge)
+    assert bool((dst[torch_idx(edge)] == 1).all()) and np.all(ref_d[edge] == 1)
+    assert rel_l2(dst.cpu().numpy(), ref_d, mesh=mesh) < (1e-11 if number == "double" else 5e-5)
     # no edge indices anywhere: interface_up is the zero operator
     mesh.edge_constrained_indices = np.zeros(0, dtype=np.int64)
     mesh.has_edge_constrained_indices = False
