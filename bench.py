@@ -107,36 +107,60 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------
 # CPU arm: the C restatement of the reference algorithm on the host cores
 # --------------------------------------------------------------------------------------
-def cpu_vmult_gdofs(cells_per_dir, degree, steps, warmup, budget_s=25.0):
-    """Time oracle/gls_oracle_c on a bounded sample of the workload (same flags, smaller cube)."""
+def cpu_sample(cells_per_dir, degree, workload="P"):
+    """The bounded sample of the workload the CPU restatement runs on: mesh, C oracle with its tables, and the
+    seeded vectors (history, linearization point, src).  Same flags as the GPU workload, smaller mesh."""
     from dealii_ns_gls_b200 import mesh as gm
     from oracle import gls_oracle as go
-    from oracle.gls_oracle_c import COracle, max_threads
+    from oracle.gls_oracle_c import COracle
 
-    mesh = gm.hypercube(3, cells_per_dir, degree)
-    K = mesh.n_cells
     rng = np.random.default_rng(SEED)
+    if workload == "C":
+        c = cells_per_dir
+        mesh = gm.cylinder_shell((max(2, c // 2), 4 * c, max(2, c // 2)), degree)
+        weights, nu, ctd, cell_wise = [15.0, -20.0, 5.0], 0.001, True, False
+    else:
+        mesh = gm.hypercube(3, cells_per_dir, degree)
+        weights, nu, ctd, cell_wise = [10.0, -10.0, 0.0], NU, False, True
     ora = go.OracleOperator(dim=3, degree=degree, cell_dofs=mesh.cell_dofs, n_dofs=mesh.n_dofs,
-                            cell_points=mesh.cell_points, mapping_degree=1, constraints={}, nu=NU, c1=C1,
-                            c2=C2, theta=1.0, order=2, consider_time_derivative=False, increment_form=True,
-                            cell_wise_stabilization=True, path="sumfac")
-    ora.set_linearization_point(rng.uniform(-1, 1, mesh.n_dofs), DT)
-    basis = ora.tb.b
-    co = COracle(dim=3, degree=degree, cell_dofs=mesh.cell_dofs, n_dofs=mesh.n_dofs, S=basis.S, D=basis.D,
-                 w=basis.wq, cartesian=True, inv_jac=mesh.cart_inv_jac, jxw=mesh.cart_det, nu=NU, theta=1.0,
-                 branch=COracle.BR_NEWTON, ctd=False, cell_wise=True)
-    co.set_tables(ora.U, ora.H.reshape(K, 9, -1), ora.P, None, None, None,
-                  ora.delta1_cell.reshape(K, 1), ora.delta2_cell.reshape(K, 1))
+                            cell_points=mesh.cell_points, mapping_degree=mesh.mapping_degree,
+                            constraints=mesh.constraints, nu=nu, c1=C1, c2=C2, theta=1.0, order=2,
+                            consider_time_derivative=ctd, increment_form=True,
+                            cell_wise_stabilization=cell_wise, path="sumfac")
+    hist = [rng.uniform(-1, 1, mesh.n_dofs) for _ in range(3)] if workload == "C" else None
+    if hist is not None:
+        ora.set_previous_solution(hist, weights)
+    lin = rng.uniform(-1, 1, mesh.n_dofs)
+    ora.set_linearization_point(lin, DT)
+    if workload == "C":
+        co = COracle.from_numpy_oracle(ora, COracle.BR_NEWTON)
+    else:
+        K, basis = mesh.n_cells, ora.tb.b
+        co = COracle(dim=3, degree=degree, cell_dofs=mesh.cell_dofs, n_dofs=mesh.n_dofs, S=basis.S, D=basis.D,
+                     w=basis.wq, cartesian=True, inv_jac=mesh.cart_inv_jac, jxw=mesh.cart_det, nu=NU, theta=1.0,
+                     branch=COracle.BR_NEWTON, ctd=False, cell_wise=True)
+        co.set_tables(ora.U, ora.H.reshape(K, 9, -1), ora.P, None, None, None,
+                      ora.delta1_cell.reshape(K, 1), ora.delta2_cell.reshape(K, 1))
     del ora
     src = rng.uniform(-1, 1, mesh.n_dofs)
+    return dict(mesh=mesh, co=co, hist=hist, lin=lin, src=src, weight=weights[0], nu=nu, ctd=ctd,
+                cell_wise=cell_wise, weights=weights)
+
+
+def cpu_vmult_gdofs(cells_per_dir, degree, steps, warmup, budget_s=25.0, sample=None):
+    """Time oracle/gls_oracle_c on a bounded sample of the workload (same flags, smaller cube)."""
+    from oracle.gls_oracle_c import max_threads
+
+    sm = cpu_sample(cells_per_dir, degree) if sample is None else sample
+    mesh, co, src = sm["mesh"], sm["co"], sm["src"]
     dst = np.empty_like(src)
     nt = max_threads()
     for _ in range(max(1, warmup)):
-        co.apply_into(dst, src, 10.0, nt)
+        co.apply_into(dst, src, sm["weight"], nt)
     t0 = time.perf_counter()
     done = 0
     for _ in range(steps):
-        co.apply_into(dst, src, 10.0, nt)
+        co.apply_into(dst, src, sm["weight"], nt)
         done += 1
         if time.perf_counter() - t0 > budget_s:
             break
@@ -144,6 +168,45 @@ def cpu_vmult_gdofs(cells_per_dir, degree, steps, warmup, budget_s=25.0):
     return dict(value=mesh.n_dofs * done / dt / 1e9, steps=done, seconds=dt, cores=nt, n_dofs=mesh.n_dofs,
                 sample=f"{cells_per_dir}^3 cells Q{degree} hypercube ({mesh.n_dofs} DoFs), {done} vmults, "
                        f"{nt} OpenMP threads, same flags as the GPU workload")
+
+
+def gpu_parity_on_sample(sm, number, dev):
+    """The CUDA path (through the C ABI) against the C restatement on the CPU sample: same mesh, same seeded
+    vectors.  The cell loop of the oracle is plain gather/scatter; constrained rows (config C: no-slip) are
+    resolved around it the way vmult does (operator_ns.cc:684-732).  Returns the relative l2 error over the
+    unconstrained rows and whether the identity rows are bit-equal."""
+    import torch
+
+    from dealii_ns_gls_b200.operator import NavierStokesOperator
+    from tests.util import TI
+    from oracle.gls_oracle_c import max_threads
+    mesh = sm["mesh"]
+    tdt = torch.float64 if number == "double" else torch.float32
+    ti = TI(2, sm["weights"], DT)
+    op = NavierStokesOperator(mesh, None, sm["nu"], C1, C2, ti, sm["ctd"], True, sm["cell_wise"], number=number,
+                              device=dev)
+    to_dev = lambda a: torch.tensor(a, dtype=tdt, device=dev)  # noqa: E731
+    if sm["hist"] is not None:
+        op.set_previous_solution([to_dev(h) for h in sm["hist"]])
+    op.set_linearization_point(to_dev(sm["lin"]))
+    dst = op.initialize_dof_vector()
+    op.vmult(dst, to_dev(sm["src"]))
+    got = dst.double().cpu().numpy()
+    variant = op.vmult_variant()
+    del op, dst
+    cons = np.fromiter(mesh.constraints.keys(), dtype=np.int64, count=len(mesh.constraints))
+    x = sm["src"].copy()
+    x[cons] = 0.0  # zero-type rows read 0 (read_dof_values)
+    ref = sm["co"].apply(x, sm["weight"], max_threads())
+    free = np.ones(mesh.n_dofs, dtype=bool)
+    free[cons] = False
+    err = float(np.linalg.norm((got - ref)[free]) / np.linalg.norm(ref[free]))
+    ident = bool(np.array_equal(got[cons], sm["src"].astype(np.float64 if number == "double" else np.float32)[cons]))
+    tol = 1e-12 if number == "double" else 2e-5
+    return {"rel_l2_unconstrained_rows": err, "identity_rows_bit_equal": ident, "tol": tol,
+            "ok": bool(err < tol and ident), "n_dofs": int(mesh.n_dofs), "n_cells": int(mesh.n_cells),
+            "n_constrained": int(len(cons)), "number": number, "kernel_variant": variant,
+            "checker": "oracle/gls_oracle_c.c (CPU restatement; parity unpinned against deal.II)"}
 
 
 def run_reference(args):
@@ -156,7 +219,9 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
         "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
+        "config": dict(workload_config(args, args.gpus),
+                       cpu_sample=f"each step = one vmult on a {args.cpu_cells}^3-cell sample ({r['n_dofs']} DoFs) "
+                                  "of this workload; GDoF/s is size-independent once the tables (1.1 GB) are out of cache"),
         "cpu_baseline": {"value": r["value"], "unit": "GDoF/s", "cores": r["cores"], "kind": "port",
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -180,7 +245,11 @@ def workload_config(args, n_gpus):
                         "Cartesian, no constraints, Newton form, cell-wise delta, BDF2 weight 10, "
                         "random U/src seed 1234" + ("" if args.number == "double" else ", Number = float"),
             "cells_per_gpu": args.cells ** 3, "degree": args.degree, "dim": 3,
-            "parallelism": f"domain decomposition, {n_gpus} z-slab(s)",
+            "parallelism": "single GPU" if n_gpus == 1 else
+            (f"domain decomposition, {n_gpus} z-slabs" if getattr(args, "partition", "morton") == "slab" else
+             f"domain decomposition by owner rank along the Morton curve (p4est): {n_gpus} boxes of "
+             f"{args.cells}^3 cells = " + {2: "z-halves", 4: "(z,y)-quarters", 8: "octants"}.get(n_gpus, "boxes") +
+             ", up to 7 neighbours per rank"),
             "l2_policy": "inputs larger than L2 (tables + vectors >> 126 MB), no flush"}
 
 
@@ -227,7 +296,8 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         from dealii_ns_gls_b200.distributed import GhostExchange
-        mesh = gm.hypercube_slab(args.cells, args.degree, n_ranks=world, rank=rank)
+        part = gm.hypercube_slab if args.partition == "slab" else gm.hypercube_box
+        mesh = part(args.cells, args.degree, n_ranks=world, rank=rank, with_points=False)
         exchange = GhostExchange(mesh.partition, dev)
     elif args.workload == "C":
         mesh = gm.cylinder_shell(shell_shape(args), args.degree)
@@ -362,13 +432,49 @@ def run_gpu(args):
                      "algorithmic_bytes_per_cell": bpc, "cells_per_launch": n_cells},
         "clocks": sampler.summary(),
     }
-    if world == 1 and not args.no_cpu_baseline and args.workload == "P":
-        r = cpu_vmult_gdofs(args.cpu_cells, args.degree, 10, 2)
-        line["cpu_baseline"] = {"value": r["value"], "unit": "GDoF/s", "cores": r["cores"], "kind": "port",
-                                "sample": r["sample"]}
-    if world == 1 and args.workload == "P" and args.time_step_refinements >= 0:
+    if traffic is not None:
+        line["roofline"]["traffic_source"] = "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of " \
+                                             "one ncu --set full capture of this kernel at this size, not measured in this run"
+    headline = world == 1 and args.workload == "P" and args.number == "double"
+    if headline and not args.no_extras:
+        # the reference's own protocol next to the random-vector one: zero vectors (performance.cc:66-79)
+        try:
+            zero = torch.zeros(n_local, dtype=tdt, device=dev)
+            op.set_linearization_point(zero)
+            zr = side_measure(op, zero, dst, min(args.steps, 10), n_cells, n_global, bpc, peaks.get("hbm_gbs"))
+            zr["note"] = "performance.cc:66-79 as written: linearization point, history and src all zero"
+            zr["dst_abs_max"] = float(dst.abs().max())
+            line["zero_vector_protocol"] = zr
+            del zero
+        except Exception as e:
+            line["zero_vector_protocol"] = {"error": f"{type(e).__name__}: {e}"}
+    if world == 1:
         del op, src, dst, h_src, h_dst
         torch.cuda.empty_cache()
+    if headline and not args.no_cpu_baseline:
+        sm = cpu_sample(args.cpu_cells, args.degree)
+        r = cpu_vmult_gdofs(args.cpu_cells, args.degree, 10, 2, sample=sm)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "GDoF/s", "cores": r["cores"], "kind": "port",
+                                "sample": r["sample"]}
+        if not args.no_extras:
+            # parity of the CUDA path against the C restatement on that same sample, and on a config-C sample
+            try:
+                line["parity"] = dict(gpu_parity_on_sample(sm, "double", dev), sample=f"{args.cpu_cells}^3-cell hypercube")
+                del sm
+                smc = cpu_sample(max(8, args.cpu_cells // 2), args.degree, workload="C")
+                line["parity_config_C"] = dict(gpu_parity_on_sample(smc, "double", dev),
+                                               sample="O-grid shell, Turek-3D flags, no-slip rows")
+                del smc
+            except Exception as e:
+                line["parity"] = {"error": f"{type(e).__name__}: {e}"}
+    if headline and not args.no_extras:
+        # config C (curved cells, q-point-wise delta, BDF2 terms) at the bench size, same protocol
+        try:
+            line["workload_C"] = config_c_measure(args, dev, peaks.get("hbm_gbs"))
+        except Exception as e:
+            line["workload_C"] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+    if world == 1 and args.workload == "P" and args.time_step_refinements >= 0:
         try:
             line["time_step"] = time_step_wall(args.time_step_refinements, dev)
         except Exception as e:  # the vmult line above stays valid on its own
@@ -376,6 +482,54 @@ def run_gpu(args):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def side_measure(op, src, dst, steps, n_cells, n_global, bpc, peak):
+    """3 warm-ups + `steps` timed vmults with CUDA events (whole step and cell kernel)"""
+    import torch
+    for _ in range(3):
+        op.vmult(dst, src)
+    torch.cuda.synchronize()
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        op.vmult(dst, src, kernel_events=k_ev[i])
+    e1.record()
+    torch.cuda.synchronize()
+    t_ms = e0.elapsed_time(e1)
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    achieved = n_cells * bpc / (k_ms * 1e-3) / 1e9
+    return {"value": n_global * steps / (t_ms * 1e-3) / 1e9, "unit": "GDoF/s", "steps": steps, "ms_per_step": t_ms / steps,
+            "kernel_ms": k_ms, "roofline_achieved_gbs": achieved, "roofline_frac": achieved / peak,
+            "algorithmic_bytes_per_cell": bpc, "kernel_variant": op.vmult_variant()}
+
+
+def config_c_measure(args, dev, peak):
+    """bench.py --workload C as an extra key of the default line"""
+    import torch
+
+    from dealii_ns_gls_b200 import mesh as gm
+    from dealii_ns_gls_b200.operator import NavierStokesOperator
+    from dealii_ns_gls_b200.time_integration import TimeIntegratorDataBDF
+    mesh = gm.cylinder_shell(shell_shape(args), args.degree)
+    ti = TimeIntegratorDataBDF(2)
+    ti.update_dt(DT)
+    ti.update_dt(DT)
+    op = NavierStokesOperator(mesh, None, 0.001, C1, C2, ti, True, True, False, number="double", device=dev)
+    n, n_cells = mesh.n_dofs, mesh.n_cells
+    del mesh
+    g = torch.Generator(device=dev).manual_seed(SEED)
+    rv = lambda: torch.rand(n, dtype=torch.float64, device=dev, generator=g) * 2 - 1  # noqa: E731
+    op.set_previous_solution([rv() for _ in range(3)])
+    op.set_linearization_point(rv())
+    src, dst = rv(), op.initialize_dof_vector()
+    bpc = algorithmic_bytes_per_cell(3, args.degree, 8, ctd=True, q_wise=True, general=True)
+    r = side_measure(op, src, dst, min(args.steps, 10), n_cells, n, bpc, peak)
+    cargs = argparse.Namespace(**dict(vars(args), workload="C"))
+    r["workload"] = workload_config(cargs, 1)["workload"]
+    r["n_dofs"] = n
+    return r
 
 
 def time_step_wall(refinements, dev, n_steps=4):
@@ -444,6 +598,9 @@ def main():
                     help="P = performance.cc hypercube (the headline); C = curved O-grid with the Turek-3D flags")
     ap.add_argument("--number", default="double", choices=["double", "float"],
                     help="double = Krylov operator (headline); float = multigrid level operator (config.h:7)")
+    ap.add_argument("--partition", default="morton", choices=["morton", "slab"],
+                    help="N > 1: morton = the reference's p4est owner ranks (halves / quarters / octants); slab = z-slabs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra keys (config C, zero vectors, parity)")
     ap.add_argument("--time-step-refinements", type=int, default=4,
                     help="n global refinements of the 3-D Q2 channel whose wall time per time step is reported "
                          "next to the vmult metric (3 -> 4.3e6 DoFs, 4 -> 3.4e7); -1 = skip")

@@ -630,7 +630,12 @@ def hypercube_hanging(dim, n_coarse, degree, *, refine=None, dirichlet=None, ind
             for nd in np.nonzero(dirichlet(node_xyz, c))[0]:
                 if int(nd) not in node_rows:
                     constraints[int(nd) * C + c] = []
-        # a hanging node whose masters are all zero-constrained stays a (consistent) weighted row
+        # AffineConstraints::close() resolves chains: a master that is itself constrained to zero drops out of
+        # the hanging-node row (a hanging node on the wall ends up as a zero row)
+        for dof in list(constraints.keys()):
+            row = constraints[dof]
+            if row:
+                constraints[dof] = [(m, w) for m, w in row if not (m in constraints and not constraints[m])]
     return mesh
 
 

@@ -365,3 +365,18 @@ def test_q2_packed_float_kernel(kind, ctd, cell_wise, monkeypatch):
         gpu.vmult(dst, _to_dev(src, "float"))
         assert gpu.vmult_variant() == "q2_regtile_tma"
         assert rel_l2(dst.cpu().numpy(), ora.vmult(src, 15.0), mesh=mesh) < TOL["float"]
+
+
+@pytest.mark.parametrize("number", ["double", "float"])
+@pytest.mark.parametrize("workload,cells", [("P", 64), ("C", 32)])
+def test_bench_sample_against_c_oracle(workload, cells, number):
+    """The CUDA path against the C restatement at the size bench.py's CPU arm runs (64^3 cells = 8.6e6 DoFs for
+    config P: 8 192 batches, i.e. ~28 batches per persistent CTA with ring refills and index-block wraparound;
+    a 32 768-cell O-grid with no-slip rows for config C) -- the `parity` object of the bench line."""
+    import bench
+    torch = _torch()
+    sm = bench.cpu_sample(cells, 2, workload=workload)
+    r = bench.gpu_parity_on_sample(sm, number, torch.device("cuda", 0))
+    assert r["kernel_variant"] == "q2_regtile_tma"
+    assert r["identity_rows_bit_equal"]
+    assert r["rel_l2_unconstrained_rows"] < TOL[number], r
