@@ -4,10 +4,13 @@
 // multigrid, time_integration and main.cc stay unchanged; main.cc:333-348 / :513-529 / :683-702 and
 // performance.cc:48-62 only swap the class name.
 //
-// NOT COMPILED IN THIS REPOSITORY: deal.II (>= 9.6, with p4est and Trilinos), MPI and the reference's
-// own headers are not available to this build.  The file is kept header-only and
-// is written against the public deal.II API; every accessor used is listed in INTEGRATION.md so a
-// maintainer with a deal.II tree can check it in one pass.  What it does is mechanical: flatten
+// deal.II (>= 9.6, with p4est and Trilinos), MPI and the reference's own headers are not available to this
+// build, so the class cannot be RUN here.  It is compiled, instantiated for
+// <2|3, double|float> and linked against libglsb200.so + NCCL by tests/cpp/test_adapter_compiles.cpp on top of
+// tests/cpp/dealii_stub/ (the used deal.II / reference signatures only), which checks syntax, every
+// `override` against OperatorBase<Number>, and the C-ABI calls.  The file is header-only and written
+// against the public deal.II API; every accessor used is listed in INTEGRATION.md so a maintainer with
+// a deal.II tree can check it in one pass.  What it does is mechanical: flatten
 // MatrixFree / DoFHandler / AffineConstraints / Partitioner into the arrays of glsb_desc
 //  once, then forward each virtual to the matching C-ABI call.
 #pragma once
@@ -269,11 +272,39 @@ public:
     d.inv_jac = inv_jac.data(), d.jxw = jxw.data(), d.cell_h_min = h_min.data(), d.cell_measure = measure.data();
     d.n_export = export_indices.size(), d.export_indices = export_indices.data();
     AssertThrow(glsb_create(&d, &op) == 0, ExcMessage(glsb_last_error(nullptr)));
+    n_owned = d.n_owned, n_ghost = d.n_ghost;
     n_local = d.n_owned + d.n_ghost;
     has_edge_constrained_indices = has_edge;
+
+    // ---- streams, exchange buffers, NCCL communicator -----------------------------------------------------
+    partitioner = matrix_free.get_vector_partitioner();
+    cuda_check(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    cuda_check(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+    cuda_check(cudaEventCreateWithFlags(&ev_compute, cudaEventDisableTiming));
+    cuda_check(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
+    n_export = export_indices.size();
+    if (n_export > 0)
+      {
+        cuda_check(cudaMalloc(&d_export, n_export * sizeof(Number)));
+        cuda_check(cudaMalloc(&d_import, n_export * sizeof(Number)));
+      }
+    if (partitioner->n_mpi_processes() > 1)
+      nccl = shared_communicator(partitioner->get_mpi_communicator());
   }
 
-  ~NavierStokesOperatorB200() override { glsb_destroy(op); }
+  ~NavierStokesOperatorB200() override
+  {
+    glsb_destroy(op);
+    for (auto &m : mirrors)
+      {
+        cudaFree(m.second.d);
+        if (m.second.registered)
+          glsb_host_unregister(const_cast<Number *>(m.first));
+      }
+    cudaFree(d_export), cudaFree(d_import);
+    cudaEventDestroy(ev_compute), cudaEventDestroy(ev_comm);
+    cudaStreamDestroy(stream), cudaStreamDestroy(comm_stream);
+  }
 
   // ---- OperatorBase<Number> -------------------------------------------------------------------
   types::global_dof_index m() const override { return cpu_operator.m(); }
@@ -292,6 +323,12 @@ public:
   {
     MyScope scope(timer, "ns::vmult"); // same section names as the reference (operator_ns.cc:689)
     const double w = time_integrator_data.get_primary_weight();
+    if (!device_vectors && !has_edge_constrained_indices)
+      {
+        // host VectorType (config.h:9-10): upload, cells and download pipelined inside the library
+        vmult_host_vectors(dst, src, w);
+        return;
+      }
     check(glsb_edge_begin(op, const_cast<void *>(dev(src)), stream)); // operator_ns.cc:692-700
     check(glsb_vmult_begin(op, dev(dst), stream));
     update_ghost_values_start(src); // NCCL send/recv of the export block into the ghost block
@@ -346,6 +383,7 @@ public:
     update_ghost_values_start(vec);
     update_ghost_values_finish();
     check(glsb_set_linearization_point(op, dev(vec), time_integrator_data.get_current_dt(), stream));
+    end_operation();
   }
 
   void set_previous_solution(const SolutionHistory<Number> &history) override
@@ -365,6 +403,7 @@ public:
         ptr.push_back(dev(history.get_vectors()[i]));
       }
     check(glsb_set_previous_solution(op, ptr.data(), time_integrator_data.get_weights().data(), order, stream));
+    end_operation();
   }
 
   void evaluate_residual(VectorType<Number> &dst, const VectorType<Number> &src) const override
@@ -403,27 +442,195 @@ public:
     update_ghost_values_start(vec);
     update_ghost_values_finish();
     double v = 0;
-    check(glsb_get_max_u(op, dev(vec), &v, stream));
+    check(glsb_get_max_u(op, dev(vec), &v, stream)); // synchronises `stream`
+    end_operation();
     return Utilities::MPI::max(v, MPI_COMM_WORLD); // operator_ns.cc:567
   }
 
 private:
   void check(const int rc) const { AssertThrow(rc == 0, ExcMessage(glsb_last_error(op))); }
 
-  // Device pointer of a vector.  MemorySpace::Default vectors: get_values() is already device memory.
-  // Host vectors: copy into a cached device mirror (and back in finish()).
-  void       *dev(VectorType<Number> &v) const;
-  const void *dev(const VectorType<Number> &v) const;
-  void        finish(VectorType<Number> &v) const;
+  static void cuda_check(const cudaError_t e) { AssertThrow(e == cudaSuccess, ExcMessage(cudaGetErrorString(e))); }
+  static void nccl_check(const ncclResult_t r) { AssertThrow(r == ncclSuccess, ExcMessage(ncclGetErrorString(r))); }
 
-  // ghost exchange over NCCL: ncclGroupStart; ncclSend(export buffer slice -> import_targets);
-  // ncclRecv(ghost block slice <- ghost_targets); ncclGroupEnd on comm_stream, packed / unpacked by
-  // glsb_pack_export / glsb_unpack_add.  Rank = GPU mapping and the communicator come from the
-  // driver (one MPI rank per GPU, ncclCommInitRank with an id broadcast over MPI).
-  void update_ghost_values_start(const VectorType<Number> &v) const;
-  void update_ghost_values_finish() const;
-  void compress_start(VectorType<Number> &v) const;
-  void compress_finish(VectorType<Number> &v) const;
+  // ---- vector residency ---------------------------------------------------------------------------------
+  // MemorySpace::Default vectors (Kokkos-CUDA deal.II, alias flipped in config.h:9-10): get_values() is
+  // device memory and is passed through.  Host vectors (the reference's default alias): every host array gets
+  // a device mirror of n_owned + n_ghost values, page-locked once (glsb_host_register); dev(const) uploads the
+  // owned block at its first use inside an operation, finish() downloads the owned block of the result.
+  static constexpr bool device_vectors =
+    std::is_same<typename VectorType<Number>::memory_space, MemorySpace::Default>::value;
+
+  struct Mirror
+  {
+    Number       *d          = nullptr;
+    unsigned long uploaded   = 0; // epoch of the last upload
+    bool          registered = false;
+  };
+
+  Mirror &mirror_of(const Number *host) const
+  {
+    auto it = mirrors.find(host);
+    if (it == mirrors.end())
+      {
+        Mirror m;
+        cuda_check(cudaMalloc(&m.d, n_local * sizeof(Number)));
+        cuda_check(cudaMemsetAsync(m.d, 0, n_local * sizeof(Number), stream));
+        m.registered = glsb_host_register(const_cast<Number *>(host), n_owned * sizeof(Number)) == 0;
+        it           = mirrors.emplace(host, m).first;
+      }
+    return it->second;
+  }
+
+  const void *dev(const VectorType<Number> &v) const
+  {
+    if (device_vectors)
+      return v.get_values();
+    Mirror &m = mirror_of(v.get_values());
+    if (m.uploaded != epoch)
+      {
+        cuda_check(cudaMemcpyAsync(m.d, v.get_values(), n_owned * sizeof(Number), cudaMemcpyHostToDevice, stream));
+        m.uploaded = epoch;
+      }
+    return m.d;
+  }
+
+  // results: no upload, the kernels overwrite the owned block
+  void *dev(VectorType<Number> &v) const
+  {
+    if (device_vectors)
+      return v.get_values();
+    Mirror &m  = mirror_of(v.get_values());
+    m.uploaded = epoch;
+    return m.d;
+  }
+
+  // the operation is over: make the result visible to the (host-side) caller
+  void finish(VectorType<Number> &v) const
+  {
+    if (!device_vectors)
+      cuda_check(cudaMemcpyAsync(v.get_values(), mirror_of(v.get_values()).d, n_owned * sizeof(Number),
+                                 cudaMemcpyDeviceToHost, stream));
+    end_operation();
+  }
+
+  void end_operation() const
+  {
+    cuda_check(cudaStreamSynchronize(stream));
+    ++epoch; // host vectors may change before the next call: upload again
+  }
+
+  // host vectors, no edge indices: the pipelined entry points
+  void vmult_host_vectors(VectorType<Number> &dst, const VectorType<Number> &src, const double w) const
+  {
+    if (nccl == nullptr && n_ghost == 0)
+      check(glsb_vmult_host(op, dst.get_values(), src.get_values(), w, stream));
+    else
+      {
+        Mirror &ms = mirror_of(src.get_values()), &md = mirror_of(dst.get_values());
+        check(glsb_vmult_host_begin(op, md.d, ms.d, dst.get_values(), src.get_values(), w, stream));
+        ms.uploaded = md.uploaded = epoch; // _begin uploaded src and zeroed dst
+        update_ghost_values_start(src);
+        update_ghost_values_finish();
+        check(glsb_vmult_cells(op, md.d, ms.d, w, GLSB_CELLS_BOUNDARY, stream));
+        compress_start(dst);
+        compress_finish(dst);
+        check(glsb_vmult_host_finish(op, md.d, dst.get_values(), stream));
+      }
+    end_operation();
+  }
+
+  // ---- ghost exchange over NCCL ---------------------------------------------------------------------------
+  // update_ghost_values: pack the owned entries other ranks read (Partitioner::import_indices, grouped by
+  // import_targets) and send them; receive the ghost block slice by slice from ghost_targets.
+  // compress(add): the same lists the other way round, added by glsb_unpack_add.  One MPI rank per GPU; the
+  // communicator is created once per process from an id broadcast over MPI.
+  static ncclComm_t shared_communicator(const MPI_Comm comm)
+  {
+    static ncclComm_t shared = nullptr;
+    if (shared == nullptr)
+      {
+        int rank = 0, size = 1;
+        MPI_Comm_rank(comm, &rank);
+        MPI_Comm_size(comm, &size);
+        ncclUniqueId id;
+        if (rank == 0)
+          nccl_check(ncclGetUniqueId(&id));
+        MPI_Bcast(&id, sizeof(id), MPI_BYTE, 0, comm);
+        nccl_check(ncclCommInitRank(&shared, size, id, rank));
+      }
+    return shared;
+  }
+
+  static constexpr ncclDataType_t nccl_type = std::is_same<Number, double>::value ? ncclFloat64 : ncclFloat32;
+
+  void update_ghost_values_start(const VectorType<Number> &v) const
+  {
+    if (nccl == nullptr)
+      return;
+    Number *vec = static_cast<Number *>(const_cast<void *>(dev(v)));
+    cuda_check(cudaEventRecord(ev_compute, stream));
+    cuda_check(cudaStreamWaitEvent(comm_stream, ev_compute, 0));
+    if (n_export > 0)
+      check(glsb_pack_export(op, d_export, vec, comm_stream));
+    nccl_check(ncclGroupStart());
+    std::size_t off = 0;
+    for (const auto &t : partitioner->import_targets()) // (rank, number of owned entries it reads)
+      {
+        nccl_check(ncclSend(d_export + off, t.second, nccl_type, t.first, nccl, comm_stream));
+        off += t.second;
+      }
+    off = n_owned;
+    for (const auto &t : partitioner->ghost_targets()) // (owner rank, number of ghosts it owns), ghost block order
+      {
+        nccl_check(ncclRecv(vec + off, t.second, nccl_type, t.first, nccl, comm_stream));
+        off += t.second;
+      }
+    nccl_check(ncclGroupEnd());
+    cuda_check(cudaEventRecord(ev_comm, comm_stream));
+  }
+
+  void update_ghost_values_finish() const
+  {
+    if (nccl != nullptr)
+      cuda_check(cudaStreamWaitEvent(stream, ev_comm, 0));
+  }
+
+  void compress_start(VectorType<Number> &v) const
+  {
+    if (nccl == nullptr)
+      return;
+    Number *vec = static_cast<Number *>(dev(v));
+    cuda_check(cudaEventRecord(ev_compute, stream));
+    cuda_check(cudaStreamWaitEvent(comm_stream, ev_compute, 0));
+    nccl_check(ncclGroupStart());
+    std::size_t off = n_owned;
+    for (const auto &t : partitioner->ghost_targets())
+      {
+        nccl_check(ncclSend(vec + off, t.second, nccl_type, t.first, nccl, comm_stream));
+        off += t.second;
+      }
+    off = 0;
+    for (const auto &t : partitioner->import_targets())
+      {
+        nccl_check(ncclRecv(d_import + off, t.second, nccl_type, t.first, nccl, comm_stream));
+        off += t.second;
+      }
+    nccl_check(ncclGroupEnd());
+    cuda_check(cudaEventRecord(ev_comm, comm_stream));
+  }
+
+  void compress_finish(VectorType<Number> &v) const
+  {
+    if (nccl == nullptr)
+      return;
+    Number *vec = static_cast<Number *>(dev(v));
+    cuda_check(cudaStreamWaitEvent(stream, ev_comm, 0));
+    if (n_export > 0)
+      check(glsb_unpack_add(op, vec, d_import, stream));
+    if (n_ghost > 0) // compress() leaves the ghost block zeroed
+      cuda_check(cudaMemsetAsync(vec + n_owned, 0, n_ghost * sizeof(Number), stream));
+  }
 
   const AffineConstraints<Number>  &constraints_inhomogeneous;
   const TimeIntegratorData         &time_integrator_data;
@@ -431,9 +638,14 @@ private:
   MatrixFree<dim, Number>           matrix_free;
   glsb_op                          *op      = nullptr;
   bool                              has_edge_constrained_indices = false;
-  std::uint64_t                     n_local = 0;
+  std::uint64_t                     n_local = 0, n_owned = 0, n_ghost = 0, n_export = 0;
   cudaStream_t                      stream = nullptr, comm_stream = nullptr;
+  cudaEvent_t                       ev_compute = nullptr, ev_comm = nullptr;
   ncclComm_t                        nccl   = nullptr;
+  Number                           *d_export = nullptr, *d_import = nullptr; // packed owned entries out / in
+  std::shared_ptr<const Utilities::MPI::Partitioner> partitioner;
+  mutable std::map<const Number *, Mirror>           mirrors; // host vectors: device mirrors by host array
+  mutable unsigned long                              epoch = 1;
   mutable MyTimerOutput             timer;
 };
 
