@@ -239,7 +239,10 @@ def workload_config(args, n_gpus):
                             f"{nr}x{nt}x{nz} curved cells, Q{args.degree} mapping (general geometry), no-slip rows, "
                             "Newton form, q-point-wise delta, BDF2 with time-derivative terms, random U/src/history "
                             f"seed 1234, Number = {args.number}",
-                "cells_per_gpu": nr * nt * nz, "degree": args.degree, "dim": 3, "parallelism": "single GPU",
+                "cells_per_gpu": nr * nt * nz, "degree": args.degree, "dim": 3,
+                "parallelism": "single GPU" if n_gpus == 1 else
+                f"domain decomposition, {n_gpus} boxes of {nr}x{nt}x{nz} cells (axial, then radial cuts; the periodic "
+                "circumferential direction is not split)",
                 "l2_policy": "inputs larger than L2 (tables + vectors >> 126 MB), no flush"}
     return {"workload": f"performance.cc: 3D hypercube, Q{args.degree}, {args.cells}^3 cells per GPU, "
                         "Cartesian, no constraints, Newton form, cell-wise delta, BDF2 weight 10, "
@@ -296,8 +299,11 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         from dealii_ns_gls_b200.distributed import GhostExchange
-        part = gm.hypercube_slab if args.partition == "slab" else gm.hypercube_box
-        mesh = part(args.cells, args.degree, n_ranks=world, rank=rank, with_points=False)
+        if args.workload == "C":
+            mesh = gm.cylinder_shell_box(shell_shape(args), args.degree, n_ranks=world, rank=rank)
+        else:
+            part = gm.hypercube_slab if args.partition == "slab" else gm.hypercube_box
+            mesh = part(args.cells, args.degree, n_ranks=world, rank=rank, with_points=False)
         exchange = GhostExchange(mesh.partition, dev)
     elif args.workload == "C":
         mesh = gm.cylinder_shell(shell_shape(args), args.degree)

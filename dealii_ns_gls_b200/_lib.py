@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libglsb200.so")
+# GLSB_LIB: an alternative build of the same library (kernel experiments under profiles/), default the in-tree one
+LIB_PATH = os.environ.get("GLSB_LIB") or os.path.join(_HERE, "libglsb200.so")
 
 GLSB_ABI_VERSION = 3
 GLSB_F64, GLSB_F32 = 0, 1

@@ -228,15 +228,15 @@ __global__ void k_edge_restore(T *__restrict__ dst, T *__restrict__ src, const T
 __global__ void k_last_touch(const uint32_t *__restrict__ idx, const uint8_t *__restrict__ chunk_of_batch,
                              const uint32_t *__restrict__ row_dof, const uint32_t *__restrict__ row_ptr,
                              const uint32_t *__restrict__ ecol, uint32_t *__restrict__ last, uint32_t n_slots,
-                             uint32_t hole_begin, uint32_t hole_end, uint32_t ndof)
+                             uint32_t ndof)
 {
+  // n_slots = whole 32-slot batches.  A row of a batch is rotated by 8 * component, so the entries of a real cell
+  // can sit in the columns of the batch's padding slots: every column of every batch is visited (padding slots
+  // repeat a real cell of the same batch, i.e. of the same chunk, and mark nothing new)
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (uint64_t)ndof * n_slots)
     return;
   const uint32_t i = t % n_slots, j = t / n_slots;
-  if (i >= hole_begin && i < hole_end)
-    return;
-  // the rotation inside a 32-cell row does not matter here: every entry of the row belongs to the batch
   const uint32_t iv = idx[((uint64_t)(i >> 5) * (ndof + 1) + j) * 32 + (i & 31)];
   const uint32_t c  = chunk_of_batch[i >> 5];
   if (iv & GLSB_CONSTRAINED_BIT)
@@ -1627,11 +1627,11 @@ static int host_pipe_setup(glsb_op *op)
       return 1;
     cudaMemset(last.p, 0, n_local * 4);
     const uint32_t ndof = (uint32_t)(op->C * op->n_loc);
-    const uint64_t tot  = (uint64_t)ndof * op->n_slots;
+    const uint32_t slots_all = (op->n_slots + 31) / 32 * 32; // whole batches, see k_last_touch
+    const uint64_t tot       = (uint64_t)ndof * slots_all;
     k_last_touch<<<(unsigned)((tot + 255) / 256), 256>>>(op->idx.as<uint32_t>(), cob.as<uint8_t>(),
                                                          op->row_dof.as<uint32_t>(), op->row_ptr.as<uint32_t>(),
-                                                         op->ecol.as<uint32_t>(), last.as<uint32_t>(), op->n_slots,
-                                                         op->n_interior, op->n_int_pad, ndof);
+                                                         op->ecol.as<uint32_t>(), last.as<uint32_t>(), slots_all, ndof);
     k_late_flags<<<(unsigned)((n_local + 255) / 256), 256>>>(last.as<uint32_t>(), d_in_end.as<uint64_t>(), nch,
                                                              hp.late_flag.as<uint8_t>(), n_local);
     if (cudaDeviceSynchronize() != cudaSuccess)
@@ -1820,11 +1820,11 @@ static int host_pipe_setup_part(glsb_op *op)
       return 1;
     cudaMemset(last.p, 0, n_local * 4);
     const uint32_t ndof = (uint32_t)(op->C * op->n_loc);
-    const uint64_t tot  = (uint64_t)ndof * op->n_slots;
+    const uint32_t slots_all = (op->n_slots + 31) / 32 * 32; // whole batches, see k_last_touch
+    const uint64_t tot       = (uint64_t)ndof * slots_all;
     k_last_touch<<<(unsigned)((tot + 255) / 256), 256>>>(op->idx.as<uint32_t>(), cob.as<uint8_t>(),
                                                          op->row_dof.as<uint32_t>(), op->row_ptr.as<uint32_t>(),
-                                                         op->ecol.as<uint32_t>(), last.as<uint32_t>(), op->n_slots,
-                                                         op->n_interior, op->n_int_pad, ndof);
+                                                         op->ecol.as<uint32_t>(), last.as<uint32_t>(), slots_all, ndof);
     if (op->n_export) // compress(add) changes the exported entries last
       k_mark_last<<<(unsigned)((op->n_export + 255) / 256), 256>>>(op->export_idx.as<uint32_t>(), op->n_export, nch + 1,
                                                                    last.as<uint32_t>());

@@ -42,10 +42,98 @@ class ChannelParameters:
         self.mg_number = "float"      # config.h:7
         self.n_stretching = 4         # simulation.cc:143-145
         self.gmg = PreconditionerGMGAdditionalData()
+        self.simulation_name = "channel"
+        self._more_defaults()
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise TypeError(f"unknown parameter {k}")
             setattr(self, k, v)
+
+    def _more_defaults(self):
+        pass
+
+    # ---- what Driver needs from a simulation (SimulationBase of include/simulation.h) ----
+    def n_levels(self):
+        return 2 + self.n_global_refinements  # refine_global(2) + n (simulation.cc:166-169)
+
+    def level_mesh(self, level):
+        return channel_level_mesh(self, level)
+
+    def inhomogeneous_constraints(self, mesh):
+        return channel_inhomogeneous_constraints(self, mesh)
+
+    def minimal_cell_diameter(self, fine):
+        return math.sqrt(self.dim) / 2 ** self.n_levels()  # GridTools::minimal_cell_diameter of a cube
+
+
+class CylinderParameters(ChannelParameters):
+    """input/input_turek_2D_Re20_stat.json, input_turek_3D_Re100.json and input_hoffmann_3D_Re3900.json on the
+    synthetic O-grid (mesh.cylinder_shell's map): Q2, q-point-wise delta, nu = 0.001, BDF2 or "none", inexact
+    Newton, direct coarse solver; no-slip rows on the cylinder, u = (u_max, 0, 0) on the upstream half of the outer
+    boundary (inhomogeneous, simulation.cc:379-431), p = 0 on the downstream half ("homogeneous nbc",
+    main.cc:279-283), and on the two z-planes either no-slip or slip walls (w = 0: what
+    compute_no_normal_flux_constraints gives on axis-aligned walls, main.cc:285-287)."""
+
+    def _more_defaults(self):
+        self.simulation_name = "cylinder"
+        self.dim, self.fe_degree, self.n_global_refinements = 2, 2, 1
+        self.cfl, self.bdf_order, self.time_integration = 1.0, 2, "bdf"
+        self.c_1, self.c_2, self.nu = 2.0, 1.0, 0.001
+        self.consider_time_derivative, self.cell_wise_stabilization = True, False
+        self.u_max = 0.3
+        self.no_slip_wall = False            # z-planes: False = slip walls (Hoffmann), True = no-slip (Turek)
+        self.base_shape = (1, 4, 1)          # coarse level: radial x circumferential (x axial) cells
+        self.r_inner, self.r_outer, self.length = 0.05, 0.5, 0.41
+
+    def n_levels(self):
+        return self.n_global_refinements
+
+    def _deform(self, x):
+        r = self.r_inner + (self.r_outer - self.r_inner) * x[..., 0] ** 1.5
+        th = 2.0 * np.pi * x[..., 1]
+        out = np.empty_like(x)
+        out[..., 0], out[..., 1] = r * np.cos(th), r * np.sin(th)
+        if self.dim == 3:
+            out[..., 2] = self.length * x[..., 2]
+        return out
+
+    def _masks(self, ref):
+        eps = 1e-12
+        inner, outer = np.abs(ref[:, 0]) < eps, np.abs(ref[:, 0] - 1.0) < eps
+        upstream = np.cos(2.0 * np.pi * ref[:, 1]) < -1e-9
+        wall = np.zeros(len(ref), dtype=bool)
+        if self.dim == 3:
+            wall = (np.abs(ref[:, 2]) < eps) | (np.abs(ref[:, 2] - 1.0) < eps)
+        return inner, outer & upstream, outer & ~upstream, wall
+
+    def _zero_constrained(self, ref, c):
+        inner, inflow, outflow, wall = self._masks(ref)
+        if c == self.dim:
+            return outflow                              # homogeneous nbc: pressure row
+        m = inner | inflow
+        if self.dim == 3:
+            m |= wall if (self.no_slip_wall or c == 2) else np.zeros(len(ref), dtype=bool)
+        return m
+
+    def level_mesh(self, level):
+        shape = tuple(s * 2 ** level for s in self.base_shape[:self.dim])
+        periodic = (False, True) + ((False,) if self.dim == 3 else ())
+        return structured_mesh(self.dim, shape, self.fe_degree, deform=self._deform, mapping_degree=self.fe_degree,
+                               periodic=periodic, dirichlet=self._zero_constrained)
+
+    def inhomogeneous_constraints(self, mesh):
+        ref, comp = dof_coordinates(mesh), dof_components(mesh)
+        inner, inflow, _, wall = self._masks(ref)
+        rows, inhom = {}, {}
+        for d in mesh.constraints:
+            rows[d] = []
+            if comp[d] == 0 and inflow[d] and not inner[d] and not (self.no_slip_wall and wall[d]):
+                inhom[d] = self.u_max
+        return AffineConstraints(rows, inhom)
+
+    def minimal_cell_diameter(self, fine):
+        from .mesh import cell_diameters
+        return float(cell_diameters(fine).min())
 
 
 def channel_level_mesh(params: ChannelParameters, level: int) -> Mesh:
@@ -88,15 +176,16 @@ def channel_inhomogeneous_constraints(params: ChannelParameters, mesh: Mesh) -> 
 
 
 class Driver:
-    """Driver<dim>::run for the channel with "preconditioner": "GMG", "nonlinear solver": "Newton"."""
+    """Driver<dim>::run with "preconditioner": "GMG", "nonlinear solver": "Newton" for the simulations the
+    parameter object describes (ChannelParameters, CylinderParameters)."""
 
     def __init__(self, params: ChannelParameters, device=None, verbose=False):
         self.params, self.verbose = params, verbose
         self.timers = None
         p = params
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        n_levels = 2 + p.n_global_refinements  # refine_global(2) + n (simulation.cc:166-169)
-        self.meshes = {l: channel_level_mesh(p, l) for l in range(n_levels + 1)}
+        n_levels = p.n_levels()
+        self.meshes = {l: p.level_mesh(l) for l in range(n_levels + 1)}
         self.minlevel, self.maxlevel = 0, n_levels
         fine = self.meshes[self.maxlevel]
         if p.time_integration == "bdf":
@@ -106,7 +195,7 @@ class Driver:
         else:
             raise NotImplementedError(p.time_integration)
         tid = self.time_integrator_data
-        self.constraints_inhomogeneous = channel_inhomogeneous_constraints(p, fine)
+        self.constraints_inhomogeneous = p.inhomogeneous_constraints(fine)
         # `constraints` of main.cc:268-306: everything but the rows of the inhomogeneous boundary ids
         self.constraints = AffineConstraints({d: r for d, r in self.constraints_inhomogeneous.rows.items()
                                               if d not in self.constraints_inhomogeneous.inhomogeneities})
@@ -143,8 +232,7 @@ class Driver:
         self.solution.solutions = [self.ns_operator.initialize_dof_vector() for _ in range(tid.get_order() + 1)]
         self.constraints_inhomogeneous.distribute(self.solution.get_current_solution())
         self.t, self.counter = 0.0, 1
-        h = 1.0 / 2 ** self.maxlevel
-        self.min_dx = h * math.sqrt(p.dim)  # GridTools::minimal_cell_diameter of a cube
+        self.min_dx = p.minimal_cell_diameter(fine)
         self.log = []
 
     # ---- main.cc:772-869 ------------------------------------------------------------------------------

@@ -325,6 +325,19 @@ def dof_coordinates(mesh: Mesh) -> np.ndarray:
     return out
 
 
+def cell_diameters(mesh: Mesh) -> np.ndarray:
+    """cell->diameter(): the largest distance between two vertices (GridTools::minimal_cell_diameter takes the
+    minimum over the cells; the CFL time step of main.cc:916-918 uses it)."""
+    k, dim = mesh.mapping_degree, mesh.dim
+    vid = [sum((k * ((v >> e) & 1)) * (k + 1) ** e for e in range(dim)) for v in range(2 ** dim)]
+    verts = mesh.cell_points[:, vid, :]
+    d = np.zeros(mesh.n_cells)
+    for a in range(len(vid)):
+        for b in range(a + 1, len(vid)):
+            d = np.maximum(d, np.sqrt(((verts[:, a] - verts[:, b]) ** 2).sum(axis=1)))
+    return d
+
+
 def dof_components(mesh: Mesh) -> np.ndarray:
     """[n_dofs] component (0..dim) of every local dof."""
     out = np.zeros(mesh.n_dofs, dtype=np.int64)
@@ -446,22 +459,28 @@ def morton_rank_grid(n_ranks, dim=3):
     return grid, coords
 
 
-def hypercube_box(n_per_dir, degree, *, n_ranks=1, rank=0, dim=3, order="morton", with_points=True,
-                  index_dtype=np.uint32):
-    """Rank `rank`'s box of n^dim cells of a hypercube partitioned the way deal.II / p4est partition it: equal
-    pieces of the Morton curve (morton_rank_grid: halves, quarters, octants), generated in O(local cells).
+def structured_box(shape, degree, *, grid, box_of, rank, periodic=None, deform=None, mapping_degree=1,
+                   dirichlet=None, box_extent=None, order="morton", with_points=True, index_dtype=np.uint32):
+    """Rank `rank`'s box of prod(shape) cells out of a grid of equal boxes (box_of[r] = box coordinates of rank r,
+    monotone: a box with smaller coordinates has the smaller rank), generated in O(local cells).
 
     Ownership follows deal.II (lowest touching rank): a box owns its nodes except those on a low face behind
     which another box lies; those are ghosts owned by the box diagonally below through every such face the node
     lies on, so a box imports from up to 2^dim - 1 neighbours (faces, edges, corner) and exports its high
     faces to as many.  Ghosts are grouped by owner; both sides order a neighbour's nodes lexicographically,
-    which is all the Partitioner-style send / receive lists need."""
-    p, C = degree, dim + 1
-    shape = (n_per_dir,) * dim
-    grid, box_of = morton_rank_grid(n_ranks, dim)
+    which is all the Partitioner-style send / receive lists need.  Directions with periodic node identification
+    (O-grid) must not be split.  deform / dirichlet act on the reference coordinates of the WHOLE block."""
+    dim = len(shape)
+    p, C, n = degree, dim + 1, degree + 1
+    shape = tuple(int(x) for x in shape)
+    grid = tuple(int(g) for g in grid)
+    box_of = np.asarray(box_of, dtype=np.int64)
+    n_ranks = len(box_of)
+    periodic = tuple(periodic) if periodic is not None else (False,) * dim
+    assert all(not (periodic[e] and grid[e] > 1) for e in range(dim)), "periodic directions are not split"
     b = box_of[rank]
     rank_of_box = {tuple(box_of[r]): r for r in range(n_ranks)}
-    cc, loc, cell_nodes, node_rank, first_cell, npts = _number_nodes(dim, shape, p, (False,) * dim, order)
+    cc, loc, cell_nodes, node_rank, first_cell, npts = _number_nodes(dim, shape, p, periodic, order)
     nnode, ncell = int(np.prod(npts)), cc.shape[0]
     node_ids = np.arange(nnode)
     ijk = np.stack([(node_ids // int(np.prod(npts[:e]))) % npts[e] for e in range(dim)], axis=1)  # x fastest
@@ -483,7 +502,7 @@ def hypercube_box(n_per_dir, degree, *, n_ranks=1, rank=0, dim=3, order="morton"
     cell_dofs = np.concatenate([local_of_node[cell_nodes] * C + c for c in range(C)], axis=1)
 
     def owned_count(bb):
-        return int(np.prod([p * n_per_dir + (1 if bb[e] == 0 else 0) for e in range(dim)])) * C
+        return int(np.prod([p * shape[e] + (1 if (bb[e] == 0 and not periodic[e]) else 0) for e in range(dim)])) * C
 
     first_owned = sum(owned_count(box_of[r]) for r in range(rank))
     part = RankPartition(rank=rank, n_ranks=n_ranks, n_owned=n_owned, n_ghost=n_ghost, owned_offset=first_owned,
@@ -499,38 +518,96 @@ def hypercube_box(n_per_dir, degree, *, n_ranks=1, rank=0, dim=3, order="morton"
             continue
         sel = ~is_ghost_node
         for e in range(dim):
-            sel &= (ijk[:, e] == top[e]) if delta[e] == 1 else np.ones(nnode, dtype=bool)
-            # the neighbour keeps for itself what lies on its own low faces towards OTHER boxes only if it owns
-            # them: nodes of mine with i_e == 0, b_e > 0 are not mine (already excluded by ~is_ghost_node)
+            if delta[e] == 1:
+                sel &= ijk[:, e] == top[e]
         exp_nodes = node_ids[sel]                                                    # lexicographic
         exp = (local_of_node[exp_nodes][:, None] * C + np.arange(C)[None, :]).reshape(-1)
         part.send.append((int(r), exp.astype(np.int64)))
 
-    hcell = 1.0 / n_per_dir
-    gn = [p * n_per_dir * grid[e] + 1 for e in range(dim)]
+    box_extent = np.ones(dim) if box_extent is None else np.asarray(box_extent, dtype=np.float64)
+    hcell = box_extent / np.asarray(shape, dtype=np.float64)
+    origin = b.astype(np.float64) * box_extent
+    gn = [p * shape[e] * grid[e] + (0 if periodic[e] else 1) for e in range(dim)]
+    k = mapping_degree if deform is not None else 1
+    pts = None
+    if with_points or deform is not None:
+        mp = gauss_lobatto_points(k)
+        mloc = np.stack(np.meshgrid(*[np.arange(k + 1)] * dim, indexing="ij"), axis=-1).reshape(-1, dim)[:, ::-1]
+        ref = origin[None, None, :] + (cc[:, None, :] + mp[mloc][None, :, :]) * hcell[None, None, :]
+        pts = deform(ref) if deform is not None else ref
+    if deform is None:
+        h_min, meas = np.full(ncell, float(hcell.min())), np.full(ncell, float(np.prod(hcell)))
+    else:
+        verts_idx = [sum((k * ((v >> e) & 1)) * (k + 1) ** e for e in range(dim)) for v in range(2 ** dim)]
+        h_min, meas = _vertex_geometry(pts[:, verts_idx, :], dim)
     mesh = Mesh(dim=dim, degree=p, n_cells=ncell, n_dofs=n_owned + n_ghost, n_owned=n_owned,
-                cell_dofs=cell_dofs.astype(index_dtype), geometry_type=0, cell_points=None, mapping_degree=1,
-                constraints={}, cell_h_min=np.full(ncell, hcell), cell_measure=np.full(ncell, hcell ** dim),
+                cell_dofs=cell_dofs.astype(index_dtype), geometry_type=0 if deform is None else 2, cell_points=pts,
+                mapping_degree=k, constraints={}, cell_h_min=h_min, cell_measure=meas,
                 partition=part, node_compact=True, n_global_dofs=int(np.prod(gn)) * C)
-    mesh.cart_inv_jac = np.full((ncell, dim), 1.0 / hcell)
-    mesh.cart_det = np.full(ncell, hcell ** dim)
+    if deform is None:
+        mesh.cart_inv_jac = np.broadcast_to(1.0 / hcell, (ncell, dim)).copy()
+        mesh.cart_det = np.full(ncell, float(np.prod(hcell)))
     mesh.cell_is_boundary = (cell_dofs >= n_owned).any(axis=1)
-    gijk = ijk + (b * p * n_per_dir)[None, :]
+    gijk = ijk + (b * p * np.asarray(shape))[None, :]
     gnode = np.zeros(nnode, dtype=np.int64)
     mul = 1
     for e in range(dim):
-        gnode += gijk[:, e] * mul
+        gnode += (gijk[:, e] % gn[e]) * mul
         mul *= gn[e]
     canon = np.empty(n_owned + n_ghost, dtype=np.int64)
     for c in range(C):
         canon[local_of_node * C + c] = gnode * C + c
     mesh.canonical_ids = canon
     mesh.shape, mesh.cell_coords = shape, np.ascontiguousarray(cc)
-    mesh.extent, mesh.origin = np.ones(dim), b.astype(np.float64)
-    if with_points:
-        mloc = np.stack(np.meshgrid(*[np.arange(2)] * dim, indexing="ij"), axis=-1).reshape(-1, dim)[:, ::-1]
-        mesh.cell_points = mesh.origin[None, None, :] + (cc[:, None, :] + mloc[None, :, :].astype(np.float64)) * hcell
+    mesh.extent, mesh.origin = box_extent, origin
+    if dirichlet is not None:
+        gp = gauss_lobatto_points(p)
+        n_loc = n ** dim
+        nref = origin[None, None, :] + (cc[:, None, :] + gp[loc][None, :, :]) * hcell[None, None, :]
+        for c in range(C):
+            mask = dirichlet(nref.reshape(-1, dim), c).reshape(ncell, n_loc)
+            dofs = cell_dofs[:, c * n_loc:(c + 1) * n_loc][mask]
+            for dof in np.unique(dofs):
+                mesh.constraints[int(dof)] = []
     return mesh
+
+
+def hypercube_box(n_per_dir, degree, *, n_ranks=1, rank=0, dim=3, order="morton", with_points=True,
+                  index_dtype=np.uint32):
+    """Rank `rank`'s box of n^dim cells of a hypercube partitioned the way deal.II / p4est partition it: equal
+    pieces of the Morton curve (morton_rank_grid: halves, quarters, octants; performance.cc:29-31)."""
+    grid, box_of = morton_rank_grid(n_ranks, dim)
+    return structured_box((n_per_dir,) * dim, degree, grid=grid, box_of=box_of, rank=rank, order=order,
+                          with_points=with_points, index_dtype=index_dtype)
+
+
+def cylinder_shell_box(shape, degree, *, n_ranks=1, rank=0, r_inner=0.05, r_outer=0.5, length=0.41,
+                       mapping_degree=None, no_slip=True, **kw):
+    """Rank `rank`'s part of the O-grid of cylinder_shell() with `shape` = (radial, circumferential, axial) cells
+    PER RANK (weak scaling): the block is cut in the axial direction first, then radially (2 ranks: 1 x 1 x 2
+    boxes, 4: 2 x 1 x 2, 8: 2 x 1 x 4); the periodic circumferential direction is never split.  Same map, same
+    no-slip rows (cylinder surface and outer wall) as the single-rank generator."""
+    mapping_degree = degree if mapping_degree is None else mapping_degree
+    grid = {1: (1, 1, 1), 2: (1, 1, 2), 4: (2, 1, 2), 8: (2, 1, 4), 16: (2, 1, 8)}[n_ranks]
+    box_of = np.array([(r % grid[0], 0, r // grid[0]) for r in range(n_ranks)], dtype=np.int64)
+
+    def deform(x):
+        r = r_inner + (r_outer - r_inner) * x[..., 0] ** 1.5
+        th = 2.0 * np.pi * x[..., 1]
+        out = np.empty_like(x)
+        out[..., 0] = r * np.cos(th)
+        out[..., 1] = r * np.sin(th)
+        out[..., 2] = length * x[..., 2]
+        return out
+
+    def dirichlet(ref, c):
+        if c == 3:
+            return np.zeros(len(ref), dtype=bool)
+        return (np.abs(ref[:, 0]) < 1e-12) | (np.abs(ref[:, 0] - 1.0) < 1e-12)
+
+    return structured_box(shape, degree, grid=grid, box_of=box_of, rank=rank, periodic=(False, True, False),
+                          deform=deform, mapping_degree=mapping_degree, dirichlet=dirichlet if no_slip else None,
+                          box_extent=1.0 / np.asarray(grid, dtype=np.float64), **kw)
 
 
 def hypercube_hanging(dim, n_coarse, degree, *, refine=None, dirichlet=None, index_dtype=np.uint32):

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-from dealii_ns_gls_b200.driver import ChannelParameters  # noqa: E402
+from dealii_ns_gls_b200.driver import ChannelParameters, CylinderParameters  # noqa: E402
 from tests.test_solver_oracle import _oracle_driver  # noqa: E402
 
 CASES = {
@@ -31,8 +31,23 @@ CASES = {
 }
 
 
-def run(kw, n_steps=3):
-    d = _oracle_driver(ChannelParameters(**kw))
+# the BASELINE configs that are not the channel, on the synthetic O-grid (driver.CylinderParameters): curved cells,
+# no-slip cylinder rows, q-point-wise delta; level operators in float like the reference (config.h:7)
+CYLINDER_CASES = {
+    # input_turek_2D_Re20_stat.json:13-37: stationary ("none"), exact Newton, c1 = 1
+    "turek2d_stat": (dict(dim=2, time_integration="none", c_1=1.0, u_max=0.3, n_global_refinements=2), 1),
+    "turek2d_bdf2": (dict(dim=2, n_global_refinements=2, newton_inexact=True, u_max=0.3), 3),
+    # input_turek_3D_Re100.json:12-31: BDF2, inexact Newton, no-slip walls
+    "turek3d_bdf2": (dict(dim=3, n_global_refinements=1, base_shape=(2, 8, 2), newton_inexact=True, u_max=1.0,
+                          no_slip_wall=True), 2),
+    # input_hoffmann_3D_Re3900.json:37 / main.cc:285-287: slip walls
+    "hoffmann3d_slip": (dict(dim=3, n_global_refinements=1, base_shape=(2, 8, 2), newton_inexact=True, u_max=1.0,
+                             no_slip_wall=False), 2),
+}
+
+
+def run(kw, n_steps=3, params=ChannelParameters, **okw):
+    d = _oracle_driver(params(**kw), **okw)
     out = []
     for _ in range(n_steps):
         r = d.step()
@@ -43,6 +58,15 @@ def run(kw, n_steps=3):
 
 
 if __name__ == "__main__":
+    if "cylinder" in sys.argv[1:]:
+        rec = {name: dict(parameters=dict(kw, base_shape=list(kw["base_shape"])) if "base_shape" in kw else kw,
+                          steps=run(kw, n, params=CylinderParameters, level_dtype=np.float32))
+               for name, (kw, n) in CYLINDER_CASES.items()}
+        with open(os.path.join(HERE, "solver_cylinder.json"), "w") as f:
+            json.dump(rec, f, indent=1)
+        for name, r in rec.items():
+            print(name, [(s["newton_iterations"], s["linear_iterations"]) for s in r["steps"]])
+        sys.exit(0)
     rec = {name: dict(parameters=kw, steps=run(kw)) for name, kw in CASES.items()}
     with open(os.path.join(HERE, "solver_channel.json"), "w") as f:
         json.dump(rec, f, indent=1)

@@ -146,3 +146,47 @@ def test_four_rank_quarters_ghost_exchange_matches_single_domain(tmp_path):
         assert np.linalg.norm(d["dst"] - ref[d["ids"]]) <= 1e-13 * np.linalg.norm(ref)
         seen[d["ids"]] = True
     assert seen.all()
+
+
+def test_partitioned_cylinder_shell_equals_single_rank_shell():
+    """config C on N > 1 ranks (mesh.cylinder_shell_box: curved cells, periodic direction, no-slip rows): the cell
+    loops of the 4 parts, summed over shared dofs, equal the single-rank O-grid's vmult on the unconstrained rows."""
+    from dealii_ns_gls_b200 import mesh as gm
+    from tests.util import TI, make_oracle
+    ti = TI(2, [15.0, -20.0, 5.0], 0.1)
+
+    def keys(m):
+        x = gm.dof_coordinates(m).copy()
+        x[:, 1] = np.mod(np.round(x[:, 1], 9), 1.0)
+        c = gm.dof_components(m)
+        return [tuple(np.round(x[i], 8)) + (int(c[i]),) for i in range(m.n_dofs)]
+
+    def fld(ks, seed):
+        return np.array([np.sin(37.0 * k[0] + 69.0 * k[1] + 5.0 * k[2] + seed + k[3]) for k in ks])
+
+    N, sh = 4, (2, 5, 2)
+    full = gm.cylinder_shell((2 * sh[0], sh[1], 2 * sh[2]), 2)
+    kf = keys(full)
+    pos = {k: i for i, k in enumerate(kf)}
+    of = make_oracle(full, ti, ctd=True, cell_wise=False, nu=0.001)
+    of.set_previous_solution([fld(kf, s) for s in (5, 6, 7)], ti.get_weights())
+    of.set_linearization_point(fld(kf, 1), 0.1)
+    ref = of.vmult(fld(kf, 2), 15.0)
+    acc, owned = np.zeros(full.n_dofs), np.zeros(full.n_dofs, dtype=int)
+    for r in range(N):
+        m = gm.cylinder_shell_box(sh, 2, n_ranks=N, rank=r)
+        km = keys(m)
+        idx = np.array([pos[k] for k in km])
+        owned[idx[:m.n_owned]] += 1
+        o = make_oracle(m, ti, ctd=True, cell_wise=False, nu=0.001)
+        o.set_previous_solution([fld(km, s) for s in (5, 6, 7)], ti.get_weights())
+        o.set_linearization_point(fld(km, 1), 0.1)
+        x = fld(km, 2).copy()
+        cons = np.array(sorted(m.constraints), dtype=np.int64)
+        x[cons] = 0
+        np.add.at(acc, idx, o._scatter(o._apply_cells(o._gather(x), 15.0, False)))
+        assert set(idx[cons].tolist()) <= set(full.constraints.keys())
+    assert (owned == 1).all()
+    free = np.ones(full.n_dofs, dtype=bool)
+    free[np.array(sorted(full.constraints), dtype=np.int64)] = False
+    assert np.linalg.norm((acc - ref)[free]) <= 1e-13 * np.linalg.norm(ref[free])

@@ -187,3 +187,53 @@ def test_vcycle_as_cuda_graph_matches_eager():
     graph.preconditioner.vmult(y1, src)
     graph.preconditioner.vmult(y1, src)
     assert rel_l2(y1.cpu().numpy(), y0.cpu().numpy()) < 1e-5  # float levels, atomics: not bit-identical
+
+
+# ---- the BASELINE configs that are not the channel: curved O-grid, no-slip cylinder rows, q-point-wise delta ----
+def _cylinder_golden():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "solver_cylinder.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("kw,n_steps", [
+    (dict(dim=2, time_integration="none", c_1=1.0, u_max=0.3, n_global_refinements=2), 1),
+    (dict(dim=2, n_global_refinements=2, newton_inexact=True, u_max=0.3), 2)], ids=["turek2d_stat", "turek2d_bdf2"])
+@pytest.mark.parametrize("mg_number", ["double", "float"])
+def test_cylinder_time_steps_identical_iteration_counts(kw, n_steps, mg_number):
+    """input_turek_2D_Re20_stat.json (stationary, exact Newton) and its BDF2 / inexact-Newton variant on the
+    synthetic O-grid: device loop against the CPU restatement run side by side, counts identical step by step"""
+    from dealii_ns_gls_b200.driver import CylinderParameters
+    p = CylinderParameters(mg_number=mg_number, **kw)
+    dev = Driver(p)
+    ora = _oracle_driver(p, level_dtype=np.float64 if mg_number == "double" else np.float32)
+    for _ in range(n_steps):
+        rd, ro = dev.step(), ora.step()
+        assert rd["newton_iterations"] == ro["newton_iterations"]
+        assert rd["linear_iterations"] == ro["linear_iterations"]
+        tol = 1e-6 if mg_number == "double" else 1e-3
+        assert abs(rd["dt"] / ro["dt"] - 1) < tol
+        assert np.allclose(rd["newton_residuals"][:2], ro["newton_residuals"][:2], rtol=tol)
+        assert rel_l2(dev.solution.get_current_solution().cpu().numpy(), ora.history[0]) < tol
+
+
+@pytest.mark.parametrize("name", ["turek2d_stat", "turek2d_bdf2", "turek3d_bdf2", "hoffmann3d_slip"])
+def test_cylinder_time_steps_match_golden_record(name):
+    """the device time loop (float level operators) against the committed record of the oracle's solver stack for
+    the Turek / Hoffmann-like configurations, tests/golden/solver_cylinder.json (3-D BDF2 + inexact Newton +
+    q-point-wise delta with no-slip and with slip walls included): iteration counts identical"""
+    from dealii_ns_gls_b200.driver import CylinderParameters
+    g = _cylinder_golden()[name]
+    kw = dict(g["parameters"])
+    if "base_shape" in kw:
+        kw["base_shape"] = tuple(kw["base_shape"])
+    dev = Driver(CylinderParameters(mg_number="float", **kw))
+    for ref in g["steps"]:
+        r = dev.step()
+        assert r["newton_iterations"] == ref["newton_iterations"]
+        assert r["linear_iterations"] == ref["linear_iterations"]
+        assert abs(r["dt"] / ref["dt"] - 1) < 1e-3
+        assert np.allclose(r["newton_residuals"][:2], ref["first_residuals"], rtol=1e-3)
+        l2 = float(torch.linalg.vector_norm(dev.solution.get_current_solution()))
+        assert abs(l2 / ref["solution_l2"] - 1) < 1e-3

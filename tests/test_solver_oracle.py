@@ -64,13 +64,14 @@ def test_gmres_matches_dense_solve():
 
 
 def _oracle_driver(p, **kw):
-    n_levels = 2 + p.n_global_refinements
-    meshes = {l: channel_level_mesh(p, l) for l in range(n_levels + 1)}
+    n_levels = p.n_levels()
+    meshes = {l: p.level_mesh(l) for l in range(n_levels + 1)}
     children = {l: M.child_cells(meshes[l - 1], meshes[l]) for l in range(1, n_levels + 1)}
-    ci = channel_inhomogeneous_constraints(p, meshes[n_levels])
+    ci = p.inhomogeneous_constraints(meshes[n_levels])
+    kw.setdefault("newton_inexact", p.newton_inexact)
     return gs.OracleChannelDriver(dim=p.dim, degree=p.fe_degree, meshes=meshes, children=children,
                                   constraints_inhomogeneous=ci.rows, inhomogeneities=ci.inhomogeneities,
-                                  min_dx=np.sqrt(p.dim) / 2 ** n_levels, nu=p.nu, c1=p.c_1, c2=p.c_2, cfl=p.cfl,
+                                  min_dx=p.minimal_cell_diameter(meshes[n_levels]), nu=p.nu, c1=p.c_1, c2=p.c_2, cfl=p.cfl,
                                   bdf_order=p.bdf_order if p.time_integration == "bdf" else 0,
                                   consider_time_derivative=p.consider_time_derivative,
                                   cell_wise_stabilization=p.cell_wise_stabilization,
@@ -112,3 +113,24 @@ def test_solver_stack_matches_golden_record(name):
         assert abs(r["dt"] / ref["dt"] - 1) < 1e-10
         assert np.allclose(r["newton_residuals"][:2], ref["first_residuals"], rtol=1e-8)
         assert abs(np.linalg.norm(d.history[0]) / ref["solution_l2"] - 1) < 1e-8
+
+
+@pytest.mark.parametrize("name", ["turek2d_stat", "turek2d_bdf2"])
+def test_cylinder_solver_stack_matches_golden_record(name):
+    """tests/golden/solver_cylinder.json pins the oracle's counts for the Turek-like configurations on the synthetic
+    O-grid (curved cells, no-slip cylinder rows, q-point-wise delta, float level operators); the 2-D cases here, the
+    3-D ones (minutes on the CPU) are checked through the device path in the GPU suite"""
+    import json
+    import os
+    from dealii_ns_gls_b200.driver import CylinderParameters
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "solver_cylinder.json")) as f:
+        g = json.load(f)[name]
+    d = _oracle_driver(CylinderParameters(**g["parameters"]), level_dtype=np.float32)
+    for ref in g["steps"]:
+        r = d.step()
+        assert r["newton_iterations"] == ref["newton_iterations"]
+        assert r["linear_iterations"] == ref["linear_iterations"]
+        assert abs(r["dt"] / ref["dt"] - 1) < 1e-10
+        assert np.allclose(r["newton_residuals"][:2], ref["first_residuals"], rtol=1e-6)
+    # the cylinder stays at rest and the inflow value is kept
+    assert np.allclose(d.history[0][d.cdofs], d.cvals)
