@@ -393,6 +393,15 @@ def run_gpu(args):
         t = torch.tensor([t_ms, e2e_ms, k_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_ms, e2e_ms, k_ms = [float(x) for x in t]
+    # wall time per time step on N > 1 GPUs: a collective piece of work, every rank takes part
+    time_step_multi = None
+    if world > 1 and args.workload == "P" and args.time_step_refinements >= 0:
+        del op, src, dst, h_src, h_dst
+        torch.cuda.empty_cache()
+        try:
+            time_step_multi = time_step_wall(args.time_step_refinements, dev, n_ranks=world, rank=rank)
+        except Exception as e:
+            time_step_multi = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -454,6 +463,8 @@ def run_gpu(args):
             del zero
         except Exception as e:
             line["zero_vector_protocol"] = {"error": f"{type(e).__name__}: {e}"}
+    if time_step_multi is not None:
+        line["time_step"] = time_step_multi
     if world == 1:
         del op, src, dst, h_src, h_dst
         torch.cuda.empty_cache()
@@ -538,7 +549,7 @@ def config_c_measure(args, dev, peak):
     return r
 
 
-def time_step_wall(refinements, dev, n_steps=4):
+def time_step_wall(refinements, dev, n_steps=4, n_ranks=1, rank=0):
     """The second half of BASELINE.json's metric, "wall time per time step": the time loop of main.cc:908-990
     (get_max_u, set_previous_solution on all levels, Newton with GMRES + geometric multigrid: relaxation
     smoothers, device transfers, dense coarse solve) on the 3-D channel of input_channel.json at Q2, with the
@@ -548,21 +559,32 @@ def time_step_wall(refinements, dev, n_steps=4):
 
     from dealii_ns_gls_b200.driver import ChannelParameters, Driver
     t0 = time.perf_counter()
-    d = Driver(ChannelParameters(dim=3, fe_degree=2, n_global_refinements=refinements), device=dev)
+    # mg_min_level = 1: the coarsest level every rank of an 8-GPU run still holds cells on (the same hierarchy at
+    # every N, so that the iteration counts can be compared across N)
+    d = Driver(ChannelParameters(dim=3, fe_degree=2, n_global_refinements=refinements, mg_min_level=1), device=dev,
+               n_ranks=n_ranks, rank=rank)
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t0
+
+    def sync():
+        torch.cuda.synchronize()
+        if n_ranks > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
     walls, recs = [], []
     for i in range(2 + n_steps):
-        torch.cuda.synchronize()
+        sync()
         t0 = time.perf_counter()
         rec = d.step()
-        torch.cuda.synchronize()
+        sync()
         if i >= 2:
             walls.append(time.perf_counter() - t0)
             recs.append(rec)
     fine = d.meshes[d.maxlevel]
     return {"wall_s_per_step": float(np.mean(walls)), "unit": "s", "steps": n_steps, "warmup_steps": 2,
-            "n_dofs": int(fine.n_dofs), "n_cells": int(fine.n_cells), "levels": d.maxlevel + 1,
+            "n_gpus": n_ranks, "scaling": "strong (the same mesh cut into x-slabs of the channel)",
+            "n_dofs": int(fine.n_global_dofs), "n_cells": int(fine.n_cells) * n_ranks, "levels": d.maxlevel + 1 - d.minlevel,
             "newton_iterations": [r["newton_iterations"] for r in recs],
             "gmres_iterations": [r["linear_iterations"] for r in recs],
             "setup_s": setup_s,

@@ -745,10 +745,10 @@ int do_matrix(glsb_op *op, void *M, double weight, cudaStream_t s)
   cell_range(op, GLSB_CELLS_ALL, p);
   p.dst         = static_cast<T *>(M);
   p.weight      = (T)weight;
-  p.unit_stride = op->n_owned;
+  p.unit_stride = op->n_owned + op->n_ghost;
   op->launches++;
-  return Kernels<dim, T>::matrix_columns(op->n, op->increment_form ? BR_NEWTON : BR_FIXED_POINT, (uint32_t)op->n_owned, p,
-                                         op->shape, s);
+  return Kernels<dim, T>::matrix_columns(op->n, op->increment_form ? BR_NEWTON : BR_FIXED_POINT,
+                                         (uint32_t)(op->n_owned + op->n_ghost), p, op->shape, s);
 }
 
 template <typename T>
@@ -1472,12 +1472,11 @@ int glsb_get_system_matrix(glsb_op *op, double *A_dev, double weight, void *stre
 {
   if (!op || !A_dev)
     return 1;
-  if (op->n_ghost != 0)
-    {
-      op->err = "glsb_get_system_matrix: single-rank operators only (the coarse level lives on one rank)";
-      return 1;
-    }
-  const uint64_t n = op->n_owned;
+  // partitioned operators: the matrix of THIS rank's cell loop over its local dofs [owned | ghost]; the host
+  // layer sums the ranks' matrices into the global one (multigrid.py, MGCoarseGridDirect)
+  const uint64_t n = op->n_owned + op->n_ghost;
+  if (op->n_ghost != 0 && (op->n_faces != 0 || op->n_edge != 0))
+    return fail(op, "glsb_get_system_matrix: partitioned operators with outflow faces or edge indices are not supported");
   if (!op->lin_valid)
     return fail(op, "glsb_get_system_matrix: set_linearization_point has not been called");
   if (op->n_faces == 0 && op->n_edge == 0 && n <= 65535)

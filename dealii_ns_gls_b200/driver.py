@@ -13,7 +13,7 @@ import math
 import numpy as np
 import torch
 
-from .mesh import Mesh, dof_components, dof_coordinates, structured_mesh
+from .mesh import Mesh, dof_components, dof_coordinates, structured_box, structured_mesh
 from .multigrid import (DeviceVectorOps, MGTransferGlobalCoarsening, MGTwoLevelTransfer, PreconditionerGMG,
                         PreconditionerGMGAdditionalData)
 from .operator import AffineConstraints, NavierStokesOperator
@@ -41,6 +41,8 @@ class ChannelParameters:
         self.newton_inexact = False
         self.mg_number = "float"      # config.h:7
         self.n_stretching = 4         # simulation.cc:143-145
+        self.mg_min_level = 0         # coarsest multigrid level ("mg min level"); a partitioned run needs every rank
+                                      # to hold cells on it
         self.gmg = PreconditionerGMGAdditionalData()
         self.simulation_name = "channel"
         self._more_defaults()
@@ -56,8 +58,8 @@ class ChannelParameters:
     def n_levels(self):
         return 2 + self.n_global_refinements  # refine_global(2) + n (simulation.cc:166-169)
 
-    def level_mesh(self, level):
-        return channel_level_mesh(self, level)
+    def level_mesh(self, level, n_ranks=1, rank=0):
+        return channel_level_mesh(self, level, n_ranks, rank)
 
     def inhomogeneous_constraints(self, mesh):
         return channel_inhomogeneous_constraints(self, mesh)
@@ -136,7 +138,7 @@ class CylinderParameters(ChannelParameters):
         return float(cell_diameters(fine).min())
 
 
-def channel_level_mesh(params: ChannelParameters, level: int) -> Mesh:
+def channel_level_mesh(params: ChannelParameters, level: int, n_ranks: int = 1, rank: int = 0) -> Mesh:
     """SimulationChannel::create_triangulation (simulation.cc:150-170): n_stretching x 1 (x 1) unit blocks,
     refined `level` times; boundary ids 0/1 = x faces, 2/3 = y, 4/5 = z (colorize = true).  The zero
     constraints are constraints_homogeneous of main.cc:258-305: no-slip walls (ids >= 2), the inflow face
@@ -154,7 +156,18 @@ def channel_level_mesh(params: ChannelParameters, level: int) -> Mesh:
             m |= (np.abs(x[:, e]) < eps) | (np.abs(x[:, e] - 1.0) < eps)
         return m
 
-    return structured_mesh(dim, shape, params.fe_degree, extent=extent, dirichlet=zero_constrained)
+    if n_ranks == 1:
+        return structured_mesh(dim, shape, params.fe_degree, extent=extent, dirichlet=zero_constrained)
+    # one x-slab of the channel per rank on every level (the partitions of consecutive levels nest: children live
+    # on the rank of their parent, like the reference's global-coarsening hierarchy after repartitioning by
+    # the same space-filling curve)
+    if shape[0] % n_ranks != 0:
+        raise ValueError(f"level {level}: {shape[0]} cells in x cannot be cut into {n_ranks} slabs; raise mg_min_level")
+    grid = (n_ranks,) + (1,) * (dim - 1)
+    box_of = np.array([(r,) + (0,) * (dim - 1) for r in range(n_ranks)], dtype=np.int64)
+    local = (shape[0] // n_ranks,) + shape[1:]
+    return structured_box(local, params.fe_degree, grid=grid, box_of=box_of, rank=rank,
+                          box_extent=np.asarray(extent) / np.asarray(grid), dirichlet=zero_constrained)
 
 
 def channel_inhomogeneous_constraints(params: ChannelParameters, mesh: Mesh) -> AffineConstraints:
@@ -179,14 +192,27 @@ class Driver:
     """Driver<dim>::run with "preconditioner": "GMG", "nonlinear solver": "Newton" for the simulations the
     parameter object describes (ChannelParameters, CylinderParameters)."""
 
-    def __init__(self, params: ChannelParameters, device=None, verbose=False):
+    def __init__(self, params: ChannelParameters, device=None, verbose=False, n_ranks=1, rank=0, group=None):
+        """n_ranks > 1: one process per GPU (torch.distributed initialised by the caller); every level is
+        partitioned into the same boxes, level vectors are [owned | ghost] like LinearAlgebra::distributed::Vector,
+        inner products are summed over the ranks (solver_l.cc:46-74, solver_nl.cc:50,76 through deal.II)."""
         self.params, self.verbose = params, verbose
         self.timers = None
         p = params
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_ranks, self.rank = n_ranks, rank
         n_levels = p.n_levels()
-        self.meshes = {l: p.level_mesh(l) for l in range(n_levels + 1)}
-        self.minlevel, self.maxlevel = 0, n_levels
+        self.minlevel, self.maxlevel = p.mg_min_level, n_levels
+        if n_ranks == 1:
+            self.meshes = {l: p.level_mesh(l) for l in range(self.minlevel, n_levels + 1)}
+            make_exchange = lambda mesh: None  # noqa: E731
+            DeviceVectorOps.allreduce_sum = None
+        else:
+            import torch.distributed as dist
+            from .distributed import GhostExchange
+            self.meshes = {l: p.level_mesh(l, n_ranks, rank) for l in range(self.minlevel, n_levels + 1)}
+            make_exchange = lambda mesh: GhostExchange(mesh.partition, self.device, group)  # noqa: E731
+            DeviceVectorOps.allreduce_sum = staticmethod(lambda t: dist.all_reduce(t, group=group))
         fine = self.meshes[self.maxlevel]
         if p.time_integration == "bdf":
             self.time_integrator_data = TimeIntegratorDataBDF(p.bdf_order)
@@ -195,7 +221,11 @@ class Driver:
         else:
             raise NotImplementedError(p.time_integration)
         tid = self.time_integrator_data
-        self.constraints_inhomogeneous = p.inhomogeneous_constraints(fine)
+        ci = p.inhomogeneous_constraints(fine)
+        # vector-level constraint objects act on the owned block only (ghost entries stay zero between calls)
+        own = fine.n_owned
+        self.constraints_inhomogeneous = AffineConstraints({d: r for d, r in ci.rows.items() if d < own},
+                                                           {d: v for d, v in ci.inhomogeneities.items() if d < own})
         # `constraints` of main.cc:268-306: everything but the rows of the inhomogeneous boundary ids
         self.constraints = AffineConstraints({d: r for d, r in self.constraints_inhomogeneous.rows.items()
                                               if d not in self.constraints_inhomogeneous.inhomogeneities})
@@ -203,21 +233,24 @@ class Driver:
         # main.cc:333-348
         self.ns_operator = NavierStokesOperator(fine, self.constraints_inhomogeneous, p.nu, p.c_1, p.c_2, tid,
                                                 p.consider_time_derivative, increment_form,
-                                                p.cell_wise_stabilization, number="double", device=self.device)
+                                                p.cell_wise_stabilization, number="double", device=self.device,
+                                                exchange=make_exchange(fine))
         # main.cc:396-568: level operators (MGNumber) and transfers
         self.mg_ns_operators = {}
         for l in range(self.minlevel, self.maxlevel + 1):
             self.mg_ns_operators[l] = NavierStokesOperator(self.meshes[l], None, p.nu, p.c_1, p.c_2, tid,
                                                            p.consider_time_derivative, increment_form,
                                                            p.cell_wise_stabilization, number=p.mg_number,
-                                                           device=self.device)
+                                                           device=self.device, exchange=make_exchange(self.meshes[l]))
         t_nc, t_c = {}, {}
         for l in range(self.minlevel + 1, self.maxlevel + 1):
             mf, mc = self.meshes[l], self.meshes[l - 1]
-            t_nc[l] = MGTwoLevelTransfer().reinit(mf, mc, None, None, number=p.mg_number, device=self.device)
+            of, oc = self.mg_ns_operators[l], self.mg_ns_operators[l - 1]
+            t_nc[l] = MGTwoLevelTransfer().reinit(mf, mc, None, None, number=p.mg_number, device=self.device,
+                                                  op_fine=of, op_coarse=oc)
             t_c[l] = MGTwoLevelTransfer().reinit(mf, mc, AffineConstraints(mf.constraints),
                                                  AffineConstraints(mc.constraints), number=p.mg_number,
-                                                 device=self.device)
+                                                 device=self.device, op_fine=of, op_coarse=oc)
         init = lambda l: self.mg_ns_operators[l].initialize_dof_vector()  # noqa: E731
         self.mg_transfer_no_constraints = MGTransferGlobalCoarsening(t_nc, init)
         self.transfer = MGTransferGlobalCoarsening(t_c, init)

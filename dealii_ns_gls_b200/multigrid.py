@@ -41,6 +41,12 @@ class DeviceVectorOps:
     """The vector operations deal.II's Multigrid / SolverGMRES do on LinearAlgebra::distributed::Vector,
     forwarded to the glsb_vec_* kernels."""
 
+    # distributed vectors: set by the driver of a multi-rank run to a function that sums a small float64 device
+    # tensor over the ranks in place (NCCL all-reduce: Utilities::MPI::sum of the local inner products, what
+    # LinearAlgebra::distributed::Vector::operator* does).  Vectors carry no ghost values between operator
+    # calls, so the local kernels may run over the whole local array.
+    allreduce_sum = None
+
     def __init__(self):
         self._lib = L.load()
 
@@ -61,6 +67,8 @@ class DeviceVectorOps:
         """out[j] = V[j] . w for j < k; V is a contiguous [m, n] block, out a float64 device vector."""
         self._chk(self._lib.glsb_vec_multi_dot(_ptr(out), _ptr(V), V.stride(0), int(k), _ptr(w), w.numel(),
                                                _type_of(w), _stream(w)), "vec_multi_dot")
+        if DeviceVectorOps.allreduce_sum is not None:
+            DeviceVectorOps.allreduce_sum(out[:int(k)])
 
     def multi_axpy(self, w, V, k, coef, scale):
         """w += scale * sum_j coef[j] V[j]"""
@@ -87,12 +95,20 @@ class MGTwoLevelTransfer:
         self._t = None
 
     def reinit(self, mesh_fine: Mesh, mesh_coarse: Mesh, constraints_fine: AffineConstraints | None = None,
-               constraints_coarse: AffineConstraints | None = None, number="float", device=None):
+               constraints_coarse: AffineConstraints | None = None, number="float", device=None,
+               op_fine=None, op_coarse=None):
+        """op_fine / op_coarse: the level operators of a PARTITIONED hierarchy (their ghost exchange and pack /
+        unpack kernels are used around the cell-wise transfer kernels).  Children live on the rank of their
+        parent (the partitions of consecutive levels nest), so the exchange is the levels' own vector exchange:
+        ghost import of the source, compress(add) of the destination."""
         if not torch.cuda.is_available():
             raise RuntimeError("MGTwoLevelTransfer needs a CUDA device; there is no CPU fallback")
         self.dtype = _torch_dtype(number)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.n_fine, self.n_coarse = mesh_fine.n_dofs, mesh_coarse.n_dofs
+        self.op_fine = op_fine if (op_fine is not None and op_fine.exchange is not None) else None
+        self.op_coarse = op_coarse if (op_coarse is not None and op_coarse.exchange is not None) else None
+        self.n_owned_fine, self.n_owned_coarse = mesh_fine.n_owned, mesh_coarse.n_owned
         ndof = (mesh_coarse.dim + 1) * mesh_coarse.n_loc
         ch = child_cells(mesh_coarse, mesh_fine)
         fidx = np.ascontiguousarray(mesh_fine.cell_dofs[ch.reshape(-1)].reshape(mesh_coarse.n_cells, -1),
@@ -112,6 +128,12 @@ class MGTwoLevelTransfer:
             cidx = np.where(r >= 0, (r | L.GLSB_CONSTRAINED_BIT).astype(np.uint32), cidx).astype(np.uint32)
         cidx = np.ascontiguousarray(cidx)
         touch = np.bincount(mesh_fine.cell_dofs.reshape(-1).astype(np.int64), minlength=mesh_fine.n_dofs)
+        if self.op_fine is not None:
+            # number of fine cells touching a dof over ALL ranks: compress(add) the local counts, send them back
+            t = torch.tensor(touch, dtype=self.op_fine.dtype, device=self.device)
+            self.op_fine.exchange.compress_add(self.op_fine, t)
+            self.op_fine.exchange.update_ghost_values(self.op_fine, t)
+            touch = np.rint(t.double().cpu().numpy()).astype(np.int64)
         weights = np.where(touch > 0, 1.0 / np.maximum(touch, 1), 0.0)
         if constraints_fine is not None and constraints_fine.rows:
             weights[np.fromiter(constraints_fine.rows.keys(), dtype=np.int64)] = 0.0
@@ -157,17 +179,41 @@ class MGTwoLevelTransfer:
         if rc != 0:
             raise L.GlsbError(f"{what} failed: " + self._lib.glsb_transfer_last_error(self._t).decode())
 
+    @staticmethod
+    def _import(op, vec):
+        if op is not None:
+            op.exchange.update_ghost_values(op, vec)
+
+    @staticmethod
+    def _drop_ghosts(op, vec):
+        if op is not None and vec.numel() > op.n_owned:
+            vec[op.n_owned:] = 0
+
+    @staticmethod
+    def _compress(op, vec):
+        if op is not None:
+            op.exchange.compress_add(op, vec)  # leaves the ghost block zeroed
+
     def prolongate_and_add(self, dst_fine, src_coarse):
+        self._import(self.op_coarse, src_coarse)
         self._call(self._lib.glsb_transfer_prolongate_and_add, dst_fine, src_coarse, self.n_fine, self.n_coarse,
                    "prolongate_and_add")
+        self._drop_ghosts(self.op_coarse, src_coarse)
+        self._compress(self.op_fine, dst_fine)
 
     def restrict_and_add(self, dst_coarse, src_fine):
+        self._import(self.op_fine, src_fine)
         self._call(self._lib.glsb_transfer_restrict_and_add, dst_coarse, src_fine, self.n_coarse, self.n_fine,
                    "restrict_and_add")
+        self._drop_ghosts(self.op_fine, src_fine)
+        self._compress(self.op_coarse, dst_coarse)
 
     def interpolate(self, dst_coarse, src_fine):
+        self._import(self.op_fine, src_fine)
         self._call(self._lib.glsb_transfer_interpolate, dst_coarse, src_fine, self.n_coarse, self.n_fine,
                    "interpolate")
+        self._drop_ghosts(self.op_fine, src_fine)
+        self._drop_ghosts(self.op_coarse, dst_coarse)  # every owned coarse dof was written by a local cell
 
 
 class MGTransferGlobalCoarsening:
@@ -226,11 +272,47 @@ class MGCoarseGridDirect:
     def __init__(self, op, ops: DeviceVectorOps):
         self.op, self._ops = op, ops
         self.matrix = op.get_system_matrix()
+        self._gid = None
+        if op.exchange is not None:
+            # partitioned coarse level: the rank-local matrices (local cells only) are summed into the global one
+            # over the partition-independent ids of the dofs, and every rank factorises / applies the same small
+            # dense matrix (the reference runs its direct solver on the distributed Trilinos matrix)
+            import torch.distributed as dist
+            mesh, dev = op.mesh, op.device
+            ng, nl = mesh.n_global_dofs, mesh.n_dofs
+            gid = torch.as_tensor(mesh.canonical_ids, dtype=torch.long, device=dev)
+            cons = torch.zeros(nl, dtype=torch.bool, device=dev)
+            if mesh.constraints:
+                cons[torch.as_tensor(np.fromiter(mesh.constraints.keys(), dtype=np.int64), device=dev)] = True
+            A = self.matrix.clone()
+            A[cons, :] = 0   # identity rows are set once, globally, below
+            A[:, cons] = 0   # constrained columns read 0 (zero-type rows)
+            G = torch.zeros((ng, ng), dtype=torch.float64, device=dev)
+            G.index_put_((gid[:, None].expand(nl, nl), gid[None, :].expand(nl, nl)), A, accumulate=True)
+            gc = torch.zeros(ng, dtype=torch.float64, device=dev)
+            gc[gid[cons]] = 1.0
+            dist.all_reduce(G, group=op.exchange.group)
+            dist.all_reduce(gc, group=op.exchange.group)
+            ci = torch.nonzero(gc > 0).flatten()
+            G[ci, ci] = 1.0
+            self.matrix = G
+            self._gid = gid[:op.n_owned]
+            self._gsrc = torch.zeros(ng, dtype=op.dtype, device=dev)
+            self._gdst = torch.zeros(ng, dtype=op.dtype, device=dev)
         # the factorisation of the direct solver: LAPACK on the host, in double, once per initialize()
         self.inverse = torch.from_numpy(np.ascontiguousarray(np.linalg.inv(self.matrix.cpu().numpy()))).to(op.device)
 
     def __call__(self, level, dst, src):
-        self._ops.dense_apply(dst, self.inverse, src)
+        if self._gid is None:
+            self._ops.dense_apply(dst, self.inverse, src)
+            return
+        import torch.distributed as dist
+        self._gsrc.zero_()
+        self._gsrc[self._gid] = src[:self.op.n_owned]
+        dist.all_reduce(self._gsrc, group=self.op.exchange.group)
+        self._ops.dense_apply(self._gdst, self.inverse, self._gsrc)
+        dst.zero_()
+        dst[:self.op.n_owned] = self._gdst[self._gid]
 
 
 class MGCoarseGridIdentity:

@@ -232,6 +232,12 @@ class NavierStokesOperator:
         if self.exchange is not None:
             self.exchange.compress_add(self, vec)
 
+    def _zero_ghosts(self, vec):
+        """vectors leave every call without ghost values, like the reference's (operator_ns.cc:540, :591): the
+        vector operations of the solvers (dots, norms, axpys over the whole local array) rely on it"""
+        if self.exchange is not None and vec.numel() > self.n_owned:
+            vec[self.n_owned:] = 0
+
     # ---- OperatorBase interface ----
     def m(self):
         return self.mesh.n_global_dofs
@@ -304,6 +310,7 @@ class NavierStokesOperator:
         dt = self.time_integrator_data.get_current_dt()
         self._chk(self._lib.glsb_set_linearization_point(self._op, self._vec(vec, "vec"), dt, self._stream()),
                   "set_linearization_point")
+        self._zero_ghosts(vec)
 
     def set_previous_solution(self, history):
         """operator_ns.cc:234-320; history = SolutionHistory or a list of vectors."""
@@ -318,6 +325,8 @@ class NavierStokesOperator:
         ws = (C.c_double * (order + 1))(*[float(x) for x in w[:order + 1]])
         self._chk(self._lib.glsb_set_previous_solution(self._op, ptrs, ws, order, self._stream()),
                   "set_previous_solution")
+        for v in vecs[1:order + 1]:
+            self._zero_ghosts(v)
 
     def evaluate_residual(self, dst: torch.Tensor, src: torch.Tensor):
         """operator_ns.cc:648-682."""
@@ -364,6 +373,7 @@ class NavierStokesOperator:
         self._chk(self._lib.glsb_get_max_u(self._op, self._vec(vec, "vec"), C.byref(out), self._stream()),
                   "get_max_u")
         val = out.value
+        self._zero_ghosts(vec)
         if self.exchange is not None:
             val = self.exchange.allreduce_max(val)
         return val

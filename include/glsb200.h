@@ -218,7 +218,9 @@ int glsb_diagonal_finish(glsb_op *op, void *diag, void *stream);
 /* get_system_matrix (operator_ns.cc:1303-1434, used by the coarse-grid solvers, multigrid.cc:395-425): the
  * matrix of vmult, dense, row-major n x n doubles on the device (A[i * n + j]), obtained column by column
  * from the operator's own cell loop (MatrixFreeTools::compute_matrix does the same cell-wise): constrained
- * rows carry 1 on the diagonal.  Meant for the coarsest multigrid level only; single-rank operators. */
+ * rows carry 1 on the diagonal.  Meant for the coarsest multigrid level only.  n = n_owned + n_ghost: a
+ * partitioned operator returns the matrix of its own cells over its local dofs, which the host layer sums over
+ * the ranks (identity rows of owned constrained dofs only). */
 int glsb_get_system_matrix(glsb_op *op, double *A_dev, double weight, void *stream);
 
 /* get_max_u (operator_ns.cc:530-568): max over the local quadrature points of |u|;

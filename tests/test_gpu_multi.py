@@ -23,3 +23,21 @@ def test_multi_gpu_parity(world):
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(" OK") >= 3 * world
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_time_step_counts_equal_single_gpu(world, tmp_path):
+    """the whole solver path partitioned (level operators, transfers, smoothers, coarse solve, Krylov reductions):
+    Newton / GMRES iteration counts of the 3-D Q2 channel on `world` GPUs equal those on one GPU"""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    rec = str(tmp_path / "step_n1.json")
+    script = os.path.join(ROOT, "tests", "multi_gpu_step_check.py")
+    r1 = subprocess.run([sys.executable, script, "--record", rec], cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r1.returncode == 0, r1.stdout[-2000:] + r1.stderr[-2000:]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29700 + world), script, "--record", rec]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(" OK") == world
