@@ -393,6 +393,7 @@ def run_gpu(args):
         t = torch.tensor([t_ms, e2e_ms, k_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_ms, e2e_ms, k_ms = [float(x) for x in t]
+    variant = op.vmult_variant()
     # wall time per time step on N > 1 GPUs: a collective piece of work, every rank takes part
     time_step_multi = None
     if world > 1 and args.workload == "P" and args.time_step_refinements >= 0:
@@ -436,14 +437,14 @@ def run_gpu(args):
         "metric": "GLS NS operator vmult throughput", "value": value, "unit": "GDoF/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": t_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.number == "double" else "f32", "data": "synthetic",
-        "config": dict(workload_config(args, world), n_dofs_global=n_global, kernel_variant=op.vmult_variant(),
+        "config": dict(workload_config(args, world), n_dofs_global=n_global, kernel_variant=variant,
                        checksum_abs_sum=checksum),
         "e2e": {"value": n_global * e2e_steps / (e2e_ms * 1e-3) / 1e9, "unit": "GDoF/s",
                 "h2d_bytes_per_step": n_local * nb, "d2h_bytes_per_step": n_local * nb, "steps": e2e_steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                      "frac": achieved / peaks.get("hbm_gbs"), "traffic": traffic,
-                     "peak_source": peaks_src, "kernel": op.vmult_variant(), "kernel_ms": k_ms,
+                     "peak_source": peaks_src, "kernel": variant, "kernel_ms": k_ms,
                      "algorithmic_bytes_per_cell": bpc, "cells_per_launch": n_cells},
         "clocks": sampler.summary(),
     }
@@ -588,7 +589,7 @@ def time_step_wall(refinements, dev, n_steps=4, n_ranks=1, rank=0):
             "newton_iterations": [r["newton_iterations"] for r in recs],
             "gmres_iterations": [r["linear_iterations"] for r in recs],
             "setup_s": setup_s,
-            "workload": f"3D channel (simulation.cc:143-189), Q2, {fine.n_cells} cells, BDF1, CFL 0.1, Newton + "
+            "workload": f"3D channel (simulation.cc:143-189), Q2, {int(fine.n_cells) * n_ranks} cells, BDF1, CFL 0.1, Newton + "
                         "GMRES(rel 1e-2) + GMG V-cycle (5 relaxation sweeps, coarse direct), fine operator f64, "
                         "level operators f32"}
 

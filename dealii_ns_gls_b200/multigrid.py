@@ -299,8 +299,13 @@ class MGCoarseGridDirect:
             self._gid = gid[:op.n_owned]
             self._gsrc = torch.zeros(ng, dtype=op.dtype, device=dev)
             self._gdst = torch.zeros(ng, dtype=op.dtype, device=dev)
-        # the factorisation of the direct solver: LAPACK on the host, in double, once per initialize()
-        self.inverse = torch.from_numpy(np.ascontiguousarray(np.linalg.inv(self.matrix.cpu().numpy()))).to(op.device)
+        # the factorisation of the direct solver, in double, once per initialize(): LAPACK on the host for the
+        # few hundred dofs of a level-0 mesh, cuSOLVER on the device (torch.linalg.inv) above that -- a coarsest
+        # level that every rank of an 8-GPU run holds cells on has 1 700 dofs (3-D Q2 channel, level 1)
+        if self.matrix.shape[0] <= 512:
+            self.inverse = torch.from_numpy(np.ascontiguousarray(np.linalg.inv(self.matrix.cpu().numpy()))).to(op.device)
+        else:
+            self.inverse = torch.linalg.inv(self.matrix).contiguous()
 
     def __call__(self, level, dst, src):
         if self._gid is None:
