@@ -37,6 +37,9 @@ namespace q2
 #ifndef GLSB_Q2_GAH
 #define GLSB_Q2_GAH 0 // gather-ahead staging of the next batch's source values (measured: no gain)
 #endif
+#ifndef GLSB_Q2_XCH
+#define GLSB_Q2_XCH 0 // 1: block layout of the component exchange (one 16-byte quad per lane, broadcast reads)
+#endif
 #ifndef GLSB_Q2_F32_CTAS
 #define GLSB_Q2_F32_CTAS 3 // resident CTAs per SM the float instantiation is compiled for
 #endif
@@ -278,6 +281,13 @@ struct alignas(16) Pair<F2>
   F2 a, b;
 };
 
+// value, d_0, d_1, d_2 of one (cell, component) as one 16-byte element (4-byte values only)
+template <typename T>
+struct alignas(16) Quad
+{
+  T a, b, c, d;
+};
+
 // issue the bulk copy of stage j (row j % 9 of quadrature points of this CTA's batch j / 9) into ring slot
 // `slot`; called by one thread.  There is no producer warp: the slot is refilled by whichever warp is the
 // last to release it (an arrival counter per slot), so no warp ever waits for another one's progress.
@@ -346,6 +356,15 @@ __global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
   const int      xp0 = 2 * (lane >> 2), xp1 = 2 * (8 + (((lane >> 2) + 4) & 7));
   const int      xpos = ((c >> 1) ? xp1 : xp0) + (c & 1);
   V             *xw   = xch + warp * 2 * XSLOT;
+#if GLSB_Q2_XCH
+  // block layout of the exchange (per slot, 160 of the XSLOT values): entry e(k, j) = 4 k + ((j + (k >> 1)) & 3) of
+  // cell k, component j holds (value, d_0, d_1, d_2) -- 16-byte quads for 4-byte values, two planes of 16-byte
+  // pairs for 8-byte values.  The rotation makes the stores of a quarter-warp AND the broadcast reads of one
+  // component by the 8 cells of a warp hit every bank once; SUPG residuals of the velocity rows follow at 128.
+  constexpr bool XW8 = sizeof(V) == 8;
+  const int      xk = lane >> 2, xrot = xk >> 1;
+  const int      xe_own = 4 * xk + ((c + xrot) & 3);
+#endif
   // column of this lane's cell in a 32-cell table row, for fields of component row 0, 1, 2 and cv
   const int      colr[4] = {col, (col + 4) & 31, (col + 8) & 31, (col + 4 * cv) & 31};
   // this lane's entries of an index block: dof (c, j) at ixo + j * CELLS, the cell's flag word at flo
@@ -610,10 +629,20 @@ __global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
                     }
                   // ---- exchange round 1: publish value and gradient of this component --------------
                   V *xs = xw + (a & 1) * XSLOT;
+#if GLSB_Q2_XCH
+                  if (!XW8)
+                    *reinterpret_cast<Quad<V> *>(xs + 4 * xe_own) = Quad<V>{val, g0, g1, g2};
+                  else
+                    {
+                      *reinterpret_cast<Pair<V> *>(xs + 2 * xe_own)      = Pair<V>{val, g0};
+                      *reinterpret_cast<Pair<V> *>(xs + 64 + 2 * xe_own) = Pair<V>{g1, g2};
+                    }
+#else
                   xs[xpos]            = val;
                   xs[XROW + xpos]     = g0;
                   xs[2 * XROW + xpos] = g1;
                   xs[3 * XROW + xpos] = g2;
+#endif
                   // tables (field offsets of the prefix are fixed: U 0..2, grad U 3..11, grad P 12..14)
                   const V U0 = GLSB_TABR(0, qx, 0), U1 = GLSB_TABR(1, qx, 1), U2 = GLSB_TABR(2, qx, 2);
                   const V H0 = GLSB_TABR(3 + 3 * cv, qx, 3), H1 = GLSB_TABR(4 + 3 * cv, qx, 3),
@@ -622,6 +651,31 @@ __global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
                   const V d1 = CELLWISE ? d1c : GLSB_TAB(p.fd1q, qx);
                   const V d2 = CELLWISE ? d2c : GLSB_TAB(p.fd2q, qx);
                   __syncwarp();
+#if GLSB_Q2_XCH
+                  // the 4 lanes of a cell read the whole 4 x 4 block (broadcast reads), then pick their column
+                  V qv[4], q0[4], q1[4], q2[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    {
+                      const int e = 4 * xk + ((j + xrot) & 3);
+                      if (!XW8)
+                        {
+                          const Quad<V> q = *reinterpret_cast<const Quad<V> *>(xs + 4 * e);
+                          qv[j] = q.a, q0[j] = q.b, q1[j] = q.c, q2[j] = q.d;
+                        }
+                      else
+                        {
+                          const Pair<V> pa = *reinterpret_cast<const Pair<V> *>(xs + 2 * e),
+                                        pb = *reinterpret_cast<const Pair<V> *>(xs + 64 + 2 * e);
+                          qv[j] = pa.a, q0[j] = pa.b, q1[j] = pb.a, q2[j] = pb.b;
+                        }
+                    }
+                  const V u0 = qv[0], u1 = qv[1], u2 = qv[2], pp = qv[3];
+                  const V div = q0[0] + q1[1] + q2[2];
+                  // column c of grad u and d_c p
+                  const V Gc0 = sel3(cv, q0[0], q1[0], q2[0]), Gc1 = sel3(cv, q0[1], q1[1], q2[1]),
+                          Gc2 = sel3(cv, q0[2], q1[2], q2[2]), gpc = sel3(cv, q0[3], q1[3], q2[3]);
+#else
                   const Pair<V> u01 = *reinterpret_cast<const Pair<V> *>(xs + xp0),
                                 u2p = *reinterpret_cast<const Pair<V> *>(xs + xp1);
                   const V u0 = u01.a, u1 = u01.b, u2 = u2p.a, pp = u2p.b;
@@ -631,6 +685,7 @@ __global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
                   const Pair<V> G01 = *reinterpret_cast<const Pair<V> *>(xc + xp0),
                                 G2p = *reinterpret_cast<const Pair<V> *>(xc + xp1);
                   const V Gc0 = G01.a, Gc1 = G01.b, Gc2 = G2p.a, gpc = G2p.b;
+#endif
                   const V  td  = val * w;
                   const V  sgu = g0 * U0 + g1 * U1 + g2 * U2; // U . grad u_c
                   const V  ugs = H0 * u0 + H1 * u1 + H2 * u2; // u . grad U_c
@@ -641,7 +696,14 @@ __global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
                   const V r0  = d1 * (y + gpc);
                   // ---- exchange round 2: the pressure row is (grad q, residual_0): it needs r0 of the three
                   // velocity rows (operator_ns.cc:1166-1172), published as they are
+#if GLSB_Q2_XCH
+                  if (!XW8)
+                    xs[128 + 4 * xk + c] = r0;
+                  else
+                    xs[128 + (c >> 1) * 16 + 2 * xk + (c & 1)] = r0;
+#else
                   xs[4 * XROW + xpos] = r0;
+#endif
                   const V sgs = H0 * U0 + H1 * U1 + H2 * U2; // U . grad U_c
                   V       rb  = Pc + sgs;
                   if (CTD)
@@ -654,11 +716,29 @@ __global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
                   V       o2   = nu * (g2 + Gc2) + U2 * r0 + u2 * rr1 + vsel(c == 2, diag, VO::zero());
                   __syncwarp();
                   // pressure row: (q, div u) and (grad q, residual_0)
+#if GLSB_Q2_XCH
+                  V rp0, rp1, rp2;
+                  if (!XW8)
+                    {
+                      const Quad<V> r = *reinterpret_cast<const Quad<V> *>(xs + 128 + 4 * xk);
+                      rp0 = r.a, rp1 = r.b, rp2 = r.c;
+                    }
+                  else
+                    {
+                      const Pair<V> r = *reinterpret_cast<const Pair<V> *>(xs + 128 + 2 * xk);
+                      rp0 = r.a, rp1 = r.b, rp2 = xs[144 + 2 * xk];
+                    }
+                  vo = vsel(is_p, div, vo);
+                  o0 = vsel(is_p, rp0, o0);
+                  o1 = vsel(is_p, rp1, o1);
+                  o2 = vsel(is_p, rp2, o2);
+#else
                   const Pair<V> r01 = *reinterpret_cast<const Pair<V> *>(xs + 4 * XROW + xp0);
                   vo = vsel(is_p, div, vo);
                   o0 = vsel(is_p, r01.a, o0);
                   o1 = vsel(is_p, r01.b, o1);
                   o2 = vsel(is_p, xs[4 * XROW + xp1], o2);
+#endif
                   // submit_value / submit_gradient: times JxW, back to the reference cell
                   V ox, oy, oz;
                   if (GENERAL)

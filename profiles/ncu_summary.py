@@ -19,6 +19,8 @@ want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",  # ALL LSU wavefronts: shared + global
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__lsuin_requests.sum.pct_of_peak_sustained_elapsed",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
         "lts__t_sector_hit_rate.pct", "smsp__warps_eligible.avg.per_cycle_active", "sm__cycles_active.avg",
         "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed",
