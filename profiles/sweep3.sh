@@ -7,7 +7,7 @@ for cfg in "$@"; do
   i=$((i+1))
   envs="${cfg%%--*}"; args=""
   case "$cfg" in *--*) args="${cfg#*--}";; esac
-  env $envs python bench.py --steps 10 --warmup 3 --no-cpu-baseline --time-step-refinements -1 $args > gpurun_out/sweep_${tag}_$i.json 2> gpurun_out/sweep_${tag}_$i.err
+  env $envs python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras --time-step-refinements -1 $args > gpurun_out/sweep_${tag}_$i.json 2> gpurun_out/sweep_${tag}_$i.err
   python - <<PY
 import json
 try:
