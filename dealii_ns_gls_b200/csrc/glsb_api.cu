@@ -1151,6 +1151,16 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
             delete op;
             return fail(nullptr, "glsb_create: bad outflow face arrays");
           }
+        // the face part of the inverse diagonal (k_faces_diag) handles plain and zero-constrained dofs only:
+        // hanging-node (weighted) rows on an outflow-face cell would silently lose their face contribution to
+        // diag(C^T A C) (MatrixFreeTools::compute_diagonal includes it, operator_ns.cc:203-218) -- refuse loudly
+        for (uint32_t f = 0; f < nf; ++f)
+          if (has_weighted[d->face_cell[f]])
+            {
+              delete op;
+              return fail(nullptr, "glsb_create: weighted (hanging-node) constraint rows on a cell with an outflow "
+                                   "face are not supported by the face part of compute_inverse_diagonal");
+            }
         op->n_faces = nf;
         compute_face_basis_host(op->degree, op->Nf, op->Gf);
         std::vector<double> zeros((size_t)nf * nqf * dm, 0.0);

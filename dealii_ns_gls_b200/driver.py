@@ -355,7 +355,11 @@ class Driver:
                    newton_residuals=list(self.nonlinear_solver.residuals),
                    linear_iterations=list(self.linear_solver.n_iterations[n_lin_before:]))
         self.log.append(rec)
-        if self.verbose:
-            print(rec)
+        if self.verbose and self.rank == 0:
+            # the reference's console lines (main.cc:921-923, solver_nl.cc:53-88, solver_l.cc:70, main.cc:971), so that
+            # a deal.II run of the reference and this run can be diffed (reflog.py)
+            from .reflog import format_step
+            l2 = float(torch.linalg.vector_norm(cur[:self.ns_operator.n_owned])) if self.n_ranks == 1 else None
+            print(format_step(dict(rec, t=rec["t"] - dt, solution_l2=l2)), flush=True)
         self.counter += 1
         return rec

@@ -134,3 +134,29 @@ def test_cylinder_solver_stack_matches_golden_record(name):
         assert np.allclose(r["newton_residuals"][:2], ref["first_residuals"], rtol=1e-6)
     # the cylinder stays at rest and the inflow value is kept
     assert np.allclose(d.history[0][d.cdofs], d.cvals)
+
+
+def test_reference_log_parser_round_trip():
+    """reflog.py reads the console lines of the reference (main.cc:921-923, :971; solver_nl.cc:53, :79, :88;
+    solver_l.cc:70) -- here a transcript typed from those format strings -- and the lines the device driver prints,
+    and diffs the iteration counts"""
+    from dealii_ns_gls_b200 import reflog
+    ref = ("    [I] Number of active cells:    1024\n    [I] Global degrees of freedom: 3267\n"
+           "\ncycle\t1 at time t = 0 with delta_t = 0.00441942 and u_max = 1\n"
+           "    [N] step 0; residual = 0.0721688\n    [L] solved in 3 iterations.\n"
+           "    [N] step 1 ; residual = 0.00123\n    [L] solved in 4 iterations.\n"
+           "    [N] step 2 ; residual = 3.1e-08\n    [N] solved in 2 iterations.\n"
+           "    [S] l2-norm of solution: 25.7391\n"
+           "\ncycle\t2 at time t = 0.00441942 with delta_t = 0.00441942 and u_max = 1\n"
+           "    [N] step 0; residual = 0.01\n    [L] solved in 2 iterations.\n"
+           "    [N] step 1 ; residual = 9e-09\n    [N] solved in 1 iterations.\n"
+           "    [S] l2-norm of solution: 25.74\n")
+    a = reflog.parse(ref)
+    assert [s["newton_iterations"] for s in a] == [2, 1]
+    assert [s["linear_iterations"] for s in a] == [[3, 4], [2]]
+    assert a[0]["dt"] == 0.00441942 and a[1]["solution_l2"] == 25.74 and len(a[0]["newton_residuals"]) == 3
+    # what the driver prints parses back to the same record
+    b = reflog.parse("\n".join(reflog.format_step(s) for s in a))
+    assert reflog.compare(a, b) == []
+    b[1]["linear_iterations"] = [3]
+    assert reflog.compare(a, b) == ["cycle 2: GMRES iterations [2] vs [3]"]
