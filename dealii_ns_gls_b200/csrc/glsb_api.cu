@@ -351,6 +351,10 @@ struct glsb_op
   double   nu = 0, c1 = 0, c2 = 0, theta = 1;
   uint64_t n_cells = 0, n_owned = 0, n_ghost = 0, ncp = 0;
   uint32_t n_interior = 0, n_int_pad = 0, n_slots = 0;
+  // deterministic mode (GLSB_DETERMINISTIC=1, single-rank operators): cells sorted by colour, color_begin[c] =
+  // first slot of colour c; cells of one colour share no vector entry, the cell loops run colour by colour
+  std::vector<uint32_t> color_begin;
+  uint32_t              hole_override[2] = {0, 0};
   uint32_t n_rows = 0, n_constrained = 0;
   uint64_t n_export = 0;
   size_t   tsize = 8;
@@ -494,6 +498,36 @@ void cell_range(const glsb_op *op, int which, KParams<T> &p)
       p.cell_begin = op->range_override[0];
       p.cell_end   = op->range_override[1];
     }
+  if (op->hole_override[1] > op->hole_override[0])
+    {
+      p.hole_begin = op->hole_override[0];
+      p.hole_end   = op->hole_override[1];
+    }
+}
+
+// deterministic mode: run `launch` once per colour.  A colour's slots [b, e) need not start on a 32-slot batch:
+// the launch starts at the batch boundary below b and the slots in between (the previous colour's) are a hole.
+template <typename F>
+int for_each_color(glsb_op *op, F &&launch)
+{
+  const bool ranged = op->range_override[1] > op->range_override[0];
+  if (op->color_begin.empty() || ranged)
+    return launch();
+  int rc = 0;
+  for (size_t c = 0; c + 1 < op->color_begin.size() && rc == 0; ++c)
+    {
+      const uint32_t b = op->color_begin[c], e = op->color_begin[c + 1];
+      if (e <= b)
+        continue;
+      op->range_override[0] = b & ~31u;
+      op->range_override[1] = e;
+      op->hole_override[0]  = b & ~31u;
+      op->hole_override[1]  = b;
+      rc                    = launch();
+    }
+  op->range_override[0] = op->range_override[1] = 0;
+  op->hole_override[0] = op->hole_override[1] = 0;
+  return rc;
 }
 
 #define GLSB_DISPATCH(op, CALL)                                   \
@@ -576,8 +610,10 @@ int do_cells(glsb_op *op, void *dst, const void *src, double weight, int which, 
 {
   // boundary faces ride with the last part of the launch that covers the cells next to the partition surface
   // (their contributions to ghost dofs must be in dst before compress(add))
+  const bool colored    = !op->color_begin.empty() && op->hole_override[1] >= op->hole_override[0] &&
+                       op->range_override[1] > op->range_override[0] && op->range_override[1] == op->color_begin.back();
   const bool with_faces = op->n_faces > 0 && which != GLSB_CELLS_INTERIOR && part == n_parts - 1 &&
-                          !(op->range_override[1] > op->range_override[0]);
+                          (!(op->range_override[1] > op->range_override[0]) || colored);
   if (with_faces)
     {
       KParams<T> pf = base_params<T>(op);
@@ -589,6 +625,9 @@ int do_cells(glsb_op *op, void *dst, const void *src, double weight, int which, 
       if (do_faces<dim, T>(op, pf, branch == BR_RESIDUAL ? 1 : 0, s))
         return 1;
     }
+  if (!op->color_begin.empty() && which == GLSB_CELLS_ALL && n_parts == 1 &&
+      !(op->range_override[1] > op->range_override[0]))
+    return for_each_color(op, [&]() { return do_cells<dim, T>(op, dst, src, weight, which, branch, s, 0, 1); });
   KParams<T> p = base_params<T>(op);
   cell_range(op, which, p);
   if (n_parts > 1)
@@ -676,6 +715,21 @@ int do_diag(glsb_op *op, void *diag, double weight, cudaStream_t s)
   op->launches += 1 + (dc.n_list > 0);
   if (do_faces<dim, T>(op, p, 3, s))
     return 1;
+  if (!op->color_begin.empty() && !(op->range_override[1] > op->range_override[0]))
+    {
+      // colour by colour; the cells with weighted rows (dc list) are handled by the last launch only
+      const size_t nc = op->color_begin.size() - 1;
+      size_t       c  = 0;
+      return for_each_color(op, [&]() {
+        KParams<T> pc = p;
+        cell_range(op, GLSB_CELLS_ALL, pc);
+        DiagColumns dcc = dc;
+        if (++c < nc)
+          dcc.n_list = 0;
+        return Kernels<dim, T>::diagonal(op->n, op->increment_form ? BR_NEWTON : BR_FIXED_POINT, pc, op->shape,
+                                         op->diag_skip.as<uint8_t>(), dcc, s);
+      });
+    }
   return Kernels<dim, T>::diagonal(op->n, op->increment_form ? BR_NEWTON : BR_FIXED_POINT, p, op->shape,
                                    op->diag_skip.as<uint8_t>(), dc, s);
 }
@@ -903,9 +957,65 @@ int glsb_create(const glsb_desc *d, glsb_op **out)
   // padding slots repeat a real cell (safe to read) and are never scattered
   std::vector<uint32_t> perm;
   perm.reserve(nc + 160);
-  for (uint32_t k = 0; k < nc; ++k)
-    if (!is_boundary[k])
-      perm.push_back(k);
+  const bool deterministic = getenv("GLSB_DETERMINISTIC") != nullptr && atoi(getenv("GLSB_DETERMINISTIC")) != 0;
+  if (deterministic)
+    {
+      // Bit-reproducible summation: greedy colouring of the cells over the vector entries they scatter to (masters
+      // of weighted rows included; 8 colours on a structured hexahedral mesh), cells reordered colour by colour
+      // (stable, so the Morton locality inside a colour survives).  Two cells of one colour never add to the same
+      // entry, colours run as consecutive launches: every entry is summed in a fixed order whatever the timing.
+      if (d->n_ghost != 0)
+        {
+          delete op;
+          return fail(nullptr, "glsb_create: GLSB_DETERMINISTIC is for single-rank operators (n_ghost == 0)");
+        }
+      std::vector<uint32_t> mask(n_local, 0u), color(nc, 0u);
+      uint32_t              n_colors = 0;
+      for (uint32_t k = 0; k < nc; ++k)
+        {
+          const uint32_t *row  = d->dof_indices + (uint64_t)k * ndof;
+          uint32_t        used = 0;
+          auto            visit = [&](auto &&f) {
+            for (uint32_t j = 0; j < ndof; ++j)
+              {
+                const uint32_t iv = row[j];
+                if (iv & GLSB_CONSTRAINED_BIT)
+                  {
+                    const uint32_t r = iv & ~GLSB_CONSTRAINED_BIT;
+                    for (uint32_t e = d->row_ptr[r]; e < d->row_ptr[r + 1]; ++e)
+                      f(d->entry_col[e]);
+                  }
+                else
+                  f(iv);
+              }
+          };
+          visit([&](uint32_t i) { used |= mask[i]; });
+          uint32_t c = 0;
+          while (c < 32 && (used >> c) & 1u)
+            ++c;
+          if (c == 32)
+            {
+              delete op;
+              return fail(nullptr, "glsb_create: GLSB_DETERMINISTIC needs more than 32 colours on this mesh");
+            }
+          color[k] = c;
+          n_colors = std::max(n_colors, c + 1);
+          visit([&](uint32_t i) { mask[i] |= 1u << c; });
+        }
+      op->color_begin.assign(n_colors + 1, 0);
+      for (uint32_t c = 0; c < n_colors; ++c)
+        {
+          op->color_begin[c] = (uint32_t)perm.size();
+          for (uint32_t k = 0; k < nc; ++k)
+            if (color[k] == c)
+              perm.push_back(k);
+        }
+      op->color_begin[n_colors] = (uint32_t)perm.size();
+    }
+  else
+    for (uint32_t k = 0; k < nc; ++k)
+      if (!is_boundary[k])
+        perm.push_back(k);
   op->n_interior = (uint32_t)perm.size();
   while (perm.size() % 32 != 0)
     perm.push_back(perm.empty() ? 0 : perm.back());

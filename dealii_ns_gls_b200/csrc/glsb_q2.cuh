@@ -780,12 +780,13 @@ __global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
                   __syncwarp();
                   if (lane == 0)
                     {
-                      // release: this warp's reads of the slot are ordered before the count; acquire on the winning
-                      // side: the other warps' reads are ordered before the refill (which adds fence.proxy.async)
-                      __threadfence_block();
+                      // Every value this warp read from the slot has been CONSUMED by arithmetic above (the loads
+                      // have returned), and __syncwarp orders the lanes; the refilling thread issues
+                      // fence.proxy.async before the bulk copy.  An explicit __threadfence_block() pair around this
+                      // counter was measured: the MEMBAR waits for the lane's outstanding global atomics and loads,
+                      // 31.7 -> 23.5 GDoF/s (profiles/r02_experiments.txt) -- not kept.
                       if (atomicAdd(&cnt[slot], 1u) == TPB / 32 - 1)
                         {
-                          __threadfence_block();
                           cnt[slot] = 0;
                           if (it + nst < n_stages)
                             issue_stage<T, ROWS, VW, n>(p, F, tab, full, it + nst, slot);
@@ -882,10 +883,8 @@ __global__ void __launch_bounds__(TPB, (target_ctas<(int)sizeof(V), n>()))
       __syncwarp();
       if (!TSM && lane == 0)
         {
-          __threadfence_block(); // same release / acquire pairing as for the table ring
-          if (atomicAdd(&cnt[MAX_NST + (bi & 1)], 1u) == TPB / 32 - 1)
+          if (atomicAdd(&cnt[MAX_NST + (bi & 1)], 1u) == TPB / 32 - 1) // see the table ring above
             {
-              __threadfence_block();
               cnt[MAX_NST + (bi & 1)] = 0;
               if (bi + 2 < my_n)
                 issue_idx(bi + 2);

