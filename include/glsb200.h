@@ -122,6 +122,12 @@ typedef struct glsb_desc
 /* ---- life cycle -------------------------------------------------------- */
 
 /* replaces the constructor NavierStokesOperator::NavierStokesOperator (operator_ns.cc:68-153) */
+/* Environment switches read by glsb_create:
+ *   GLSB_DETERMINISTIC=1  bit-reproducible cell loops for single-rank operators: the cells are coloured over the
+ *                         vector entries they scatter to and run colour by colour, so every entry is summed in a
+ *                         fixed order instead of in the arrival order of the atomics (about 25 % slower; the
+ *                         register-tiled vmult is reproducible on hanging-node meshes too, the generic kernels on
+ *                         meshes without weighted rows). */
 int  glsb_create(const glsb_desc *desc, glsb_op **out);
 void glsb_destroy(glsb_op *op);
 /* last error text of op (or of the last failed glsb_create when op == NULL) */

@@ -31,6 +31,8 @@ def _mesh(kind, dim, degree):
             m.constraints[int(dof)] = [] if t >= 6 else [(int(a), float(w)) for a, w in
                                                          zip(masters, rng.uniform(-0.5, 1.0, len(masters)))]
         return m
+    if kind == "hanging":  # a true 2:1 mesh with deal.II's hanging-node rows (mesh.hypercube_hanging)
+        return gm.hypercube_hanging(dim, 2, degree)
     return gm.cylinder_shell((2, 5) if dim == 2 else (1, 4, 1), degree)
 
 
@@ -61,7 +63,7 @@ def test_points_agree_with_the_oracles():
 
 @pytest.mark.parametrize("theta", [1.0, 0.5])
 @pytest.mark.parametrize("kind,dim,degree", [("cube", 2, 1), ("shell", 2, 2), ("cube_hanging", 2, 2), ("cube", 3, 1),
-                                             ("shell", 3, 2), ("cube", 2, 3)])
+                                             ("shell", 3, 2), ("cube", 2, 3), ("hanging", 2, 2), ("hanging", 3, 1)])
 def test_matrix_free_equals_matrix_based(kind, dim, degree, theta):
     mesh = _mesh(kind, dim, degree)
     rng = np.random.default_rng(42)
