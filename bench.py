@@ -209,6 +209,24 @@ def gpu_parity_on_sample(sm, number, dev):
             "checker": "oracle/gls_oracle_c.c (CPU restatement; parity unpinned against deal.II)"}
 
 
+def gpu_parity_full_size(chk, op, dst, tdt, number):
+    """The `parity_full_size` object of the bench line: the operator bench.py has just timed, on fields that repeat
+    every 4 cells, against the numpy oracle on a 12^3-cell block of the same mesh size -- every entry of the
+    result compared (tests/full_size.py has the argument).  Changes the operator's linearization point."""
+    from tests.full_size import oracle_on_small
+    (lin_s, lin_b), (src_s, src_b) = chk.field(), chk.field()
+    op.set_linearization_point(lin_b.to(tdt))
+    op.vmult(dst, src_b.to(tdt))
+    ref = oracle_on_small(chk, lin=lin_s, src=src_s, hist=None, nu=NU, c1=C1, c2=C2, weights=[10.0, -10.0, 0.0],
+                          dt=DT, ctd=False, cell_wise=True)
+    r = chk.compare(dst, ref)
+    tol = 1e-12 if number == "double" else 2e-5
+    r.update(tol=tol, ok=bool(r["rel_l2_all_rows"] < tol), number=number, kernel_variant=op.vmult_variant(),
+             checker="oracle/gls_oracle.py (numpy restatement; parity unpinned against deal.II) on the small block, "
+                     "mapped to every dof of the big block by periodicity")
+    return r
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -323,6 +341,14 @@ def run_gpu(args):
     n_local, n_owned = mesh.n_dofs, mesh.n_owned
     n_global = mesh.n_global_dofs
     n_cells = mesh.n_cells
+    full_size = None
+    if world == 1 and args.workload == "P" and not args.no_extras and args.cells % 4 == 0 and args.cells >= 12:
+        # dof map of the every-cell parity check at the bench size (tests/full_size.py), built while the mesh exists
+        try:
+            from tests.full_size import PeriodicFullSizeCheck
+            full_size = PeriodicFullSizeCheck(mesh, dev, period_cells=4)
+        except Exception as e:
+            full_size = {"error": f"{type(e).__name__}: {e}"}
     del mesh
 
     g = torch.Generator(device=dev).manual_seed(SEED + rank)
@@ -452,6 +478,14 @@ def run_gpu(args):
         line["roofline"]["traffic_source"] = "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of " \
                                              "one ncu --set full capture of this kernel at this size, not measured in this run"
     headline = world == 1 and args.workload == "P" and args.number == "double"
+    if full_size is not None:
+        # every cell of THIS operator (the timed one, at the bench size) against the CPU oracle
+        try:
+            line["parity_full_size"] = full_size if isinstance(full_size, dict) else \
+                gpu_parity_full_size(full_size, op, dst, tdt, args.number)
+        except Exception as e:
+            line["parity_full_size"] = {"error": f"{type(e).__name__}: {e}"}
+        full_size = None
     if headline and not args.no_extras:
         # the reference's own protocol next to the random-vector one: zero vectors (performance.cc:66-79)
         try:
