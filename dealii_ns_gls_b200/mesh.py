@@ -19,7 +19,10 @@ range (= lowest touching rank, like deal.II).
 """
 from __future__ import annotations
 
+import ctypes
 from dataclasses import dataclass, field
+import os
+
 import numpy as np
 
 
@@ -48,6 +51,60 @@ def _morton_key(coords: np.ndarray) -> np.ndarray:
         for e in range(dim):
             key |= ((coords[:, e].astype(np.uint64) >> np.uint64(b)) & np.uint64(1)) << np.uint64(b * dim + e)
     return key
+
+
+# ---- native helpers (csrc/glsb_meshgen.c -> libglsb_meshgen.so) ---------------------------------------------
+# The numbering passes below are O(cells) array sweeps that numpy needs ~20 s for at the bench size; the C
+# versions give identical arrays in well under a second.  GLSB_MESHGEN_NUMPY=1 forces the numpy code (the tests
+# compare the two); without the library the numpy code is used as well -- this is the synthetic generator, not
+# the operator, whose library has no fallback.
+_meshgen = None
+
+
+def _native():
+    global _meshgen
+    if os.environ.get("GLSB_MESHGEN_NUMPY") == "1":
+        return None
+    if _meshgen is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libglsb_meshgen.so")
+        if not os.path.exists(path):
+            _meshgen = False
+        else:
+            lib = ctypes.CDLL(path)
+            P, I, L = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+            lib.glsm_number_nodes.restype = I
+            lib.glsm_number_nodes.argtypes = [I, P, I, P, I, P, P, P, P]
+            lib.glsm_assemble_cell_dofs.restype = I
+            lib.glsm_assemble_cell_dofs.argtypes = [L, I, I, P, P, L, I, P, P]
+            lib.glsm_general_geometry.restype = L
+            lib.glsm_general_geometry.argtypes = [I, L, I, I, P, P, P, P, P]
+            _meshgen = lib
+    return _meshgen or None
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _assemble_cell_dofs(cell_nodes, local_of_node, C, n_owned, index_dtype):
+    """cell_dofs[cell, c * n_loc + l] = local_of_node[cell_nodes[cell, l]] * C + c (components of a node
+    consecutive) in `index_dtype`, and the mask of cells touching an index >= n_owned (ghosts)."""
+    lib = _native()
+    ncell, n_loc = cell_nodes.shape
+    idt = np.dtype(index_dtype)
+    if lib is not None and idt in (np.dtype(np.uint32), np.dtype(np.int64)):
+        cn = np.ascontiguousarray(cell_nodes, dtype=np.int64)
+        lo = np.ascontiguousarray(local_of_node, dtype=np.int64)
+        out = np.empty((ncell, C * n_loc), dtype=idt)
+        bnd = np.empty(ncell, dtype=np.uint8)
+        rc = lib.glsm_assemble_cell_dofs(ncell, n_loc, C, _ptr(cn), _ptr(lo), int(n_owned), idt.itemsize, _ptr(out),
+                                         _ptr(bnd))
+        if rc != 0:
+            raise OverflowError("dof indices do not fit the index type")
+        return out, bnd.astype(bool)
+    ln = np.asarray(local_of_node)[cell_nodes]
+    cell_dofs = np.concatenate([ln * C + c for c in range(C)], axis=1)
+    return cell_dofs.astype(index_dtype), (cell_dofs >= n_owned).any(axis=1)
 
 
 @dataclass
@@ -102,31 +159,64 @@ class Mesh:
         return (self.degree + 1) ** self.dim
 
 
+def _det_small(J):
+    """determinants of a stack of 2 x 2 or 3 x 3 matrices [..., d, d] in closed form"""
+    if J.shape[-1] == 2:
+        return J[..., 0, 0] * J[..., 1, 1] - J[..., 0, 1] * J[..., 1, 0]
+    return (J[..., 0, 0] * (J[..., 1, 1] * J[..., 2, 2] - J[..., 1, 2] * J[..., 2, 1])
+            - J[..., 0, 1] * (J[..., 1, 0] * J[..., 2, 2] - J[..., 1, 2] * J[..., 2, 0])
+            + J[..., 0, 2] * (J[..., 1, 0] * J[..., 2, 1] - J[..., 1, 1] * J[..., 2, 0]))
+
+
 def _vertex_geometry(verts: np.ndarray, dim: int):
     """minimum_vertex_distance() and measure() from the 2^dim vertices."""
     nv = verts.shape[1]
-    h = np.full(verts.shape[0], np.inf)
+    h2 = np.full(verts.shape[0], np.inf)
     for a in range(nv):
         for b in range(a + 1, nv):
-            h = np.minimum(h, np.sqrt(((verts[:, a] - verts[:, b]) ** 2).sum(axis=1)))
+            d = verts[:, a] - verts[:, b]
+            h2 = np.minimum(h2, np.einsum("ki,ki->k", d, d))
+    h = np.sqrt(h2)
     # measure of the multilinear cell: 2-point Gauss per direction is exact
     g = np.array([0.5 - 0.5 / np.sqrt(3.0), 0.5 + 0.5 / np.sqrt(3.0)])
     meas = np.zeros(verts.shape[0])
+    vt = np.ascontiguousarray(verts.transpose(0, 2, 1))            # [cell, i, v]
     for qi in range(2 ** dim):
         xi = [g[(qi >> e) & 1] for e in range(dim)]
-        J = np.zeros((verts.shape[0], dim, dim))
+        dphi = np.ones((nv, dim))                                  # d phi_v / d xi_e at this point
         for v in range(2 ** dim):
             for e in range(dim):
-                dphi = 1.0
                 for f in range(dim):
                     bit = (v >> f) & 1
                     if f == e:
-                        dphi *= 1.0 if bit else -1.0
+                        dphi[v, e] *= 1.0 if bit else -1.0
                     else:
-                        dphi *= xi[f] if bit else 1.0 - xi[f]
-                J[:, :, e] += verts[:, v, :] * dphi
-        meas += np.linalg.det(J) / 2 ** dim
+                        dphi[v, e] *= xi[f] if bit else 1.0 - xi[f]
+        meas += _det_small(vt @ dphi) / 2 ** dim                   # J[cell, i, e]
     return h, meas
+
+
+def _grid_node_coordinates(npts, p, hcell, origin):
+    """[nnode, dim] reference coordinates of the grid nodes of a structured block (node ids lexicographic, x
+    fastest): node i of a direction lies in cell i // p at the Gauss-Lobatto point i % p."""
+    dim = len(npts)
+    gp = gauss_lobatto_points(p)
+    axes = []
+    for e in range(dim):
+        i = np.arange(npts[e])
+        axes.append(origin[e] + (i // p + gp[i % p]) * hcell[e])
+    grids = np.meshgrid(*axes[::-1], indexing="ij")               # slowest direction first
+    return np.stack([g.reshape(-1) for g in grids[::-1]], axis=1)
+
+
+def _zero_constraints_by_node(constraints, dirichlet, coords, local_of_node, C):
+    """constraints[dof] = [] for every (node, component) the mask callable selects; same rows, same insertion
+    order (by component, ascending dof) as the cell-wise evaluation, one evaluation per node instead of one per
+    cell-local node"""
+    for c in range(C):
+        mask = np.asarray(dirichlet(coords, c), dtype=bool)
+        dofs = np.sort(local_of_node[mask] * C + c)
+        constraints.update({d: [] for d in dofs.tolist()})
 
 
 def _number_nodes(dim, shape, p, periodic, order):
@@ -138,6 +228,22 @@ def _number_nodes(dim, shape, p, periodic, order):
     n = p + 1
     n_loc = n ** dim
     ncell = int(np.prod(shape))
+    lib = _native()
+    if lib is not None:
+        npts = tuple(p * shape[e] + (0 if periodic[e] else 1) for e in range(dim))
+        nnode = int(np.prod(npts))
+        cc = np.empty((ncell, dim), dtype=np.int64)
+        cell_nodes = np.empty((ncell, n_loc), dtype=np.int64)
+        node_rank = np.empty(nnode, dtype=np.int64)
+        first_cell = np.empty(nnode, dtype=np.int64)
+        shp = np.asarray(shape, dtype=np.int64)
+        per = np.asarray(periodic, dtype=np.uint8)
+        rc = lib.glsm_number_nodes(dim, _ptr(shp), p, _ptr(per), 1 if order == "morton" else 0, _ptr(cc),
+                                   _ptr(cell_nodes), _ptr(node_rank), _ptr(first_cell))
+        if rc != 0:
+            raise RuntimeError("glsm_number_nodes failed")
+        loc = np.stack(np.meshgrid(*[np.arange(n)] * dim, indexing="ij"), axis=-1).reshape(-1, dim)[:, ::-1].copy()
+        return cc, loc, cell_nodes, node_rank, first_cell, npts
     # ---- cell traversal order -------------------------------------------------
     cc = np.stack(np.meshgrid(*[np.arange(s) for s in shape], indexing="ij"), axis=-1).reshape(-1, dim)
     if order == "morton":
@@ -216,8 +322,9 @@ def structured_mesh(dim, shape, degree, *, deform=None, mapping_degree=1, period
 
     c0, c1 = bounds[rank], bounds[rank + 1]
     my_cells = slice(c0, c1)
-    my_nodes_g = node_rank[cell_nodes[my_cells]]  # global node ranks [ncell_loc, n_loc]
     ncell_loc = c1 - c0
+    fast = n_ranks == 1 and numbering == "node"   # one rank, components of a node consecutive: assembled in C
+    my_nodes_g = None if fast else node_rank[cell_nodes[my_cells]]  # global node ranks [ncell_loc, n_loc]
 
     if numbering == "node":
         def gdof(noderank, c):
@@ -230,13 +337,16 @@ def structured_mesh(dim, shape, degree, *, deform=None, mapping_degree=1, period
             cnt = owned_counts[own]
             return base * C + c * cnt + (noderank - base)
 
-    cell_gdofs = np.concatenate([gdof(my_nodes_g, c) for c in range(C)], axis=1)  # comp-blocked
-
     n_global_dofs = nnode * C
     owned_lo = owned_off_nodes[rank] * C
     owned_hi = owned_off_nodes[rank + 1] * C
     n_owned = int(owned_hi - owned_lo)
-    if n_ranks == 1:
+    is_boundary = None
+    cell_gdofs = None if fast else np.concatenate([gdof(my_nodes_g, c) for c in range(C)], axis=1)  # comp-blocked
+    if fast:
+        n_ghost = 0
+        local, is_boundary = _assemble_cell_dofs(cell_nodes, node_rank, C, n_owned, index_dtype)
+    elif n_ranks == 1:
         ghosts = np.zeros(0, dtype=np.int64)
         n_ghost = 0
         local = cell_gdofs
@@ -288,7 +398,7 @@ def structured_mesh(dim, shape, degree, *, deform=None, mapping_degree=1, period
         h_min, meas = _vertex_geometry(pts[:, verts_idx, :], dim)
 
     mesh = Mesh(dim=dim, degree=p, n_cells=ncell_loc, n_dofs=n_local, n_owned=n_owned,
-                cell_dofs=local.astype(index_dtype), geometry_type=0 if deform is None else 2,
+                cell_dofs=local.astype(index_dtype, copy=False), geometry_type=0 if deform is None else 2,
                 cell_points=pts, mapping_degree=k, constraints={}, cell_h_min=h_min,
                 cell_measure=meas, partition=part, node_compact=(numbering == "node"),
                 n_global_dofs=n_global_dofs, cell_coords=np.ascontiguousarray(cc[my_cells]), shape=shape,
@@ -296,10 +406,13 @@ def structured_mesh(dim, shape, degree, *, deform=None, mapping_degree=1, period
     if deform is None:
         mesh.cart_inv_jac = np.broadcast_to(1.0 / hcell, (ncell_loc, dim)).copy()
         mesh.cart_det = np.full(ncell_loc, float(np.prod(hcell)))
-    mesh.cell_is_boundary = (local >= n_owned).any(axis=1)
+    mesh.cell_is_boundary = (local >= n_owned).any(axis=1) if is_boundary is None else is_boundary
 
     # ---- zero (Dirichlet-type) constraints -------------------------------------
-    if dirichlet is not None:
+    if dirichlet is not None and fast:
+        _zero_constraints_by_node(mesh.constraints, dirichlet, _grid_node_coordinates(npts, p, hcell, origin),
+                                  node_rank, C)
+    elif dirichlet is not None:
         gp = gauss_lobatto_points(p)
         nref = origin[None, None, :] + (cc[my_cells][:, None, :] + gp[loc][None, :, :]) * hcell[None, None, :]
         for c in range(C):
@@ -397,8 +510,7 @@ def hypercube_slab(n_per_dir, degree, *, n_ranks=1, rank=0, dim=3, order="morton
     ghost_nodes = np.nonzero(is_ghost_node)[0]    # lexicographic in the plane = canonical order
     local_of_node[ghost_nodes] = n_owned_nodes + np.arange(len(ghost_nodes))
     n_owned, n_ghost = n_owned_nodes * C, len(ghost_nodes) * C
-    ln = local_of_node[cell_nodes]
-    cell_dofs = np.concatenate([ln * C + c for c in range(C)], axis=1)
+    cell_dofs, is_boundary = _assemble_cell_dofs(cell_nodes, local_of_node, C, n_owned, index_dtype)
 
     # rank 0 owns all its node planes, every other rank all but its bottom plane
     first_owned = 0 if rank == 0 else C * plane * (p * n_per_dir * rank + 1)
@@ -416,12 +528,12 @@ def hypercube_slab(n_per_dir, degree, *, n_ranks=1, rank=0, dim=3, order="morton
     hcell = 1.0 / n_per_dir
     nodes_last = p * n_per_dir * n_ranks + 1
     mesh = Mesh(dim=dim, degree=p, n_cells=ncell, n_dofs=n_owned + n_ghost, n_owned=n_owned,
-                cell_dofs=cell_dofs.astype(index_dtype), geometry_type=0, cell_points=None, mapping_degree=1,
+                cell_dofs=cell_dofs, geometry_type=0, cell_points=None, mapping_degree=1,
                 constraints={}, cell_h_min=np.full(ncell, hcell), cell_measure=np.full(ncell, hcell ** dim),
                 partition=part, node_compact=True, n_global_dofs=plane * nodes_last * C)
     mesh.cart_inv_jac = np.full((ncell, dim), 1.0 / hcell)
     mesh.cart_det = np.full(ncell, hcell ** dim)
-    mesh.cell_is_boundary = (cell_dofs >= n_owned).any(axis=1)
+    mesh.cell_is_boundary = is_boundary
     # canonical global id of every local dof (tests use it to compare against a 1-rank run)
     gz = k_of + rank * p * n_per_dir
     gnode = (node_ids % plane) + plane * gz
@@ -499,7 +611,7 @@ def structured_box(shape, degree, *, grid, box_of, rank, periodic=None, deform=N
     ghost_nodes, owner_rank = ghost_nodes[gorder], owner_rank[gorder]
     local_of_node[ghost_nodes] = n_owned_nodes + np.arange(len(ghost_nodes))
     n_owned, n_ghost = n_owned_nodes * C, len(ghost_nodes) * C
-    cell_dofs = np.concatenate([local_of_node[cell_nodes] * C + c for c in range(C)], axis=1)
+    cell_dofs, is_boundary = _assemble_cell_dofs(cell_nodes, local_of_node, C, n_owned, index_dtype)
 
     def owned_count(bb):
         return int(np.prod([p * shape[e] + (1 if (bb[e] == 0 and not periodic[e]) else 0) for e in range(dim)])) * C
@@ -541,13 +653,13 @@ def structured_box(shape, degree, *, grid, box_of, rank, periodic=None, deform=N
         verts_idx = [sum((k * ((v >> e) & 1)) * (k + 1) ** e for e in range(dim)) for v in range(2 ** dim)]
         h_min, meas = _vertex_geometry(pts[:, verts_idx, :], dim)
     mesh = Mesh(dim=dim, degree=p, n_cells=ncell, n_dofs=n_owned + n_ghost, n_owned=n_owned,
-                cell_dofs=cell_dofs.astype(index_dtype), geometry_type=0 if deform is None else 2, cell_points=pts,
+                cell_dofs=cell_dofs, geometry_type=0 if deform is None else 2, cell_points=pts,
                 mapping_degree=k, constraints={}, cell_h_min=h_min, cell_measure=meas,
                 partition=part, node_compact=True, n_global_dofs=int(np.prod(gn)) * C)
     if deform is None:
         mesh.cart_inv_jac = np.broadcast_to(1.0 / hcell, (ncell, dim)).copy()
         mesh.cart_det = np.full(ncell, float(np.prod(hcell)))
-    mesh.cell_is_boundary = (cell_dofs >= n_owned).any(axis=1)
+    mesh.cell_is_boundary = is_boundary
     gijk = ijk + (b * p * np.asarray(shape))[None, :]
     gnode = np.zeros(nnode, dtype=np.int64)
     mul = 1
@@ -561,14 +673,8 @@ def structured_box(shape, degree, *, grid, box_of, rank, periodic=None, deform=N
     mesh.shape, mesh.cell_coords = shape, np.ascontiguousarray(cc)
     mesh.extent, mesh.origin = box_extent, origin
     if dirichlet is not None:
-        gp = gauss_lobatto_points(p)
-        n_loc = n ** dim
-        nref = origin[None, None, :] + (cc[:, None, :] + gp[loc][None, :, :]) * hcell[None, None, :]
-        for c in range(C):
-            mask = dirichlet(nref.reshape(-1, dim), c).reshape(ncell, n_loc)
-            dofs = cell_dofs[:, c * n_loc:(c + 1) * n_loc][mask]
-            for dof in np.unique(dofs):
-                mesh.constraints[int(dof)] = []
+        _zero_constraints_by_node(mesh.constraints, dirichlet, _grid_node_coordinates(npts, p, hcell, origin),
+                                  local_of_node, C)
     return mesh
 
 
@@ -799,17 +905,32 @@ def general_geometry(mesh: Mesh, n_q_1d: int | None = None):
         return V, D
 
     V, D = lag(xg)
-    J = np.zeros((mesh.n_cells, nq ** dim, dim, dim))
+    Ts = []
     for e in range(dim):
         mats = [V] * dim
         mats[e] = D
         T = mats[0]
         for mtx in mats[1:]:
             T = np.kron(mtx, T)
-        J[:, :, :, e] = np.einsum("qm,kmi->kqi", T, mesh.cell_points)
+        Ts.append(T)
     w = wg
     for _ in range(dim - 1):
         w = np.kron(wg, w)
+    lib = _native()
+    if lib is not None:
+        T = np.ascontiguousarray(np.stack(Ts), dtype=np.float64)
+        pts = np.ascontiguousarray(mesh.cell_points, dtype=np.float64)
+        inv_jac = np.empty((mesh.n_cells, nq ** dim, dim, dim))
+        jxw = np.empty((mesh.n_cells, nq ** dim))
+        wq = np.ascontiguousarray(w, dtype=np.float64)
+        rc = lib.glsm_general_geometry(dim, mesh.n_cells, nq ** dim, pts.shape[1], _ptr(T), _ptr(wq), _ptr(pts),
+                                       _ptr(inv_jac), _ptr(jxw))
+        if rc < 0:
+            raise RuntimeError("glsm_general_geometry failed")
+        return inv_jac, jxw
+    J = np.zeros((mesh.n_cells, nq ** dim, dim, dim))
+    for e in range(dim):
+        J[:, :, :, e] = np.einsum("qm,kmi->kqi", Ts[e], mesh.cell_points)
     return np.linalg.inv(J), np.linalg.det(J) * w[None, :]
 
 

@@ -84,7 +84,7 @@ def build_desc(mesh: Mesh, *, number, nu, c_1, c_2, theta, time_order, consider_
     keep = {}
     C_ = mesh.dim + 1
     ndof = C_ * mesh.n_loc
-    idx = np.ascontiguousarray(mesh.cell_dofs, dtype=np.uint32).copy()
+    idx = np.ascontiguousarray(mesh.cell_dofs, dtype=np.uint32)  # never written in place below
     assert idx.shape == (mesh.n_cells, ndof)
 
     # constraint rows
