@@ -175,16 +175,15 @@ def channel_inhomogeneous_constraints(params: ChannelParameters, mesh: Mesh) -> 
     outflow pressure, plus u = (1, 0, 0) on the inflow face where no wall constraint exists yet
     (InflowBoundaryValues::Channel(0, 1), simulation.cc:176-177)."""
     dim = params.dim
-    x, comp = dof_coordinates(mesh), dof_components(mesh)
+    cdofs = np.fromiter(mesh.constraints.keys(), dtype=np.int64, count=len(mesh.constraints))
+    x, comp = dof_coordinates(mesh, only=cdofs), dof_components(mesh, only=cdofs)
     eps = 1e-12
-    wall = np.zeros(mesh.n_dofs, dtype=bool)
+    wall = np.zeros(len(cdofs), dtype=bool)
     for e in range(1, dim):
         wall |= (np.abs(x[:, e]) < eps) | (np.abs(x[:, e] - 1.0) < eps)
-    rows, inhom = {}, {}
-    for d in mesh.constraints:
-        rows[d] = []
-        if comp[d] == 0 and abs(x[d, 0]) < eps and not wall[d]:
-            inhom[d] = 1.0
+    inflow = (comp == 0) & (np.abs(x[:, 0]) < eps) & ~wall
+    rows = {d: [] for d in mesh.constraints}
+    inhom = {int(d): 1.0 for d in cdofs[inflow]}
     return AffineConstraints(rows, inhom)
 
 

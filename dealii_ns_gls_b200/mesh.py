@@ -423,14 +423,30 @@ def structured_mesh(dim, shape, degree, *, deform=None, mapping_degree=1, period
     return mesh
 
 
-def dof_coordinates(mesh: Mesh) -> np.ndarray:
+def _cells_touching(mesh: Mesh, only):
+    """(cells, local node, component) triples of the entries of cell_dofs that hold one of the dofs `only`, and
+    the position of each in `only`"""
+    pos = np.full(mesh.n_dofs, -1, dtype=np.int64)
+    pos[np.asarray(only, dtype=np.int64)] = np.arange(len(only))
+    hit = pos[mesh.cell_dofs]                       # [n_cells, C * n_loc]
+    cell, col = np.nonzero(hit >= 0)
+    return cell, col % mesh.n_loc, col // mesh.n_loc, hit[cell, col]
+
+
+def dof_coordinates(mesh: Mesh, only=None) -> np.ndarray:
     """[n_dofs, dim] coordinates of the support point of every local dof of an undeformed structured block
-    (what DoFTools::map_dofs_to_support_points gives; used for boundary values)."""
+    (what DoFTools::map_dofs_to_support_points gives; used for boundary values).  only = array of dofs: the
+    coordinates of just those, [len(only), dim]."""
     dim, p = mesh.dim, mesh.degree
     n = p + 1
     gp = gauss_lobatto_points(p)
     loc = np.stack(np.meshgrid(*[np.arange(n)] * dim, indexing="ij"), axis=-1).reshape(-1, dim)[:, ::-1]
     hcell = mesh.extent / np.asarray(mesh.shape, dtype=np.float64)
+    if only is not None:
+        cell, l, _, where = _cells_touching(mesh, only)
+        out = np.zeros((len(only), dim))
+        out[where] = mesh.origin[None, :] + (mesh.cell_coords[cell] + gp[loc][l]) * hcell[None, :]
+        return out
     x = mesh.origin[None, None, :] + (mesh.cell_coords[:, None, :] + gp[loc][None, :, :]) * hcell[None, None, :]
     out = np.zeros((mesh.n_dofs, dim))
     for c in range(dim + 1):
@@ -451,8 +467,13 @@ def cell_diameters(mesh: Mesh) -> np.ndarray:
     return d
 
 
-def dof_components(mesh: Mesh) -> np.ndarray:
-    """[n_dofs] component (0..dim) of every local dof."""
+def dof_components(mesh: Mesh, only=None) -> np.ndarray:
+    """[n_dofs] component (0..dim) of every local dof (only = array of dofs: of just those)."""
+    if only is not None:
+        _, _, comp, where = _cells_touching(mesh, only)
+        out = np.zeros(len(only), dtype=np.int64)
+        out[where] = comp
+        return out
     out = np.zeros(mesh.n_dofs, dtype=np.int64)
     for c in range(mesh.dim + 1):
         out[mesh.cell_dofs[:, c * mesh.n_loc:(c + 1) * mesh.n_loc].astype(np.int64).reshape(-1)] = c
