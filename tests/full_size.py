@@ -68,10 +68,12 @@ class PeriodicFullSizeCheck:
         lut_d = torch.from_numpy(lut).to(self.device)
         cc = torch.from_numpy(np.ascontiguousarray(big.cell_coords).astype(np.int32)).to(self.device).long()
         key = torch.full((big.n_dofs,), -1, dtype=torch.int32, device=self.device)
+        assert big.n_dofs < 2 ** 31
+        cd = np.ascontiguousarray(big.cell_dofs)
+        cd = torch.from_numpy(cd.view(np.int32) if cd.dtype == np.uint32 else cd).to(self.device)  # one upload
         for c in range(C):
             for l in range(n_loc):
-                col = np.ascontiguousarray(big.cell_dofs[:, c * n_loc + l]).astype(np.int64)
-                idx = torch.from_numpy(col).to(self.device)
+                idx = cd[:, c * n_loc + l].long()
                 mapped = []
                 for e in range(dim):
                     i = p * cc[:, e] + int(loc[l][e])
@@ -80,6 +82,7 @@ class PeriodicFullSizeCheck:
                     m = torch.where(i == p * N[e], torch.full_like(m, p * M), m)
                     mapped.append(m)
                 key[idx] = lut_d[(c,) + tuple(mapped)].to(torch.int32)
+        del cd
         assert int(key.min()) >= 0
         self.key = key.long()
         self.rng = np.random.default_rng(seed)
