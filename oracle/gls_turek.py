@@ -248,3 +248,90 @@ if __name__ == "__main__":
         lit = LITERATURE[k.split("_consistent")[0]]
         print(f"{k:16s} {r[k]: .8f}   literature {lit: .8f}   rel. dev. {r[k] / lit - 1: .2e}")
     print(r["n_cells"], "cells,", r["n_dofs"], "dofs,", len(r["newton_residuals"]) - 1, "Newton steps")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# DFG benchmark 2D-2 (periodic vortex shedding at Re = 100): the time-dependent terms
+# ---------------------------------------------------------------------------------------------------------
+LITERATURE_2D2 = {"drag_max": (3.22, 3.24), "lift_max": (0.99, 1.01), "strouhal": (0.295, 0.305)}
+
+
+class UnsteadyTurek:
+    """input/input_turek_2D_Re100.json on this file's mesh: u_max = 1.5 (mean velocity 1, Re = 100), BDF2
+    (include/time_integration.cc:61-91 through gls_oracle.OracleBDF), time-derivative terms in the Galerkin and in
+    the stabilisation part, q-point-wise delta with the 1/dt^2 term, inflow ramp over t_init = 0.01
+    (simulation.cc:46-49).  The time loop is main.cc:908-990; the nonlinear solve is Newton on the residual branch
+    with a matrix assembled from the Newton branch that is kept for a few iterations / steps (the converged
+    iterate does not depend on how fresh the matrix is; solver_nl.cc:36-89 with newton inexact)."""
+
+    def __init__(self, level=2, dt=1.0 / 300.0, u_max=1.5, t_init=0.01, nu=NU, refresh=4):
+        self.mesh = TurekMesh(level)
+        m = self.mesh
+        self.dt, self.u_max, self.t_init, self.nu, self.refresh = dt, u_max, t_init, nu, refresh
+        self.op = go.OracleOperator(dim=2, degree=2, cell_dofs=m.cell_dofs, n_dofs=m.n_dofs,
+                                    cell_points=m.cell_points, mapping_degree=2, constraints=m.constraints, nu=nu,
+                                    c1=2.0, c2=1.0, theta=1.0, order=2, consider_time_derivative=True,
+                                    increment_form=True, cell_wise_stabilization=False, path="sumfac")
+        self.bdf = go.OracleBDF(2)
+        self.history = [np.zeros(m.n_dofs) for _ in range(3)]
+        self.t, self.n_steps, self._lu, self._age = 0.0, 0, None, 0
+        self.profile = {d: v / U_MAX for d, v in m.inhomogeneities.items()}   # parabola with peak 1
+        self.records = []
+
+    def _distribute(self, x, t):
+        f = self.u_max * min(t / self.t_init, 1.0) if self.t_init > 0 else self.u_max
+        for d, v in self.profile.items():
+            x[d] = f * v
+
+    def step(self):
+        op, w_old = self.op, None
+        self.bdf.update_dt(self.dt)
+        w = self.bdf.weights
+        self.history[2], self.history[1] = self.history[1], self.history[0].copy()
+        x = self.history[0]
+        self._distribute(x, self.t)        # main.cc:926-942: boundary values at the old time level t
+        op.set_previous_solution(self.history, w)
+        if self._lu is not None and (self._w0 != w[0]):
+            self._lu = None
+        n_it = 0
+        while True:
+            op.set_linearization_point(x, self.dt)
+            rhs = op.evaluate_residual(x, w[0])
+            res = float(np.linalg.norm(rhs))
+            if res < 1e-7:
+                break
+            if self._lu is None or self._age >= self.refresh or n_it >= 6:
+                self._lu, self._age, self._w0 = spla.splu(system_matrix(op, w[0])), 0, w[0]
+            inc = self._lu.solve(rhs)
+            inc[op.constrained] = 0.0
+            x += inc
+            n_it += 1
+            if n_it > 40:
+                raise RuntimeError(f"Newton iteration did not converge at t = {self.t}: {res}")
+        self._age += 1
+        self.t += self.dt
+        self.n_steps += 1
+        f = drag_lift_pressure(self.mesh, x, self.nu)
+        u_bar = self.u_max * 2.0 / 3.0
+        rescale = (U_MAX * 2.0 / 3.0) ** 2 / u_bar ** 2      # drag_lift_pressure scales with the 2D-1 mean velocity
+        rec = {"t": self.t, "drag": float(f["drag"] * rescale), "lift": float(f["lift"] * rescale),
+               "p_diff": float(f["p_diff"]), "newton_iterations": n_it}
+        self.records.append(rec)
+        return rec
+
+
+def shedding_statistics(records, t_from):
+    """maxima of drag and lift and the Strouhal number (D / (u_mean T), u_mean = 1) from the upward zero crossings
+    of the lift's oscillating part after t_from"""
+    t = np.array([r["t"] for r in records])
+    cl = np.array([r["lift"] for r in records])
+    cd = np.array([r["drag"] for r in records])
+    sel = t >= t_from
+    t, cl, cd = t[sel], cl[sel], cd[sel]
+    osc = cl - 0.5 * (cl.max() + cl.min())
+    up = np.nonzero((osc[:-1] < 0) & (osc[1:] >= 0))[0]
+    tc = t[up] - osc[up] * (t[up + 1] - t[up]) / (osc[up + 1] - osc[up])
+    period = float(np.mean(np.diff(tc))) if len(tc) > 1 else float("nan")
+    return {"drag_max": float(cd.max()), "drag_min": float(cd.min()), "lift_max": float(cl.max()),
+            "lift_min": float(cl.min()), "period": period, "strouhal": 2.0 * R_CYL / period,
+            "n_periods": int(len(tc) - 1)}
