@@ -162,16 +162,20 @@ static inline __attribute__((always_inline)) void sweep(const int dim, const int
 
 static inline __attribute__((always_inline)) void cell_batch(const glso_t *o, const int dim, const int n, int64_t b,
                                                             const double *src, vd *res /* [C*n_loc] */,
-                                                            const double weight)
+                                                            const double weight,
+                                                            const vd *local_in /* [C*n_loc] or NULL: gather from src */)
 {
   const int C = dim + 1, n_loc = dim == 2 ? n * n : n * n * n, nq = n_loc;
   vd        val[4][MAXLOC], tmp[MAXLOC], rg[4][3][MAXLOC];
   const uint32_t *ix = o->idx + b * C * n_loc * LANES;
   for (int c = 0; c < C; ++c)
     {
-      for (int i = 0; i < n_loc; ++i)
-        for (int l = 0; l < LANES; ++l)
-          val[c][i][l] = src[ix[(c * n_loc + i) * LANES + l]];
+      if (local_in)
+        memcpy(val[c], local_in + c * n_loc, sizeof(vd) * n_loc);
+      else
+        for (int i = 0; i < n_loc; ++i)
+          for (int l = 0; l < LANES; ++l)
+            val[c][i][l] = src[ix[(c * n_loc + i) * LANES + l]];
       /* evaluate: interpolate to q points, then collocation derivatives */
       for (int e = 0; e < dim; ++e)
         {
@@ -356,11 +360,12 @@ static inline __attribute__((always_inline)) void cell_batch(const glso_t *o, co
 #define DISPATCH(DIM, N)                       \
   if (o->dim == DIM && o->n == N)              \
     {                                          \
-      cell_batch(o, DIM, N, b, src, res, weight); \
+      cell_batch(o, DIM, N, b, src, res, weight, local_in); \
       return;                                  \
     }
 
-static void cell_batch_dispatch(const glso_t *o, int64_t b, const double *src, vd *res, double weight)
+static void cell_batch_dispatch(const glso_t *o, int64_t b, const double *src, vd *res, double weight,
+                                const vd *local_in)
 {
   DISPATCH(3, 3)
   DISPATCH(3, 2)
@@ -435,7 +440,7 @@ void glso_apply(glso_t *o, double *dst, const double *src, double weight, int ze
     int64_t b0 = o->n_batches * t / n_threads, b1 = o->n_batches * (t + 1) / n_threads;
     for (int64_t b = b0; b < b1; ++b)
       {
-        cell_batch_dispatch(o, b, src, res, weight);
+        cell_batch_dispatch(o, b, src, res, weight, NULL);
         const uint32_t *ix    = o->idx + b * ndof * LANES;
         const int       lanes = (b == o->n_batches - 1) ? (int)(o->n_cells - b * LANES) : LANES;
         for (int j = 0; j < ndof; ++j)
@@ -449,6 +454,65 @@ void glso_apply(glso_t *o, double *dst, const double *src, double weight, int ze
                 }
               else
                 dst[d] += res[j][l];
+            }
+      }
+  }
+}
+
+/* diag += sum_cells scatter(diag(A_cell)): the cell operator applied to each of the C * n^dim local unit vectors,
+ * the way MatrixFreeTools::compute_diagonal does it for the reference (operator_ns.cc:210-218).  Plain scatter:
+ * the caller sets the constrained rows to 1 (zero-type constraints only) and inverts (operator_ns.cc:219-224). */
+void glso_diagonal(glso_t *o, double *diag, double weight, int zero_dst, int n_threads)
+{
+  const int ndof = o->C * o->n_loc;
+#ifdef _OPENMP
+  if (n_threads <= 0)
+    n_threads = omp_get_max_threads();
+#else
+  n_threads = 1;
+#endif
+  if (o->n_threads_prepared != n_threads)
+    prepare_shared(o, n_threads);
+#pragma omp parallel num_threads(n_threads)
+  {
+#ifdef _OPENMP
+    const int t = omp_get_thread_num();
+#else
+    const int t = 0;
+#endif
+    if (zero_dst)
+      {
+        int64_t i0 = o->n_dofs * t / n_threads, i1 = o->n_dofs * (t + 1) / n_threads;
+        memset(diag + i0, 0, sizeof(double) * (i1 - i0));
+      }
+#pragma omp barrier
+    vd      res[4 * MAXLOC], unit[4 * MAXLOC], dl[4 * MAXLOC];
+    int64_t b0 = o->n_batches * t / n_threads, b1 = o->n_batches * (t + 1) / n_threads;
+    memset(unit, 0, sizeof(vd) * ndof);
+    for (int64_t b = b0; b < b1; ++b)
+      {
+        for (int j = 0; j < ndof; ++j)
+          {
+            for (int l = 0; l < LANES; ++l)
+              unit[j][l] = 1.0;
+            cell_batch_dispatch(o, b, NULL, res, weight, unit);
+            dl[j] = res[j];
+            for (int l = 0; l < LANES; ++l)
+              unit[j][l] = 0.0;
+          }
+        const uint32_t *ix    = o->idx + b * ndof * LANES;
+        const int       lanes = (b == o->n_batches - 1) ? (int)(o->n_cells - b * LANES) : LANES;
+        for (int j = 0; j < ndof; ++j)
+          for (int l = 0; l < lanes; ++l)
+            {
+              const uint32_t d = ix[j * LANES + l];
+              if (o->shared[d])
+                {
+#pragma omp atomic
+                  diag[d] += dl[j][l];
+                }
+              else
+                diag[d] += dl[j][l];
             }
       }
   }

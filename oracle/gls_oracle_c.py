@@ -39,6 +39,8 @@ def load():
         lib.glso_destroy.argtypes = [P]
         lib.glso_apply.restype = None
         lib.glso_apply.argtypes = [P, P, P, D, I, I]
+        lib.glso_diagonal.restype = None
+        lib.glso_diagonal.argtypes = [P, P, D, I, I]
         lib.glso_max_threads.restype = I
         lib.glso_max_threads.argtypes = []
         _lib = lib
@@ -87,6 +89,12 @@ class COracle:
 
     def apply_into(self, dst, src, weight, n_threads=0):
         self.lib.glso_apply(self.h, _p(dst), _p(src), float(weight), 1, int(n_threads))
+
+    def diagonal(self, weight, n_threads=0):
+        """sum over the cells of the diagonal of the cell matrix (unit-vector applications, plain scatter)"""
+        diag = np.empty(self.n_dofs, dtype=np.float64)
+        self.lib.glso_diagonal(self.h, _p(diag), float(weight), 1, int(n_threads))
+        return diag
 
     def __del__(self):
         if getattr(self, "h", None):

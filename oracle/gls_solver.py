@@ -91,18 +91,26 @@ def interpolation_matrix(dim, degree, fine_cell_dofs, coarse_cell_dofs, children
     nodes = go.gauss_lobatto_points(degree)
     child_1d = (nodes > 0.5).astype(int)
     R1 = np.stack([go.lagrange_tables(nodes, np.array([2 * nodes[j] - child_1d[j]]))[0][0] for j in range(n)])
-    R = sp.lil_matrix((n_coarse, n_fine))
     fine_cell_dofs = np.asarray(fine_cell_dofs, dtype=np.int64)
     coarse_cell_dofs = np.asarray(coarse_cell_dofs, dtype=np.int64)
+    rows, cols, vals = [], [], []
     for j in range(n_loc):
         jj = [(j // n ** e) % n for e in range(dim)]
         ch = sum(child_1d[jj[e]] << e for e in range(dim))
         row = _kron_lex([R1[jj[e]][None, :] for e in range(dim)])[0]
         nz = np.nonzero(np.abs(row) > 1e-15)[0]
         for c in range(C):
-            for k in range(coarse_cell_dofs.shape[0]):
-                R[coarse_cell_dofs[k, c * n_loc + j], fine_cell_dofs[children[k, ch], c * n_loc + nz]] = row[nz]
-    return R.tocsr()
+            r = coarse_cell_dofs[:, c * n_loc + j]
+            f = fine_cell_dofs[children[:, ch]][:, c * n_loc + nz]          # [n_coarse_cells, len(nz)]
+            rows.append(np.repeat(r, len(nz)))
+            cols.append(f.reshape(-1))
+            vals.append(np.tile(row[nz], len(r)))
+    rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+    # a coarse dof shared by several cells gets the same row from each of them: keep one copy (an assignment,
+    # not a sum)
+    key = rows * np.int64(n_fine) + cols
+    _, first = np.unique(key, return_index=True)
+    return sp.csr_matrix((vals[first], (rows[first], cols[first])), shape=(n_coarse, n_fine))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -212,14 +220,17 @@ class OracleChannelDriver:
 
     def __init__(self, *, dim, degree, meshes, children, constraints_inhomogeneous, inhomogeneities, min_dx,
                  nu, c1, c2, cfl, bdf_order, consider_time_derivative=True, cell_wise_stabilization=True,
-                 rel_tol=1e-2, abs_tol=1e-12, newton_inexact=False, level_dtype=np.float64):
+                 rel_tol=1e-2, abs_tol=1e-12, newton_inexact=False, level_dtype=np.float64,
+                 operator_class=go.OracleOperator):
+        """operator_class: gls_oracle.OracleOperator (numpy cell loops, the checker of the tests) or
+        gls_fast.FastOracleOperator (the same operator with its cell loops in C: the timed CPU baseline)"""
         self.dim, self.cfl, self.min_dx = dim, cfl, min_dx
         self.lo, self.hi = min(meshes), max(meshes)
         self.bdf = go.OracleBDF(bdf_order) if bdf_order > 0 else _TimeNone()
         self.rel_tol, self.abs_tol, self.inexact = rel_tol, abs_tol, newton_inexact
 
         def make(mesh, dtype):
-            return go.OracleOperator(dim=dim, degree=degree, cell_dofs=mesh.cell_dofs, n_dofs=mesh.n_dofs,
+            return operator_class(dim=dim, degree=degree, cell_dofs=mesh.cell_dofs, n_dofs=mesh.n_dofs,
                                      cell_points=mesh.cell_points, mapping_degree=mesh.mapping_degree,
                                      constraints=mesh.constraints, nu=nu, c1=c1, c2=c2, theta=1.0, order=bdf_order,
                                      consider_time_derivative=consider_time_derivative, increment_form=True,

@@ -31,8 +31,10 @@ if __name__ == "__main__":
     tail = [r for r in sim.records if r["t"] >= t_final - 1.5]
     out = {"literature": gt.LITERATURE_2D2, "level": level, "dt": sim.dt, "t_final": sim.t, "n_steps": sim.n_steps,
            "n_cells": int(sim.mesh.n_cells), "n_dofs": int(sim.mesh.n_dofs), "statistics": stats, "tail": tail}
-    with open(os.path.join(ROOT, "tests", "golden", "turek_2d2.json"), "w") as f:
-        json.dump(out, f, indent=1)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "turek_2d2_state.npz"),
                         history=np.stack(sim.history).astype(np.float64), t=sim.t, dt=sim.dt,
                         bdf_dt=np.array(sim.bdf.dt, dtype=np.float64))
+    # three more steps from the saved state: what the test re-computes
+    out["continuation"] = [sim.step() for _ in range(3)]
+    with open(os.path.join(ROOT, "tests", "golden", "turek_2d2.json"), "w") as f:
+        json.dump(out, f, indent=1)

@@ -73,3 +73,52 @@ def test_a_wrong_viscous_factor_would_be_seen():
     x, _ = gt.solve_stationary(mesh, nu=0.5 * gt.NU)
     d = gt.drag_lift_pressure(mesh, x, nu=0.5 * gt.NU)["drag"]
     assert abs(d / gt.LITERATURE["drag"] - 1.0) > 0.1
+
+
+# ---- DFG benchmark 2D-2: periodic vortex shedding at Re = 100 (input/input_turek_2D_Re100.json) -----------------
+@pytest.fixture(scope="module")
+def golden_unsteady():
+    with open(os.path.join(HERE, "golden", "turek_2d2.json")) as f:
+        return json.load(f)
+
+
+def test_unsteady_record_against_published_intervals(golden_unsteady):
+    """BDF2, time-derivative terms in the Galerkin and the stabilisation part, 1 / dt^2 in delta_1: the recorded run
+    (840 Q2 cells, dt = 1 / 300, t = 9) sheds vortices at the published frequency, and the force maxima are
+    within a coarse-mesh margin of the published intervals c_D,max in [3.22, 3.24], c_L,max in [0.99, 1.01],
+    St in [0.295, 0.305] (Schaefer & Turek 1996)."""
+    s, lit = golden_unsteady["statistics"], golden_unsteady["literature"]
+    assert s["n_periods"] >= 4
+    assert lit["strouhal"][0] <= s["strouhal"] <= lit["strouhal"][1]
+    assert abs(s["drag_max"] / 3.23 - 1.0) < 0.025
+    assert abs(s["lift_max"] / 1.0 - 1.0) < 0.05
+    # the recorded cycle is periodic: statistics of its first and second half agree
+    tail = golden_unsteady["tail"]
+    half = len(tail) // 2
+    a = gt.shedding_statistics(tail[:half], 0.0)
+    b = gt.shedding_statistics(tail[half:], 0.0)
+    assert abs(a["lift_max"] - b["lift_max"]) < 5e-3 and abs(a["drag_max"] - b["drag_max"]) < 5e-3
+    assert abs(a["period"] - b["period"]) < 2e-3
+
+
+def test_unsteady_run_continues_from_the_recorded_state(golden_unsteady):
+    """three BDF2 steps from the stored history vectors give the recorded forces (the oracle has not moved)"""
+    st = np.load(os.path.join(HERE, "golden", "turek_2d2_state.npz"))
+    sim = gt.UnsteadyTurek(level=golden_unsteady["level"], dt=float(st["dt"]))
+    assert sim.mesh.n_dofs == golden_unsteady["n_dofs"] == st["history"].shape[1]
+    sim.history = [h.copy() for h in st["history"]]
+    sim.t = float(st["t"])
+    sim.bdf.update_dt(float(st["bdf_dt"][1]))
+    for ref in golden_unsteady["continuation"]:
+        r = sim.step()
+        assert r["t"] == pytest.approx(ref["t"])
+        for k in ("drag", "lift", "p_diff"):
+            assert r[k] == pytest.approx(ref[k], rel=1e-5), k
+
+
+def test_strouhal_number_of_a_synthetic_signal():
+    t = np.arange(0.0, 3.0, 1.0 / 300.0)
+    rec = [{"t": float(x), "lift": float(0.1 + np.sin(2 * np.pi * 3.0 * x)), "drag": float(3.2 + 0.03 * np.sin(4 * np.pi * 3.0 * x))}
+           for x in t]
+    s = gt.shedding_statistics(rec, 1.0)
+    assert s["strouhal"] == pytest.approx(0.3, rel=1e-4) and s["lift_max"] == pytest.approx(1.1, abs=1e-3)
