@@ -529,8 +529,15 @@ def run_gpu(args):
     if world == 1 and args.workload == "P" and args.time_step_refinements >= 0:
         try:
             line["time_step"] = time_step_wall(args.time_step_refinements, dev)
+            line["time_step"]["dofs_per_s"] = line["time_step"]["n_dofs"] / line["time_step"]["wall_s_per_step"]
         except Exception as e:  # the vmult line above stays valid on its own
             line["time_step"] = {"error": f"{type(e).__name__}: {e}"}
+        if not args.no_cpu_baseline and "error" not in line["time_step"]:
+            try:
+                line["time_step"]["cpu_baseline"] = time_step_cpu(min(args.time_step_cpu_refinements,
+                                                                      args.time_step_refinements))
+            except Exception as e:
+                line["time_step"]["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -634,6 +641,58 @@ def time_step_wall(refinements, dev, n_steps=4, n_ranks=1, rank=0):
                         "level operators f32"}
 
 
+def time_step_cpu(refinements, n_steps=1, budget_s=20.0):
+    """`time_step.cpu_baseline`: the same time loop (same channel, same flags, same hierarchy with mg_min_level = 1,
+    float level vectors) on the host cores -- the CPU restatement of the solver stack (oracle/gls_solver.py: Newton,
+    GMRES(28), V-cycle with 5-sweep relaxation smoothers and their 20-step power iteration, unit-vector diagonals,
+    dense coarse solve) with every cell loop in the C restatement (oracle/gls_fast.py, all host threads) -- on a
+    bounded sample: a coarser refinement of the mesh the device runs.  Two untimed steps, then up to n_steps timed
+    steps inside budget_s.  `cell_loops_in_c_s` is the part of a step spent inside the C loops; the rest is numpy /
+    scipy glue (table evaluation, transfers as sparse matrices) that a compiled CPU code would not pay."""
+    from dealii_ns_gls_b200 import mesh as gm
+    from dealii_ns_gls_b200.driver import ChannelParameters
+    from oracle import gls_solver as gs
+    from oracle.gls_fast import FastOracleOperator
+    from oracle.gls_oracle_c import max_threads
+
+    p = ChannelParameters(dim=3, fe_degree=2, n_global_refinements=refinements, mg_min_level=1)
+    n_levels = p.n_levels()
+    meshes = {l: p.level_mesh(l) for l in range(p.mg_min_level, n_levels + 1)}
+    children = {l: gm.child_cells(meshes[l - 1], meshes[l]) for l in range(p.mg_min_level + 1, n_levels + 1)}
+    fine = meshes[n_levels]
+    ci = p.inhomogeneous_constraints(fine)
+    t0 = time.perf_counter()
+    d = gs.OracleChannelDriver(dim=p.dim, degree=p.fe_degree, meshes=meshes, children=children,
+                               constraints_inhomogeneous=ci.rows, inhomogeneities=ci.inhomogeneities,
+                               min_dx=p.minimal_cell_diameter(fine), nu=p.nu, c1=p.c_1, c2=p.c_2, cfl=p.cfl,
+                               bdf_order=p.bdf_order, consider_time_derivative=p.consider_time_derivative,
+                               cell_wise_stabilization=p.cell_wise_stabilization, rel_tol=p.lin_relative_tolerance,
+                               abs_tol=p.lin_absolute_tolerance, newton_inexact=p.newton_inexact,
+                               level_dtype=np.float32, operator_class=FastOracleOperator)
+    setup_s = time.perf_counter() - t0
+    for _ in range(2):      # like time_step_wall: the first two steps (impulsive start, more Newton steps) are warm-up
+        d.step()
+    walls, recs, c_s = [], [], []
+    t_start = time.perf_counter()
+    for _ in range(n_steps):
+        c0, t0 = FastOracleOperator.c_seconds, time.perf_counter()
+        recs.append(d.step())
+        walls.append(time.perf_counter() - t0)
+        c_s.append(FastOracleOperator.c_seconds - c0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    wall = float(np.mean(walls))
+    return {"wall_s_per_step": wall, "unit": "s", "steps": len(walls), "warmup_steps": 2, "kind": "port",
+            "cores": max_threads(), "n_dofs": int(fine.n_dofs), "n_cells": int(fine.n_cells),
+            "levels": n_levels + 1 - p.mg_min_level, "dofs_per_s": fine.n_dofs / wall,
+            "cell_loops_in_c_s": float(np.mean(c_s)), "setup_s": setup_s,
+            "newton_iterations": [r["newton_iterations"] for r in recs],
+            "gmres_iterations": [r["linear_iterations"] for r in recs],
+            "sample": f"the same 3-D Q2 channel time loop at n global refinements = {refinements} "
+                      f"({int(fine.n_cells)} cells, {int(fine.n_dofs)} DoFs), CPU restatement of the solver stack "
+                      "(oracle/gls_solver.py) with the cell loops in C (oracle/gls_fast.py), not deal.II"}
+
+
 _REAL_STDOUT = None
 
 
@@ -673,6 +732,9 @@ def main():
     ap.add_argument("--time-step-refinements", type=int, default=4,
                     help="n global refinements of the 3-D Q2 channel whose wall time per time step is reported "
                          "next to the vmult metric (3 -> 4.3e6 DoFs, 4 -> 3.4e7); -1 = skip")
+    ap.add_argument("--time-step-cpu-refinements", type=int, default=2,
+                    help="refinements of the bounded sample the CPU restatement of the time step runs on "
+                         "(2 -> 5.6e5 DoFs, a few seconds per step)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

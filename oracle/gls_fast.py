@@ -8,6 +8,8 @@ in double precision whatever the level number type (results are rounded to it). 
 (what the channel and cylinder configurations have)."""
 from __future__ import annotations
 
+import time
+
 import numpy as np
 
 from . import gls_oracle as go
@@ -15,6 +17,15 @@ from .gls_oracle_c import COracle, max_threads
 
 
 class FastOracleOperator(go.OracleOperator):
+    c_seconds = 0.0   # wall time spent inside the C cell loops, summed over all instances (for the breakdown of a
+    #                   timed run: the rest is numpy / scipy glue a compiled CPU code would not have)
+
+    def _timed(self, fn, *a):
+        t0 = time.perf_counter()
+        out = fn(*a)
+        FastOracleOperator.c_seconds += time.perf_counter() - t0
+        return out
+
     def __init__(self, **kw):
         kw.setdefault("path", "sumfac")
         super().__init__(**kw)
@@ -77,22 +88,22 @@ class FastOracleOperator(go.OracleOperator):
         x = np.array(src, dtype=np.float64)
         if len(self.constrained):
             x[self.constrained] = 0.0
-        dst = self._handle(COracle.BR_NEWTON if self.increment_form else COracle.BR_FIXED_POINT) \
-            .apply(x, weight, self.n_threads)
+        co = self._handle(COracle.BR_NEWTON if self.increment_form else COracle.BR_FIXED_POINT)
+        dst = self._timed(co.apply, x, weight, self.n_threads)
         if len(self.constrained):
             dst[self.constrained] = src[self.constrained]
         return dst.astype(self.dtype)
 
     def evaluate_residual(self, src_with_bc, weight):
-        dst = self._handle(COracle.BR_RESIDUAL).apply(np.asarray(src_with_bc, dtype=np.float64), weight,
-                                                      self.n_threads)
+        dst = self._timed(self._handle(COracle.BR_RESIDUAL).apply, np.asarray(src_with_bc, dtype=np.float64), weight,
+                          self.n_threads)
         if len(self.constrained):
             dst[self.constrained] = 0.0
         return (-dst).astype(self.dtype)
 
     def compute_inverse_diagonal(self, weight, edge_constrained_indices=None):
-        diag = self._handle(COracle.BR_NEWTON if self.increment_form else COracle.BR_FIXED_POINT) \
-            .diagonal(weight, self.n_threads)
+        co = self._handle(COracle.BR_NEWTON if self.increment_form else COracle.BR_FIXED_POINT)
+        diag = self._timed(co.diagonal, weight, self.n_threads)
         if len(self.constrained):
             diag[self.constrained] = 1.0
         if edge_constrained_indices is not None and len(edge_constrained_indices):

@@ -62,3 +62,17 @@ def test_bench_parity_full_size_object_with_the_oracle_standing_in_for_the_devic
 
     r = bench.gpu_parity_full_size(chk, Op(), torch.zeros(big.n_dofs, dtype=torch.float64), torch.float64, "double")
     assert r["ok"] and r["n_cells"] == 12 ** 3 and r["oracle_cells"] == 12 ** 3 and r["rel_l2_all_rows"] < 1e-13, r
+
+
+def test_bench_time_step_cpu_baseline_runs():
+    """bench.time_step_cpu (the CPU figure beside the device's wall time per time step) on the smallest hierarchy;
+    the C-backed operator it uses is compared with the numpy oracle in tests/test_oracle.py"""
+    import bench
+    from dealii_ns_gls_b200.driver import ChannelParameters
+
+    r = bench.time_step_cpu(0, n_steps=1)
+    assert r["kind"] == "port" and r["warmup_steps"] == 2 and r["steps"] == 1 and r["levels"] == 2
+    assert 0.0 < r["cell_loops_in_c_s"] < r["wall_s_per_step"]
+    assert 1 <= r["newton_iterations"][0] <= 6 and all(1 <= k <= 20 for k in r["gmres_iterations"][0])
+    p = ChannelParameters(dim=3, fe_degree=2, n_global_refinements=0, mg_min_level=1)
+    assert r["n_dofs"] == p.level_mesh(p.n_levels()).n_dofs

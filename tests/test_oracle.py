@@ -290,3 +290,39 @@ def test_relaxation_restatement_smooths():
     r0 = np.linalg.norm(e)
     r5 = np.linalg.norm(sm.step(e, np.zeros_like(e)))  # error propagation of 5 sweeps
     assert r5 < 0.9 * r0
+
+
+@pytest.mark.parametrize("kind,order,cell_wise", [("channel3", 1, True), ("shell2", 2, False), ("channel2", 0, False)])
+def test_c_backed_operator_matches_numpy_oracle(kind, order, cell_wise):
+    """oracle/gls_fast.py (vmult, residual and unit-vector diagonal in C, Cartesian cells detected) against the
+    numpy oracle it derives from, before and after a change of the linearization point"""
+    from dealii_ns_gls_b200 import mesh as gm
+    from dealii_ns_gls_b200.driver import ChannelParameters, channel_level_mesh
+    from oracle.gls_fast import FastOracleOperator
+    rng = np.random.default_rng(0)
+    if kind == "channel3":
+        m = channel_level_mesh(ChannelParameters(dim=3, fe_degree=2, n_global_refinements=0), 1)
+    elif kind == "channel2":
+        m = channel_level_mesh(ChannelParameters(dim=2, fe_degree=1, n_global_refinements=1), 2)
+    else:
+        m = gm.cylinder_shell((3, 8), 2)
+    kw = dict(dim=m.dim, degree=m.degree, cell_dofs=m.cell_dofs, n_dofs=m.n_dofs, cell_points=m.cell_points,
+              mapping_degree=m.mapping_degree, constraints=m.constraints, nu=0.01, c1=2.0, c2=1.0, theta=1.0, order=order,
+              consider_time_derivative=True, increment_form=True, cell_wise_stabilization=cell_wise)
+    a, b = go.OracleOperator(path="sumfac", **kw), FastOracleOperator(**kw)
+    assert b._cartesian == (kind != "shell2")
+    hist = [rng.uniform(-1, 1, m.n_dofs) for _ in range(order + 1)]
+    w = [3.0, -4.0, 1.0][:order + 1] if order else [0.0]
+    src = rng.uniform(-1, 1, m.n_dofs)
+
+    def err(x, y):
+        return np.linalg.norm(x - y) / np.linalg.norm(y)
+
+    for _ in range(2):
+        lin = rng.uniform(-1, 1, m.n_dofs)
+        for o in (a, b):
+            o.set_previous_solution(hist, w)
+            o.set_linearization_point(lin, 0.1)
+        assert err(b.vmult(src, w[0]), a.vmult(src, w[0])) < 1e-14
+        assert err(b.evaluate_residual(src, w[0]), a.evaluate_residual(src, w[0])) < 1e-14
+        assert err(b.compute_inverse_diagonal(w[0]), a.compute_inverse_diagonal(w[0])) < 1e-13
