@@ -1,4 +1,4 @@
-"""Writes tests/golden/turek_2d2.json (+ turek_2d2_state.npz): the DFG benchmark 2D-2 (periodic flow around a
+"""Writes tests/golden/turek_2d2.json (+ turek/turek_2d2_state.npz): the DFG benchmark 2D-2 (periodic flow around a
 cylinder at Re = 100; input/input_turek_2D_Re100.json of the reference) on the CPU oracle -- BDF2, time-derivative
 terms, q-point-wise stabilisation -- run from rest until the vortex shedding is periodic.  Records the force
 history of the last periods, the maxima of drag and lift and the Strouhal number, and the three history vectors at
@@ -31,7 +31,8 @@ if __name__ == "__main__":
     tail = [r for r in sim.records if r["t"] >= t_final - 1.5]
     out = {"literature": gt.LITERATURE_2D2, "level": level, "dt": sim.dt, "t_final": sim.t, "n_steps": sim.n_steps,
            "n_cells": int(sim.mesh.n_cells), "n_dofs": int(sim.mesh.n_dofs), "statistics": stats, "tail": tail}
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "turek_2d2_state.npz"),
+    os.makedirs(os.path.join(ROOT, "tests", "golden", "turek"), exist_ok=True)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "turek", "turek_2d2_state.npz"),
                         history=np.stack(sim.history).astype(np.float64), t=sim.t, dt=sim.dt,
                         bdf_dt=np.array(sim.bdf.dt, dtype=np.float64))
     # three more steps from the saved state: what the test re-computes

@@ -103,7 +103,7 @@ def test_unsteady_record_against_published_intervals(golden_unsteady):
 
 def test_unsteady_run_continues_from_the_recorded_state(golden_unsteady):
     """three BDF2 steps from the stored history vectors give the recorded forces (the oracle has not moved)"""
-    st = np.load(os.path.join(HERE, "golden", "turek_2d2_state.npz"))
+    st = np.load(os.path.join(HERE, "golden", "turek", "turek_2d2_state.npz"))
     sim = gt.UnsteadyTurek(level=golden_unsteady["level"], dt=float(st["dt"]))
     assert sim.mesh.n_dofs == golden_unsteady["n_dofs"] == st["history"].shape[1]
     sim.history = [h.copy() for h in st["history"]]
