@@ -206,7 +206,7 @@ def gpu_parity_on_sample(sm, number, dev):
     return {"rel_l2_unconstrained_rows": err, "identity_rows_bit_equal": ident, "tol": tol,
             "ok": bool(err < tol and ident), "n_dofs": int(mesh.n_dofs), "n_cells": int(mesh.n_cells),
             "n_constrained": int(len(cons)), "number": number, "kernel_variant": variant,
-            "checker": "oracle/gls_oracle_c.c (CPU restatement; parity unpinned against deal.II)"}
+            "checker": "oracle/gls_oracle_c.c (CPU restatement: its quadrature-point physics is pinned to the reference's own object code, tests/test_reference_qpoint.py; deal.II's parts are restated, unpinned)"}
 
 
 def gpu_parity_full_size(chk, op, dst, tdt, number):
@@ -222,7 +222,7 @@ def gpu_parity_full_size(chk, op, dst, tdt, number):
     r = chk.compare(dst, ref)
     tol = 1e-12 if number == "double" else 2e-5
     r.update(tol=tol, ok=bool(r["rel_l2_all_rows"] < tol), number=number, kernel_variant=op.vmult_variant(),
-             checker="oracle/gls_oracle.py (numpy restatement; parity unpinned against deal.II) on the small block, "
+             checker="oracle/gls_oracle.py (numpy restatement: quadrature-point physics pinned to the reference's own object code, deal.II's parts unpinned) on the small block, "
                      "mapped to every dof of the big block by periodicity")
     return r
 

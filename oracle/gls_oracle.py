@@ -5,15 +5,25 @@ TEST INFRASTRUCTURE ONLY.  Nothing in the product path (the package
 only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 ``--impl reference`` legs of ``bench.py`` use it, and only as the checker.
 
-PARITY UNPINNED: the reference (peterrum/dealii-ns-gls) has no tests, golden
-vectors or fixtures, and its arithmetic lives in deal.II (MatrixFree /
-FEEvaluation, >= 9.6, not vendored, not installable here).  This file is a
-restatement of the reference's algorithm from its sources plus the published
-deal.II conventions listed in SURVEY.md section 8c.  It is checked against
-closed-form answers (tests/test_oracle.py): Q1 element matrices, polynomial
-exactness, finite-difference Jacobian consistency (Newton branch vs residual
-branch), naive-full-tensor vs sum-factorised evaluation, unit-vector matrix vs
-vmult, and 1/diag vs the assembled diagonal.
+PARITY: PINNED FOR THE REFERENCE'S OWN ARITHMETIC, UNPINNED FOR DEAL.II'S.  The reference
+(peterrum/dealii-ns-gls) has no tests, golden vectors or fixtures, and the operator as a whole cannot be built
+here (deal.II >= 9.6 with p4est / Trilinos / MPI, not vendored, not installable).  What does compile without
+deal.II is the code the reference itself contributes to the path, and it is run here as object code
+(oracle/_ref/, built from /root/reference by `make -C oracle _ref`, recorded in tests/golden/reference*):
+  * include/time_integration.cc, the whole file       -> OracleBDF below is bit-equal to it
+    (tests/test_reference_time_integration.py);
+  * include/operator_ns.cc:880-1182 (do_vmult_cell, both branches, symm_scalar_product_add), :1195-1301
+    (do_vmult_boundary) and :348-421 (the cell loop of compute_penalty_parameters), compiled unmodified on
+    stand-in Tensor / VectorizedArray / FEEvaluation types  ->  _cell_newton, _cell_fixed_point, _face_qpoint
+    and _penalty below agree with them to <= 4e-15 in every branch / flag combination
+    (tests/test_reference_qpoint.py).
+Everything deal.II computes around those kernels -- FE_Q / QGauss tables, sum-factorised evaluate / integrate,
+MappingQ geometry, constraint resolution in read_dof_values / distribute_local_to_global, compute_diagonal --
+is a restatement from the published deal.II conventions listed in SURVEY.md section 8c and stays unpinned; it is
+checked against closed-form answers (tests/test_oracle.py: Q1 element matrices, polynomial exactness,
+finite-difference Jacobian consistency, naive-full-tensor vs sum-factorised evaluation, unit-vector matrix vs
+vmult, 1/diag vs the assembled diagonal), against an independent FEValues-style restatement of the reference's
+matrix-based operator (oracle/gls_matrix_based.py) and against published benchmark numbers (oracle/gls_turek.py).
 
 Reference files restated (all relative to /root/reference):
   include/operator_ns.cc:899-916    symm_scalar_product_add
@@ -609,6 +619,28 @@ class OracleOperator:
         u = self._gather(vec)[F["cell"]][:, : self.dim]  # [f, d, i]
         F["velocity"] = np.einsum("fqi,fdi->fqd", F["N"], u).astype(self.dtype)
 
+    def _face_qpoint(self, kind, val, grad, n, beta, velocity, target, residual):
+        """do_vmult_boundary at the face quadrature points (operator_ns.cc:1195-1301): what the reference hands to
+        submit_value / submit_gradient.  kind[f] 1 = cut, 2 = Nitsche; val[f, d, q], grad[f, d, j, q] velocity
+        values and physical gradients, n[f, q, j] outward normals, beta[f], velocity[f, q, d] (face_velocity of the
+        linearization point), target[f, q, d] or None."""
+        T = self.dtype.type
+        beta = beta[:, None, None]
+        vr = np.zeros_like(val)
+        gr = np.zeros_like(grad)
+        cut = kind == 1
+        nit = kind == 2
+        if cut.any():
+            sv = val if residual else np.moveaxis(velocity, 2, 1)  # [f, d, q]
+            no = np.minimum(T(0), np.einsum("fdq,fqd->fq", sv, n))
+            vr[cut] = (beta * no[:, None, :] * val)[cut]
+        if nit.any():
+            v = val - np.moveaxis(target, 2, 1) if (residual and target is not None) else val
+            gn = np.einsum("fcjq,fqj->fcq", grad, n)
+            vr[nit] = (beta * v - T(self.nu) * gn)[nit]
+            gr[nit] = (-T(self.nu) * v[:, :, None, :] * np.moveaxis(n, 2, 1)[:, None, :, :])[nit]
+        return vr, gr
+
     def _apply_faces(self, loc_in, out, residual):
         F, d = self.faces, self.dim
         T = self.dtype.type
@@ -616,21 +648,7 @@ class OracleOperator:
         val = np.einsum("fqi,fci->fcq", F["N"], u)
         rg = np.einsum("feqi,fci->fceq", F["dN"], u)
         grad = np.einsum("fqej,fceq->fcjq", F["Jinv"], rg)
-        n = F["normal"]
-        beta = F["beta"][:, None, None]
-        vr = np.zeros_like(val)
-        gr = np.zeros_like(grad)
-        cut = F["kind"] == 1
-        nit = F["kind"] == 2
-        if cut.any():
-            sv = val if residual else np.moveaxis(F["velocity"], 2, 1)  # [f, d, q]
-            no = np.minimum(T(0), np.einsum("fdq,fqd->fq", sv, n))
-            vr[cut] = (beta * no[:, None, :] * val)[cut]
-        if nit.any():
-            v = val - np.moveaxis(F["target"], 2, 1) if (residual and F["target"] is not None) else val
-            gn = np.einsum("fcjq,fqj->fcq", grad, n)
-            vr[nit] = (beta * v - T(self.nu) * gn)[nit]
-            gr[nit] = (-T(self.nu) * v[:, :, None, :] * np.moveaxis(n, 2, 1)[:, None, :, :])[nit]
+        vr, gr = self._face_qpoint(F["kind"], val, grad, F["normal"], F["beta"], F["velocity"], F["target"], residual)
         vq = vr * F["jxw"][:, None, :]
         rgq = np.einsum("fqej,fcjq->fceq", F["Jinv"], gr) * F["jxw"][:, None, None, :]
         loc = np.einsum("fqi,fcq->fci", F["N"], vq) + np.einsum("feqi,fceq->fci", F["dN"], rgq)

@@ -3,8 +3,9 @@
  *
  * TEST INFRASTRUCTURE ONLY: used by tests/ as a second, independently written checker next
  * to oracle/gls_oracle.py, and by bench.py as the timed CPU baseline ("port": this is a
- * restatement of the reference algorithm, not deal.II).  PARITY UNPINNED (the reference has
- * no golden vectors; see the header of gls_oracle.py).
+ * restatement of the reference algorithm, not deal.II).  Pinned through gls_oracle.py, with
+ * which it agrees to round-off: that file's quadrature-point physics is compared with the
+ * reference's own object code (oracle/_ref), deal.II's parts stay unpinned (see its header).
  *
  * Follows /root/reference:
  *   include/operator_ns.cc:806-830    do_vmult_range: gather, cell kernel, scatter-add

@@ -1,8 +1,10 @@
 """Schaefer-Turek benchmark 2D-1 (stationary flow around a cylinder, Re = 20) solved with the CPU oracle -- a
 PHYSICS known-answer test for the restatement.  TEST INFRASTRUCTURE ONLY (see oracle/gls_oracle.py).
 
-Why it exists.  The reference holds no golden vectors and cannot be built here, so nothing ties the oracle to the
-reference's own output ("parity unpinned").  What the reference does hold is the input of
+Why it exists.  The reference holds no golden vectors and cannot be built here as a whole; its own
+quadrature-point code is run as object code (tests/test_reference_qpoint.py), but everything deal.II does around
+it -- basis, quadrature, evaluate / integrate, mapping, constraints -- is restated and nothing ties THAT to the
+reference's output.  What the reference does hold is the input of
 a benchmark with published answers: input/input_turek_2D_Re20_stat.json is the DFG benchmark 2D-1 (nu = 0.001,
 parabolic inflow with u_max = 0.3 on a 2.2 x 0.41 channel, cylinder of diameter 0.1, Q2 elements, Newton,
 "time intration": "none", q-point-wise stabilisation), and SimulationCylinder::postprocess
