@@ -129,3 +129,40 @@ def test_both_regimes_of_the_cell_wise_parameters_are_in_the_record():
         above += int((nu >= h).sum())
     assert below > 10 and above > 10
     assert any(dt == 0.0 for _, _, dt, _ in gen.PENALTY)
+
+
+# ---- the PRODUCT's CUDA source against the reference record, on the host ------------------------------------------
+def _product_lib():
+    import ctypes as C
+    import subprocess
+    path = os.path.join(HERE, "cpp", "libprod_qpoint.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["bash", os.path.join(HERE, "cpp", "build_qpoint_host.sh")])
+    lib = C.CDLL(path)
+    P, D, I = C.c_void_p, C.c_double, C.c_int
+    lib.prod_qpoint.restype = I
+    lib.prod_qpoint.argtypes = [I, I, D, D, D, I, I, I] + [P] * 10 + [I, P, P]
+    return lib
+
+
+@pytest.mark.parametrize("i", range(len(gen.CASES)))
+def test_cuda_source_qpoint_physics_equals_the_reference(i, record):
+    """qpoint_physics of dealii_ns_gls_b200/csrc/glsb_kernels.cuh (what the generic, column, diagonal and residual
+    kernels run per quadrature point), compiled for the host by tests/cpp/build_qpoint_host.sh, on the inputs of the
+    reference record: the CUDA source against the reference's own do_vmult_cell, no GPU and no oracle in between"""
+    lib = _product_lib()
+    dim, res, inc, ctd, cw, th, old = gen.CASES[i]
+    dim, res, inc, ctd, cw, old = int(dim), int(res), int(inc), int(ctd), int(cw), int(old)
+    a = gen.inputs(i, dim, 3 ** dim)
+    branch = 2 if res else (0 if inc else 1)
+    f = lambda x: np.ascontiguousarray(x, dtype=np.float64)  # noqa: E731
+    arrs = [f(a[k]) for k in ("value", "grad", "u_star", "u_star_grad", "p_star_grad", "u_tdo", "u_old_grad",
+                              "p_old_grad", "d1", "d2")]
+    vo, go_ = np.zeros_like(arrs[0]), np.zeros_like(arrs[1])
+    ptr = lambda x: x.ctypes.data_as(__import__("ctypes").c_void_p)  # noqa: E731
+    rc = lib.prod_qpoint(dim, branch, float(th), 0.037, 7.25, ctd, old, 3 ** dim, *[ptr(x) for x in arrs], cw,
+                         ptr(vo), ptr(go_))
+    assert rc == 0
+    ref_v, ref_g = record[f"value_out_{i}"], record[f"grad_out_{i}"]
+    scale = max(np.abs(ref_v).max(), np.abs(ref_g).max())
+    assert np.abs(vo - ref_v).max() <= 4e-15 * scale and np.abs(go_ - ref_g).max() <= 4e-15 * scale, gen.CASES[i]
