@@ -87,3 +87,47 @@ def test_solution_history_commit(record):
         for _ in range(case["commits"]):
             h.commit_solution()
         assert [float(s[0]) for s in h.get_vectors()] == case["after"]
+
+
+def test_cpp_host_mirror_is_bit_equal_to_the_reference(record):
+    """glsb::TimeIntegratorDataBDF / Theta / None of dealii_ns_gls_b200/cpp/operator_b200.h (what a C++ host program
+    on top of the C ABI reads its weights from), compiled for the host, on the record of the reference's own code"""
+    import ctypes as C
+    import subprocess
+    path = os.path.join(HERE, "cpp", "libmirror_time_integration.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-I/usr/local/cuda/include", "-o", path,
+                               os.path.join(HERE, "cpp", "time_integration_host.cpp")])
+    lib = C.CDLL(path)
+    lib.mirror_create.restype = C.c_void_p
+    lib.mirror_create.argtypes = [C.c_int, C.c_int, C.c_double]
+    lib.mirror_destroy.argtypes = [C.c_void_p]
+    lib.mirror_update_dt.restype = C.c_int
+    lib.mirror_update_dt.argtypes = [C.c_void_p, C.c_double]
+    lib.mirror_query.restype = C.c_int
+    lib.mirror_query.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint)]
+
+    def query(h):
+        w = (C.c_double * 8)()
+        pw, dt, th, order = C.c_double(), C.c_double(), C.c_double(), C.c_uint()
+        n = lib.mirror_query(h, w, 8, C.byref(pw), C.byref(dt), C.byref(th), C.byref(order))
+        return {"weights": [w[i] for i in range(n)], "primary_weight": pw.value, "current_dt": dt.value,
+                "theta": th.value, "order": int(order.value)}
+
+    for case in record["bdf"]:
+        h = lib.mirror_create(0, case["order"], 1.0)
+        for dt, ref in zip(case["dts"], case["after_each_update"]):
+            assert lib.mirror_update_dt(h, dt) == 0
+            assert query(h) == {k: v for k, v in ref.items() if k != "accepted"}
+        lib.mirror_destroy(h)
+    for case in record["theta"]:
+        h = lib.mirror_create(1, 0, case["theta"])
+        for dt, ref in zip(case["dts"], case["after_each_update"]):
+            lib.mirror_update_dt(h, dt)
+            assert query(h) == ref
+        lib.mirror_destroy(h)
+    h = lib.mirror_create(2, 0, 1.0)
+    lib.mirror_update_dt(h, 0.3)
+    assert query(h) == record["none"]
+    lib.mirror_destroy(h)
