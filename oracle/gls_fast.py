@@ -49,7 +49,7 @@ class FastOracleOperator(go.OracleOperator):
     def _handle(self, branch):
         co = self._c.get(branch)
         if co is None:
-            K, d = self.n_cells, self.dim
+            d = self.dim
             b = self.tb.b
             if self._cartesian:
                 J = np.asarray(self.Jinv, dtype=np.float64)

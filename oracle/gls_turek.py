@@ -286,7 +286,7 @@ class UnsteadyTurek:
             x[d] = f * v
 
     def step(self):
-        op, w_old = self.op, None
+        op = self.op
         self.bdf.update_dt(self.dt)
         w = self.bdf.weights
         self.history[2], self.history[1] = self.history[1], self.history[0].copy()
