@@ -207,7 +207,40 @@ def mapping_jacobians(cell_points: np.ndarray, mapping_degree: int, tb: TensorBa
         mats[e] = mb.G
         dM.append(_kron_all(mats))
     dM = np.stack(dM)  # [e, q, m]
-    return np.einsum("eqm,kmi->kqie", dM, cell_points)
+    # J[k, q, i, e] = sum_m dM[e, q, m] X[k, m, i]: one matrix product per direction (BLAS) instead of an einsum
+    K, nq = cell_points.shape[0], dM.shape[1]
+    J = np.empty((K, nq, dim, dim))
+    for e in range(dim):
+        J[:, :, :, e] = np.matmul(dM[e][None, :, :], cell_points)
+    return J
+
+
+def small_inverse_and_determinant(J):
+    """inverse and determinant of a stack of 2 x 2 or 3 x 3 matrices [..., d, d] in closed form (adjugate / det);
+    np.linalg for other sizes"""
+    d = J.shape[-1]
+    if d == 2:
+        det = J[..., 0, 0] * J[..., 1, 1] - J[..., 0, 1] * J[..., 1, 0]
+        inv = np.empty_like(J)
+        inv[..., 0, 0], inv[..., 0, 1] = J[..., 1, 1], -J[..., 0, 1]
+        inv[..., 1, 0], inv[..., 1, 1] = -J[..., 1, 0], J[..., 0, 0]
+        return inv / det[..., None, None], det
+    if d == 3:
+        a = J
+        c00 = a[..., 1, 1] * a[..., 2, 2] - a[..., 1, 2] * a[..., 2, 1]
+        c01 = a[..., 1, 2] * a[..., 2, 0] - a[..., 1, 0] * a[..., 2, 2]
+        c02 = a[..., 1, 0] * a[..., 2, 1] - a[..., 1, 1] * a[..., 2, 0]
+        det = a[..., 0, 0] * c00 + a[..., 0, 1] * c01 + a[..., 0, 2] * c02
+        inv = np.empty_like(J)
+        inv[..., 0, 0], inv[..., 1, 0], inv[..., 2, 0] = c00, c01, c02
+        inv[..., 0, 1] = a[..., 0, 2] * a[..., 2, 1] - a[..., 0, 1] * a[..., 2, 2]
+        inv[..., 0, 2] = a[..., 0, 1] * a[..., 1, 2] - a[..., 0, 2] * a[..., 1, 1]
+        inv[..., 1, 1] = a[..., 0, 0] * a[..., 2, 2] - a[..., 0, 2] * a[..., 2, 0]
+        inv[..., 1, 2] = a[..., 0, 2] * a[..., 1, 0] - a[..., 0, 0] * a[..., 1, 2]
+        inv[..., 2, 1] = a[..., 0, 1] * a[..., 2, 0] - a[..., 0, 0] * a[..., 2, 1]
+        inv[..., 2, 2] = a[..., 0, 0] * a[..., 1, 1] - a[..., 0, 1] * a[..., 1, 0]
+        return inv / det[..., None, None], det
+    return np.linalg.inv(J), np.linalg.det(J)
 
 
 def cell_vertices(cell_points: np.ndarray, mapping_degree: int, dim: int):
@@ -284,8 +317,9 @@ class OracleOperator:
         self._mapping_degree = mapping_degree
         self.faces = None  # boundary faces with outflow terms (set_outflow_faces)
         J = mapping_jacobians(np.asarray(cell_points, dtype=np.float64), mapping_degree, self.tb)
-        self.Jinv = np.linalg.inv(J).astype(self.dtype)  # [k,q,e,j] = (J^-1)_{e j}
-        self.JxW = (np.linalg.det(J) * self.tb.w[None, :]).astype(self.dtype)
+        Jinv, detJ = small_inverse_and_determinant(J)
+        self.Jinv = Jinv.astype(self.dtype)  # [k,q,e,j] = (J^-1)_{e j}
+        self.JxW = (detJ * self.tb.w[None, :]).astype(self.dtype)
         verts = cell_vertices(np.asarray(cell_points, dtype=np.float64), mapping_degree, dim)
         self.h_min = minimum_vertex_distance(verts)
         self.measure = vertex_measure(verts, dim)
