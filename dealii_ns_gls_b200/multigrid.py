@@ -113,7 +113,7 @@ class MGTwoLevelTransfer:
         ch = child_cells(mesh_coarse, mesh_fine)
         fidx = np.ascontiguousarray(mesh_fine.cell_dofs[ch.reshape(-1)].reshape(mesh_coarse.n_cells, -1),
                                     dtype=np.uint32)
-        cidx = np.ascontiguousarray(mesh_coarse.cell_dofs, dtype=np.uint32).copy()
+        cidx = np.ascontiguousarray(mesh_coarse.cell_dofs, dtype=np.uint32)  # replaced, never written in place
         row_ptr, ecol, ev = [0], [], []
         rows = constraints_coarse.rows if constraints_coarse is not None else {}
         if rows:
@@ -122,10 +122,9 @@ class MGTwoLevelTransfer:
                 for m, w in rows[int(d)]:
                     ecol.append(m), ev.append(w)
                 row_ptr.append(len(ecol))
-            row_of = np.full(mesh_coarse.n_dofs, -1, dtype=np.int64)
-            row_of[cdofs] = np.arange(len(cdofs))
-            r = row_of[cidx.astype(np.int64)]
-            cidx = np.where(r >= 0, (r | L.GLSB_CONSTRAINED_BIT).astype(np.uint32), cidx).astype(np.uint32)
+            look = np.arange(mesh_coarse.n_dofs, dtype=np.uint32)
+            look[cdofs] = np.arange(len(cdofs), dtype=np.uint32) | np.uint32(L.GLSB_CONSTRAINED_BIT)
+            cidx = np.take(look, cidx)
         cidx = np.ascontiguousarray(cidx)
         touch = np.bincount(mesh_fine.cell_dofs.reshape(-1).astype(np.int64), minlength=mesh_fine.n_dofs)
         if self.op_fine is not None:

@@ -97,10 +97,11 @@ def build_desc(mesh: Mesh, *, number, nu, c_1, c_2, theta, time_order, consider_
             ev.append(w)
         row_ptr.append(len(ecol))
     if len(cdofs):
-        row_of = np.full(mesh.n_dofs, -1, dtype=np.int64)
-        row_of[cdofs] = np.arange(len(cdofs))
-        r = row_of[idx.astype(np.int64)]
-        idx = np.where(r >= 0, (r | L.GLSB_CONSTRAINED_BIT).astype(np.uint32), idx).astype(np.uint32)
+        # one gather through a lookup that is the identity on unconstrained dofs and GLSB_CONSTRAINED_BIT | row on
+        # constrained ones
+        look = np.arange(mesh.n_dofs, dtype=np.uint32)
+        look[cdofs] = np.arange(len(cdofs), dtype=np.uint32) | np.uint32(L.GLSB_CONSTRAINED_BIT)
+        idx = np.take(look, idx)
     keep["idx"] = np.ascontiguousarray(idx)
     keep["row_dof"] = cdofs.astype(np.uint32)
     keep["row_ptr"] = np.array(row_ptr, dtype=np.uint32)
