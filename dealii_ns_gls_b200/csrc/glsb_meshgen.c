@@ -257,3 +257,64 @@ int64_t glsm_general_geometry(int dim, int64_t ncell, int n_q, int n_m, const do
     }
   return bad;
 }
+
+/* minimum_vertex_distance() and measure() of every cell from its 2^dim vertices (verts[cell][v][dim], vertex v at
+ * the corner with bit e of v set in direction e): the smallest distance between two vertices, and the volume of
+ * the multilinear cell by 2-point Gauss quadrature per direction (exact for it).  Same formulas as
+ * mesh.py::_vertex_geometry. */
+int glsm_vertex_geometry(int dim, int64_t ncell, const double *verts, double *h_min, double *measure)
+{
+  if (dim < 2 || dim > 3)
+    return 1;
+  const int    nv = 1 << dim;
+  const double g[2] = {0.5 - 0.5 / 1.7320508075688772, 0.5 + 0.5 / 1.7320508075688772};
+  /* d phi_v / d xi_e at the 2^dim Gauss points */
+  double dphi[8][8][3];
+  for (int qi = 0; qi < nv; ++qi)
+    for (int v = 0; v < nv; ++v)
+      for (int e = 0; e < dim; ++e)
+        {
+          double t = 1.0;
+          for (int f = 0; f < dim; ++f)
+            {
+              const int    bit = (v >> f) & 1;
+              const double xi  = g[(qi >> f) & 1];
+              t *= (f == e) ? (bit ? 1.0 : -1.0) : (bit ? xi : 1.0 - xi);
+            }
+          dphi[qi][v][e] = t;
+        }
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < ncell; ++c)
+    {
+      const double *X  = verts + c * (int64_t)nv * dim;
+      double        h2 = 1e300;
+      for (int a = 0; a < nv; ++a)
+        for (int b = a + 1; b < nv; ++b)
+          {
+            double s = 0;
+            for (int i = 0; i < dim; ++i)
+              s += (X[a * dim + i] - X[b * dim + i]) * (X[a * dim + i] - X[b * dim + i]);
+            if (s < h2)
+              h2 = s;
+          }
+      double meas = 0;
+      for (int qi = 0; qi < nv; ++qi)
+        {
+          double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+          for (int v = 0; v < nv; ++v)
+            for (int i = 0; i < dim; ++i)
+              for (int e = 0; e < dim; ++e)
+                J[i][e] += X[v * dim + i] * dphi[qi][v][e];
+          double det;
+          if (dim == 2)
+            det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+          else
+            det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                  J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+          meas += det / nv;
+        }
+      h_min[c]   = __builtin_sqrt(h2);
+      measure[c] = meas;
+    }
+  return 0;
+}

@@ -76,6 +76,8 @@ def _native():
             lib.glsm_number_nodes.argtypes = [I, P, I, P, I, P, P, P, P]
             lib.glsm_assemble_cell_dofs.restype = I
             lib.glsm_assemble_cell_dofs.argtypes = [L, I, I, P, P, L, I, P, P]
+            lib.glsm_vertex_geometry.restype = I
+            lib.glsm_vertex_geometry.argtypes = [I, L, P, P, P]
             lib.glsm_general_geometry.restype = L
             lib.glsm_general_geometry.argtypes = [I, L, I, I, P, P, P, P, P]
             _meshgen = lib
@@ -170,6 +172,13 @@ def _det_small(J):
 
 def _vertex_geometry(verts: np.ndarray, dim: int):
     """minimum_vertex_distance() and measure() from the 2^dim vertices."""
+    lib = _native()
+    if lib is not None and dim in (2, 3):
+        v = np.ascontiguousarray(verts, dtype=np.float64)
+        h, meas = np.empty(v.shape[0]), np.empty(v.shape[0])
+        if lib.glsm_vertex_geometry(dim, v.shape[0], _ptr(v), _ptr(h), _ptr(meas)) != 0:
+            raise RuntimeError("glsm_vertex_geometry failed")
+        return h, meas
     nv = verts.shape[1]
     h2 = np.full(verts.shape[0], np.inf)
     for a in range(nv):
@@ -315,9 +324,12 @@ def structured_mesh(dim, shape, degree, *, deform=None, mapping_degree=1, period
 
     # ---- partition ------------------------------------------------------------
     bounds = [(ncell * r) // n_ranks for r in range(n_ranks + 1)]
-    node_owner_of_rank = np.searchsorted(np.asarray(bounds[1:]), first_cell, side="right")
-    # owned node ranges in the global numbering are contiguous
-    owned_counts = np.bincount(node_owner_of_rank, minlength=n_ranks)
+    if n_ranks == 1:
+        owned_counts = np.array([nnode])
+    else:
+        node_owner_of_rank = np.searchsorted(np.asarray(bounds[1:]), first_cell, side="right")
+        # owned node ranges in the global numbering are contiguous
+        owned_counts = np.bincount(node_owner_of_rank, minlength=n_ranks)
     owned_off_nodes = np.concatenate([[0], np.cumsum(owned_counts)])
 
     c0, c1 = bounds[rank], bounds[rank + 1]

@@ -65,3 +65,12 @@ def test_general_geometry(shape, p, monkeypatch):
     assert np.abs(ja - jb).max() <= 1e-14 * np.abs(jb).max()
     (ia, ja), (ib, jb) = _both(lambda: gm.general_geometry(m, n_q_1d=p + 2), monkeypatch)
     assert np.abs(ia - ib).max() <= 1e-13 * np.abs(ib).max() and np.abs(ja - jb).max() <= 1e-14 * np.abs(jb).max()
+
+
+def test_vertex_geometry(monkeypatch):
+    for m in (gm.cylinder_shell((3, 8), 2), gm.cylinder_shell((2, 6, 3), 2)):
+        k, dim = m.mapping_degree, m.dim
+        vid = [sum((k * ((v >> e) & 1)) * (k + 1) ** e for e in range(dim)) for v in range(2 ** dim)]
+        verts = m.cell_points[:, vid, :]
+        (ha, ma), (hb, mb) = _both(lambda: gm._vertex_geometry(verts, dim), monkeypatch)
+        assert np.abs(ha / hb - 1).max() < 1e-15 and np.abs(ma / mb - 1).max() < 1e-14
