@@ -24,9 +24,16 @@ sed -n '348,421p' "$ref/include/operator_ns.cc" > "$pen"
 [ "$(sed -n '1p' "$pen")" = "  const auto tau  = this->time_integrator_data.get_current_dt();" ]
 grep -q 'delta_2_q\[cell\]\[q\] = std::sqrt(u_mag_squared) \* h \* 0.5;' "$pen"
 [ "$(tail -1 "$pen")" = "    }" ]
+# effective_beta_face of the outflow faces (:428-457)
+bet="$here/_ref/beta_extract.inc"
+trap 'rm -f "$inc" "$pen" "$bet"' EXIT
+sed -n '428,457p' "$ref/include/operator_ns.cc" > "$bet"
+[ "$(sed -n '1p' "$bet")" = "      const double beta = 1.0; // TODO" ]
+grep -q 'beta / std::pow(cell_size, static_cast<Number>(fe_degree + 1));' "$bet"
+[ "$(tail -1 "$bet")" = "        }" ]
 # do_vmult_boundary: the "cut" and Nitsche outflow-face terms (:1195-1301)
 bnd="$here/_ref/boundary_extract.inc"
-trap 'rm -f "$inc" "$pen" "$bnd"' EXIT
+trap 'rm -f "$inc" "$pen" "$bet" "$bnd"' EXIT
 sed -n '1195,1301p' "$ref/include/operator_ns.cc" > "$bnd"
 [ "$(sed -n '1p' "$bnd")" = "template <int dim, typename Number>" ]
 grep -q 'NavierStokesOperator<dim, Number>::do_vmult_boundary(' "$bnd"

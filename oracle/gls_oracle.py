@@ -13,7 +13,8 @@ deal.II is the code the reference itself contributes to the path, and it is run 
   * include/time_integration.cc, the whole file       -> OracleBDF below is bit-equal to it
     (tests/test_reference_time_integration.py);
   * include/operator_ns.cc:880-1182 (do_vmult_cell, both branches, symm_scalar_product_add), :1195-1301
-    (do_vmult_boundary) and :348-421 (the cell loop of compute_penalty_parameters), compiled unmodified on
+    (do_vmult_boundary), :348-421 (the cell loop of compute_penalty_parameters) and :428-457 (beta of the
+    outflow faces), compiled unmodified on
     stand-in Tensor / VectorizedArray / FEEvaluation types  ->  _cell_newton, _cell_fixed_point, _face_qpoint
     and _penalty below agree with them to <= 4e-15 in every branch / flag combination
     (tests/test_reference_qpoint.py).

@@ -29,6 +29,8 @@ def load():
         lib.refq_apply.argtypes = [I, I, I, I, I, D, D, D, I] + [P] * 12
         lib.refq_boundary.restype = I
         lib.refq_boundary.argtypes = [I, I, I, D, D, I] + [P] * 8 + [I]
+        lib.refq_face_beta.restype = I
+        lib.refq_face_beta.argtypes = [I, I, I, P, P]
         lib.refq_penalty.restype = I
         lib.refq_penalty.argtypes = [I, D, D, D, D, I, I, I] + [P] * 7
         _lib = lib
@@ -97,3 +99,15 @@ def boundary(*, dim, residual, kind, nu, beta, value, grad, normal, face_velocit
     if rc != 0:
         raise RuntimeError("refq_boundary failed")
     return vo, go_, dv
+
+
+def face_beta(*, dim, degree, measure):
+    """effective_beta_face (include/operator_ns.cc:428-457) of faces whose cells have the given measures"""
+    lib = load()
+    if lib is None:
+        raise RuntimeError("oracle/_ref/libref_qpoint.so is not available")
+    measure = np.ascontiguousarray(measure, dtype=np.float64)
+    out = np.empty_like(measure)
+    if lib.refq_face_beta(dim, int(degree), len(measure), _p(measure), _p(out)) != 0:
+        raise RuntimeError("refq_face_beta failed")
+    return out

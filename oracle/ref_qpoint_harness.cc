@@ -11,6 +11,8 @@
 // tests/test_reference_qpoint.py compares oracle/gls_oracle.py's _cell_newton / _cell_fixed_point with it.
 #include "qpoint_shim.h"
 
+#include <utility>
+
 using namespace dealii;
 
 struct TimeIntegratorData
@@ -118,6 +120,7 @@ struct CellIterator
 struct PenaltyMatrixFree
 {
   std::vector<CellIterator> cells;
+  unsigned int              degree = 0;
   unsigned int
   n_active_entries_per_cell_batch(const unsigned int) const
   {
@@ -127,6 +130,33 @@ struct PenaltyMatrixFree
   get_cell_iterator(const unsigned int cell, const unsigned int) const
   {
     return cells[cell];
+  }
+  // boundary faces: face f belongs to cell f of `cells`
+  unsigned int
+  n_active_entries_per_face_batch(const unsigned int) const
+  {
+    return 1;
+  }
+  std::pair<CellIterator, unsigned int>
+  get_face_iterator(const unsigned int face, const unsigned int) const
+  {
+    return {cells[face], 0u};
+  }
+  // matrix_free.get_dof_handler().get_fe().tensor_degree()
+  const PenaltyMatrixFree &
+  get_dof_handler() const
+  {
+    return *this;
+  }
+  const PenaltyMatrixFree &
+  get_fe() const
+  {
+    return *this;
+  }
+  unsigned int
+  tensor_degree() const
+  {
+    return degree;
   }
 };
 
@@ -183,6 +213,16 @@ struct PenaltyHarness
   Number                                 c_1, c_2;
   AlignedVector<VectorizedArray<Number>> delta_1, delta_2;
   Table<2, VectorizedArray<Number>>      delta_1_q, delta_2_q;
+
+  // effective_beta_face of the outflow faces, include/operator_ns.cc:428-457 (one "face" per entry of
+  // matrix_free.cells)
+  Table<1, VectorizedArray<Number>> effective_beta_face;
+  void
+  compute_beta()
+  {
+    const unsigned int n_inner_faces = 0, n_boundary_faces = matrix_free.cells.size();
+#include "beta_extract.inc"
+  }
 
   void
   compute(const double *u, const unsigned int n_cells, const unsigned int n_quadrature_points,
@@ -398,6 +438,34 @@ refq_boundary(int dim, int residual, int kind, double nu, double beta, int n_q, 
   else if (dim == 3)
     run_boundary<3>(residual, kind, nu, beta, n_q, value, grad, normal, face_velocity, target, value_out, grad_out,
                     dof_values, n_dof_values);
+  else
+    return 1;
+  return 0;
+}
+
+// beta of the outflow faces (operator_ns.cc:428-457) from the measures of the cells behind them
+extern "C" int
+refq_face_beta(int dim, int degree, int n_faces, const double *measure, double *beta)
+{
+  auto run = [&](auto &h) {
+    h.matrix_free.degree = degree;
+    h.matrix_free.cells.resize(n_faces);
+    for (int f = 0; f < n_faces; ++f)
+      h.matrix_free.cells[f] = CellIterator{0.0, measure[f]};
+    h.compute_beta();
+    for (int f = 0; f < n_faces; ++f)
+      beta[f] = h.effective_beta_face[f].data;
+  };
+  if (dim == 2)
+    {
+      PenaltyHarness<2, double> h;
+      run(h);
+    }
+  else if (dim == 3)
+    {
+      PenaltyHarness<3, double> h;
+      run(h);
+    }
   else
     return 1;
   return 0;

@@ -417,6 +417,12 @@ namespace std
   }
   template <typename Number>
   inline dealii::VectorizedArray<Number>
+  pow(const dealii::VectorizedArray<Number> &x, const Number p)
+  {
+    return dealii::VectorizedArray<Number>(std::pow(x.data, p));
+  }
+  template <typename Number>
+  inline dealii::VectorizedArray<Number>
   min(const dealii::VectorizedArray<Number> &a, const dealii::VectorizedArray<Number> &b)
   {
     return dealii::VectorizedArray<Number>(a.data < b.data ? a.data : b.data);

@@ -92,5 +92,11 @@ if __name__ == "__main__":
         r = rq.penalty(dim=dim, dt=dt, nu=nu, c1=4.0, c2=2.0, degree=degree, **a)
         for name, arr in zip(("d1_cell", "d2_cell", "d1_q", "d2_q"), r):
             out[f"{name}_{i}"] = arr
+    # effective_beta_face (:428-457) for dim 2 / 3, degrees 1-4
+    beta_measure = np.random.default_rng(4000).uniform(1e-5, 1e-1, 16)
+    out["beta_measure"] = beta_measure
+    for dim in (2, 3):
+        for degree in (1, 2, 3, 4):
+            out[f"beta_{dim}_{degree}"] = rq.face_beta(dim=dim, degree=degree, measure=beta_measure)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reference", "qpoint.npz"), **out)
     print(len(CASES), "q-point cases,", len(BOUNDARY), "boundary cases,", len(PENALTY), "penalty cases written")

@@ -131,6 +131,24 @@ def test_both_regimes_of_the_cell_wise_parameters_are_in_the_record():
     assert any(dt == 0.0 for _, _, dt, _ in gen.PENALTY)
 
 
+@pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 2), (3, 3), (3, 4)])
+def test_oracle_outflow_face_penalty_equals_the_reference(dim, degree, record):
+    """effective_beta_face = 1 / h^(p+1), h after Lethe from the cell measure (operator_ns.cc:428-457) against
+    set_outflow_faces of the oracle"""
+    if rq.load() is not None:
+        assert np.array_equal(rq.face_beta(dim=dim, degree=degree, measure=record["beta_measure"]),
+                              record[f"beta_{dim}_{degree}"])
+    n_cells = len(record["beta_measure"])
+    shape = (n_cells,) + (1,) * (dim - 1)
+    m = gm.structured_mesh(dim, shape, degree)
+    o = go.OracleOperator(dim=dim, degree=degree, cell_dofs=m.cell_dofs, n_dofs=m.n_dofs, cell_points=m.cell_points,
+                          mapping_degree=1, constraints={}, nu=0.01, c1=4.0, c2=2.0, theta=1.0, order=1,
+                          consider_time_derivative=True, increment_form=True, cell_wise_stabilization=True, path="sumfac")
+    o.measure = record["beta_measure"].copy()
+    o.set_outflow_faces(np.arange(n_cells), np.full(n_cells, 2), np.ones(n_cells, dtype=np.int64))
+    assert np.abs(o.faces["beta"] / record[f"beta_{dim}_{degree}"] - 1.0).max() < 4e-15
+
+
 # ---- the PRODUCT's CUDA source against the reference record, on the host ------------------------------------------
 def _product_lib():
     import ctypes as C
