@@ -27,6 +27,8 @@ def load():
         P, D, I = C.c_void_p, C.c_double, C.c_int
         lib.refq_apply.restype = I
         lib.refq_apply.argtypes = [I, I, I, I, I, D, D, D, I] + [P] * 12
+        lib.refq_apply_f32.restype = I
+        lib.refq_apply_f32.argtypes = [I, I, I, I, I, D, D, D, I] + [P] * 12
         lib.refq_boundary.restype = I
         lib.refq_boundary.argtypes = [I, I, I, D, D, I] + [P] * 8 + [I]
         lib.refq_face_beta.restype = I
@@ -42,7 +44,7 @@ def _p(a):
 
 
 def apply(*, dim, residual, increment_form, ctd, cell_wise, theta, nu, weight, value, grad, u_star, u_star_grad,
-          p_star_grad, u_tdo=None, u_old_grad=None, p_old_grad=None, d1, d2):
+          p_star_grad, u_tdo=None, u_old_grad=None, p_old_grad=None, d1, d2, number="double"):
     """One cell.  Point-major arrays: value[q, C], grad[q, C, dim] (what get_value / get_gradient return),
     u_star[q, dim], u_star_grad[q, dim, dim], p_star_grad[q, dim], u_tdo[q, dim] or None (no
     u_time_derivative_old table), u_old_grad[q, dim, dim] / p_old_grad[q, dim] or None, d1 / d2: [1] (cell-wise)
@@ -55,9 +57,10 @@ def apply(*, dim, residual, increment_form, ctd, cell_wise, theta, nu, weight, v
     u_tdo, u_old_grad, p_old_grad, d1, d2 = f(u_tdo), f(u_old_grad), f(p_old_grad), f(d1), f(d2)
     n_q = value.shape[0]
     vo, go_ = np.empty_like(value), np.empty_like(grad)
-    rc = lib.refq_apply(dim, int(residual), int(increment_form), int(ctd), int(cell_wise), float(theta), float(nu),
-                        float(weight), n_q, _p(value), _p(grad), _p(u_star), _p(u_star_grad), _p(p_star_grad),
-                        _p(u_tdo), _p(u_old_grad), _p(p_old_grad), _p(d1), _p(d2), _p(vo), _p(go_))
+    fn = lib.refq_apply if number == "double" else lib.refq_apply_f32   # float: Number = MGNumber (config.h:7)
+    rc = fn(dim, int(residual), int(increment_form), int(ctd), int(cell_wise), float(theta), float(nu),
+            float(weight), n_q, _p(value), _p(grad), _p(u_star), _p(u_star_grad), _p(p_star_grad),
+            _p(u_tdo), _p(u_old_grad), _p(p_old_grad), _p(d1), _p(d2), _p(vo), _p(go_))
     if rc != 0:
         raise RuntimeError("refq_apply failed")
     return vo, go_

@@ -277,7 +277,7 @@ refq_penalty(int dim, double dt, double nu, double c1, double c2, int degree, in
   return 0;
 }
 
-template <int dim>
+template <int dim, typename Number = double>
 static void
 run(const bool residual, const bool increment_form, const bool ctd, const bool cell_wise, const double theta,
     const double nu, const double weight, const int n_q, const double *value, const double *grad,
@@ -288,9 +288,9 @@ run(const bool residual, const bool increment_form, const bool ctd, const bool c
   constexpr int      C = dim + 1;
   TimeIntegratorData ti;
   ti.weight = weight;
-  NavierStokesOperator<dim, double> op(ti, theta, nu, ctd, increment_form, cell_wise);
-  op.delta_1.assign(1, VectorizedArray<double>(d1[0]));
-  op.delta_2.assign(1, VectorizedArray<double>(d2[0]));
+  NavierStokesOperator<dim, Number> op(ti, Number(theta), Number(nu), ctd, increment_form, cell_wise);
+  op.delta_1.assign(1, VectorizedArray<Number>(Number(d1[0])));
+  op.delta_2.assign(1, VectorizedArray<Number>(Number(d2[0])));
   op.delta_1_q.reinit(1, n_q);
   op.delta_2_q.reinit(1, n_q);
   op.u_star_value.reinit(1, n_q);
@@ -303,7 +303,7 @@ run(const bool residual, const bool increment_form, const bool ctd, const bool c
       op.u_old_gradient.reinit(1, n_q);
       op.p_old_gradient.reinit(1, n_q);
     }
-  typename NavierStokesOperator<dim, double>::FECellIntegrator phi;
+  typename NavierStokesOperator<dim, Number>::FECellIntegrator phi;
   phi.values_in.resize(n_q);
   phi.values_out.resize(n_q);
   phi.gradients_in.resize(n_q);
@@ -312,29 +312,29 @@ run(const bool residual, const bool increment_form, const bool ctd, const bool c
     {
       if (!cell_wise)
         {
-          op.delta_1_q[0][q] = d1[q];
-          op.delta_2_q[0][q] = d2[q];
+          op.delta_1_q[0][q] = Number(d1[q]);
+          op.delta_2_q[0][q] = Number(d2[q]);
         }
       for (int i = 0; i < dim; ++i)
         {
-          op.u_star_value[0][q][i]    = u_star[q * dim + i];
-          op.p_star_gradient[0][q][i] = p_star_grad[q * dim + i];
+          op.u_star_value[0][q][i]    = Number(u_star[q * dim + i]);
+          op.p_star_gradient[0][q][i] = Number(p_star_grad[q * dim + i]);
           if (u_tdo)
-            op.u_time_derivative_old[0][q][i] = u_tdo[q * dim + i];
+            op.u_time_derivative_old[0][q][i] = Number(u_tdo[q * dim + i]);
           if (u_old_grad)
-            op.p_old_gradient[0][q][i] = p_old_grad[q * dim + i];
+            op.p_old_gradient[0][q][i] = Number(p_old_grad[q * dim + i]);
           for (int j = 0; j < dim; ++j)
             {
-              op.u_star_gradient[0][q][i][j] = u_star_grad[(q * dim + i) * dim + j];
+              op.u_star_gradient[0][q][i][j] = Number(u_star_grad[(q * dim + i) * dim + j]);
               if (u_old_grad)
-                op.u_old_gradient[0][q][i][j] = u_old_grad[(q * dim + i) * dim + j];
+                op.u_old_gradient[0][q][i][j] = Number(u_old_grad[(q * dim + i) * dim + j]);
             }
         }
       for (int c = 0; c < C; ++c)
         {
-          phi.values_in[q][c] = value[q * C + c];
+          phi.values_in[q][c] = Number(value[q * C + c]);
           for (int j = 0; j < dim; ++j)
-            phi.gradients_in[q][c][j] = grad[(q * C + c) * dim + j];
+            phi.gradients_in[q][c][j] = Number(grad[(q * C + c) * dim + j]);
         }
     }
   if (residual)
@@ -362,6 +362,25 @@ refq_apply(int dim, int residual, int increment_form, int ctd, int cell_wise, do
   else if (dim == 3)
     run<3>(residual, increment_form, ctd, cell_wise, theta, nu, weight, n_q, value, grad, u_star, u_star_grad,
            p_star_grad, u_tdo, u_old_grad, p_old_grad, d1, d2, value_out, grad_out);
+  else
+    return 1;
+  return 0;
+}
+
+// the same with Number = float (the multigrid level operators, include/config.h:7): inputs are rounded to float,
+// the time-integration weight stays a double as in the reference (TimeIntegratorData returns the global Number)
+extern "C" int
+refq_apply_f32(int dim, int residual, int increment_form, int ctd, int cell_wise, double theta, double nu, double weight,
+               int n_q, const double *value, const double *grad, const double *u_star, const double *u_star_grad,
+               const double *p_star_grad, const double *u_tdo, const double *u_old_grad, const double *p_old_grad,
+               const double *d1, const double *d2, double *value_out, double *grad_out)
+{
+  if (dim == 2)
+    run<2, float>(residual, increment_form, ctd, cell_wise, theta, nu, weight, n_q, value, grad, u_star, u_star_grad,
+                  p_star_grad, u_tdo, u_old_grad, p_old_grad, d1, d2, value_out, grad_out);
+  else if (dim == 3)
+    run<3, float>(residual, increment_form, ctd, cell_wise, theta, nu, weight, n_q, value, grad, u_star, u_star_grad,
+                  p_star_grad, u_tdo, u_old_grad, p_old_grad, d1, d2, value_out, grad_out);
   else
     return 1;
   return 0;

@@ -42,7 +42,7 @@ def inputs(case_no, dim, n_q):
                 d1=rng.uniform(0.05, 1.0, n_q), d2=rng.uniform(0.05, 1.0, n_q))
 
 
-def run_case(case_no, case):
+def run_case(case_no, case, number="double"):
     dim, res, inc, ctd, cw, th, old = case
     n_q = 3 ** dim
     a = inputs(case_no, dim, n_q)
@@ -51,7 +51,7 @@ def run_case(case_no, case):
                        u_star_grad=a["u_star_grad"], p_star_grad=a["p_star_grad"], u_tdo=a["u_tdo"] if old else None,
                        u_old_grad=a["u_old_grad"] if th != 1.0 else None,
                        p_old_grad=a["p_old_grad"] if th != 1.0 else None,
-                       d1=a["d1"][:1] if cw else a["d1"], d2=a["d2"][:1] if cw else a["d2"])
+                       d1=a["d1"][:1] if cw else a["d1"], d2=a["d2"][:1] if cw else a["d2"], number=number)
 
 
 def boundary_inputs(no, dim):
@@ -83,6 +83,8 @@ if __name__ == "__main__":
     for i, case in enumerate(CASES):
         _, (v, g) = run_case(i, case)
         out[f"value_out_{i}"], out[f"grad_out_{i}"] = v, g
+        _, (v, g) = run_case(i, case, number="float")     # Number = float (the multigrid level operators)
+        out[f"value_out_f32_{i}"], out[f"grad_out_f32_{i}"] = v, g
     out["boundary_cases"] = np.array(BOUNDARY, dtype=np.float64)
     for i, case in enumerate(BOUNDARY):
         _, (v, g) = run_boundary(i, case)

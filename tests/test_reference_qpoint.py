@@ -85,6 +85,38 @@ def test_oracle_qpoint_physics_equals_the_reference(i, record):
     assert np.abs(got_v - ref_v).max() <= 4e-15 * scale and np.abs(got_g - ref_g).max() <= 4e-15 * scale, gen.CASES[i]
 
 
+@pytest.mark.parametrize("i", range(len(gen.CASES)))
+def test_oracle_qpoint_physics_in_float_equals_the_reference(i, record):
+    """Number = float, the multigrid level operators (config.h:7): the oracle's float32 path against the float
+    instantiation of the reference's kernel, to float round-off"""
+    dim, res, inc, ctd, cw, th, old = gen.CASES[i]
+    dim, res, inc, ctd, cw, old = int(dim), bool(res), bool(inc), bool(ctd), bool(cw), bool(old)
+    if rq.load() is not None:
+        _, (v, g) = gen.run_case(i, gen.CASES[i], number="float")
+        assert np.array_equal(v, record[f"value_out_f32_{i}"]) and np.array_equal(g, record[f"grad_out_f32_{i}"])
+    a = gen.inputs(i, dim, 3 ** dim)
+    o = _oracle(dim, 2, nu=0.037, c1=4.0, c2=2.0, theta=th, order=2 if (old or ctd) else 0,
+                consider_time_derivative=ctd, increment_form=inc, cell_wise_stabilization=cw, dtype=np.float32)
+    t = lambda x: np.ascontiguousarray(np.moveaxis(x, 0, -1))[None].astype(np.float32)  # noqa: E731
+    o.U, o.H, o.P = t(a["u_star"]), t(a["u_star_grad"]), t(a["p_star_grad"])
+    o.o = t(a["u_tdo"]) if old else None
+    o.Gold, o.gold_p = (t(a["u_old_grad"]), t(a["p_old_grad"])) if th != 1.0 else (None, None)
+    o.delta1_cell, o.delta2_cell = a["d1"][:1].astype(np.float32), a["d2"][:1].astype(np.float32)
+    o.delta1_q, o.delta2_q = a["d1"][None].astype(np.float32), a["d2"][None].astype(np.float32)
+    val, grad = t(a["value"]), t(a["grad"])
+    if res or not inc:
+        vo, go_ = o._cell_fixed_point(val, grad, 7.25, res)
+    else:
+        vo, go_ = o._cell_newton(val, grad, 7.25)
+    assert vo.dtype == np.float32 and go_.dtype == np.float32
+    ref_v, ref_g = record[f"value_out_f32_{i}"], record[f"grad_out_f32_{i}"]
+    scale = max(np.abs(ref_v).max(), np.abs(ref_g).max())
+    assert np.abs(np.moveaxis(vo[0], -1, 0) - ref_v).max() <= 2e-6 * scale
+    assert np.abs(np.moveaxis(go_[0], -1, 0) - ref_g).max() <= 2e-6 * scale
+    # and the float result is the double result to float accuracy (nothing else changed)
+    assert np.abs(ref_v - record[f"value_out_{i}"]).max() <= 1e-5 * scale
+
+
 @pytest.mark.parametrize("i", range(len(gen.BOUNDARY)))
 def test_oracle_outflow_face_physics_equals_the_reference(i, record):
     """do_vmult_boundary (operator_ns.cc:1195-1301) at the face quadrature points: cut faces (v, beta min(0, U.n) u)
