@@ -13,7 +13,7 @@ namespace glsb
 {
 #include "qpoint_product_extract.inc"
 
-  template <int dim, int BR>
+  template <int dim, int BR, typename T = double>
   static void
   run(const double theta, const double nu, const double weight, const int ctd, const int has_o, const int n_q,
       const double *value, const double *grad, const double *u_star, const double *u_star_grad,
@@ -21,39 +21,39 @@ namespace glsb
       const double *d1, const double *d2, const int cell_wise, double *value_out, double *grad_out)
   {
     constexpr int   C = dim + 1;
-    KParams<double> p{};
-    p.weight     = weight;
-    p.nu         = nu;
-    p.theta      = theta;
+    KParams<T> p{};
+    p.weight     = T(weight);
+    p.nu         = T(nu);
+    p.theta      = T(theta);
     p.ctd        = ctd;
     p.has_o      = has_o;
     p.theta_ne_1 = theta != 1.0;
     p.cell_wise  = cell_wise;
     for (int q = 0; q < n_q; ++q)
       {
-        QTables<dim, double> tb{};
-        tb.d1 = cell_wise ? d1[0] : d1[q];
-        tb.d2 = cell_wise ? d2[0] : d2[q];
+        QTables<dim, T> tb{};
+        tb.d1 = T(cell_wise ? d1[0] : d1[q]);
+        tb.d2 = T(cell_wise ? d2[0] : d2[q]);
         for (int i = 0; i < dim; ++i)
           {
-            tb.U[i]      = u_star[q * dim + i];
-            tb.P[i]      = p_star_grad[q * dim + i];
-            tb.O[i]      = (u_tdo && (BR == BR_NEWTON ? ctd : (BR == BR_RESIDUAL && has_o))) ? u_tdo[q * dim + i] : 0.0;
-            tb.gold_p[i] = (BR == BR_RESIDUAL && p.theta_ne_1) ? p_old_grad[q * dim + i] : 0.0;
+            tb.U[i]      = T(u_star[q * dim + i]);
+            tb.P[i]      = T(p_star_grad[q * dim + i]);
+            tb.O[i]      = (u_tdo && (BR == BR_NEWTON ? ctd : (BR == BR_RESIDUAL && has_o))) ? T(u_tdo[q * dim + i]) : T(0);
+            tb.gold_p[i] = (BR == BR_RESIDUAL && p.theta_ne_1) ? T(p_old_grad[q * dim + i]) : T(0);
             for (int j = 0; j < dim; ++j)
               {
-                tb.H[i][j]    = u_star_grad[(q * dim + i) * dim + j];
-                tb.Gold[i][j] = (BR == BR_RESIDUAL && p.theta_ne_1) ? u_old_grad[(q * dim + i) * dim + j] : 0.0;
+                tb.H[i][j]    = T(u_star_grad[(q * dim + i) * dim + j]);
+                tb.Gold[i][j] = (BR == BR_RESIDUAL && p.theta_ne_1) ? T(u_old_grad[(q * dim + i) * dim + j]) : T(0);
               }
           }
-        double val[C], g[C][dim], vout[C], gout[C][dim];
+        T val[C], g[C][dim], vout[C], gout[C][dim];
         for (int c = 0; c < C; ++c)
           {
-            val[c] = value[q * C + c];
+            val[c] = T(value[q * C + c]);
             for (int j = 0; j < dim; ++j)
-              g[c][j] = grad[(q * C + c) * dim + j];
+              g[c][j] = T(grad[(q * C + c) * dim + j]);
           }
-        qpoint_physics<dim, double, BR>(p, tb, val, g, vout, gout);
+        qpoint_physics<dim, T, BR>(p, tb, val, g, vout, gout);
         for (int c = 0; c < C; ++c)
           {
             value_out[q * C + c] = vout[c];
@@ -66,8 +66,9 @@ namespace glsb
 
 // branch: 0 Newton, 1 fixed point, 2 residual (glsb::Branch).  The table entries are filled the way load_tables
 // fills them for that branch (entries the kernel does not load are zero).
+// is_float != 0: T = float (the level operators)
 extern "C" int
-prod_qpoint(int dim, int branch, double theta, double nu, double weight, int ctd, int has_o, int n_q,
+prod_qpoint(int is_float, int dim, int branch, double theta, double nu, double weight, int ctd, int has_o, int n_q,
             const double *value, const double *grad, const double *u_star, const double *u_star_grad,
             const double *p_star_grad, const double *u_tdo, const double *u_old_grad, const double *p_old_grad,
             const double *d1, const double *d2, int cell_wise, double *value_out, double *grad_out)
@@ -75,8 +76,12 @@ prod_qpoint(int dim, int branch, double theta, double nu, double weight, int ctd
 #define GO(D, B)                                                                                                   \
   if (dim == D && branch == B)                                                                                     \
     {                                                                                                              \
-      glsb::run<D, B>(theta, nu, weight, ctd, has_o, n_q, value, grad, u_star, u_star_grad, p_star_grad, u_tdo,    \
-                      u_old_grad, p_old_grad, d1, d2, cell_wise, value_out, grad_out);                             \
+      if (is_float)                                                                                                \
+        glsb::run<D, B, float>(theta, nu, weight, ctd, has_o, n_q, value, grad, u_star, u_star_grad, p_star_grad,  \
+                               u_tdo, u_old_grad, p_old_grad, d1, d2, cell_wise, value_out, grad_out);             \
+      else                                                                                                         \
+        glsb::run<D, B>(theta, nu, weight, ctd, has_o, n_q, value, grad, u_star, u_star_grad, p_star_grad, u_tdo,  \
+                        u_old_grad, p_old_grad, d1, d2, cell_wise, value_out, grad_out);                           \
       return 0;                                                                                                    \
     }
   GO(2, 0) GO(2, 1) GO(2, 2) GO(3, 0) GO(3, 1) GO(3, 2)

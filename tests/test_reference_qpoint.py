@@ -191,12 +191,13 @@ def _product_lib():
     lib = C.CDLL(path)
     P, D, I = C.c_void_p, C.c_double, C.c_int
     lib.prod_qpoint.restype = I
-    lib.prod_qpoint.argtypes = [I, I, D, D, D, I, I, I] + [P] * 10 + [I, P, P]
+    lib.prod_qpoint.argtypes = [I, I, I, D, D, D, I, I, I] + [P] * 10 + [I, P, P]
     return lib
 
 
+@pytest.mark.parametrize("number", ["double", "float"])
 @pytest.mark.parametrize("i", range(len(gen.CASES)))
-def test_cuda_source_qpoint_physics_equals_the_reference(i, record):
+def test_cuda_source_qpoint_physics_equals_the_reference(i, number, record):
     """qpoint_physics of dealii_ns_gls_b200/csrc/glsb_kernels.cuh (what the generic, column, diagonal and residual
     kernels run per quadrature point), compiled for the host by tests/cpp/build_qpoint_host.sh, on the inputs of the
     reference record: the CUDA source against the reference's own do_vmult_cell, no GPU and no oracle in between"""
@@ -210,9 +211,10 @@ def test_cuda_source_qpoint_physics_equals_the_reference(i, record):
                               "p_old_grad", "d1", "d2")]
     vo, go_ = np.zeros_like(arrs[0]), np.zeros_like(arrs[1])
     ptr = lambda x: x.ctypes.data_as(__import__("ctypes").c_void_p)  # noqa: E731
-    rc = lib.prod_qpoint(dim, branch, float(th), 0.037, 7.25, ctd, old, 3 ** dim, *[ptr(x) for x in arrs], cw,
-                         ptr(vo), ptr(go_))
+    rc = lib.prod_qpoint(int(number == "float"), dim, branch, float(th), 0.037, 7.25, ctd, old, 3 ** dim,
+                         *[ptr(x) for x in arrs], cw, ptr(vo), ptr(go_))
     assert rc == 0
-    ref_v, ref_g = record[f"value_out_{i}"], record[f"grad_out_{i}"]
+    sfx, tol = ("", 4e-15) if number == "double" else ("_f32", 2e-6)   # float: the reference's float instantiation
+    ref_v, ref_g = record[f"value_out{sfx}_{i}"], record[f"grad_out{sfx}_{i}"]
     scale = max(np.abs(ref_v).max(), np.abs(ref_g).max())
-    assert np.abs(vo - ref_v).max() <= 4e-15 * scale and np.abs(go_ - ref_g).max() <= 4e-15 * scale, gen.CASES[i]
+    assert np.abs(vo - ref_v).max() <= tol * scale and np.abs(go_ - ref_g).max() <= tol * scale, gen.CASES[i]
