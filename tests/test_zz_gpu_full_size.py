@@ -13,7 +13,11 @@ TOL = {"double": 1e-12, "float": 2e-5}
 
 
 def _run(n, degree, number, ctd, cell_wise, period=4):
+    import gc
+
     import torch
+    gc.collect()
+    torch.cuda.empty_cache()      # the 160^3 case wants ~30 GB next to whatever earlier tests left in torch's cache
     tdt = torch.float64 if number == "double" else torch.float32
     big = gm.hypercube(3, n, degree)
     chk = PeriodicFullSizeCheck(big, "cuda", period_cells=period)
